@@ -1,0 +1,786 @@
+// engine.cu -- host side of the engine and the C ABI of include/wavernn_b200.h.
+// Owns device memory, streams and launches; no torch, no CPU arithmetic on the data path (the only host
+// math is one-off weight preparation at wrnn_finalize and O(folds) index planning).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/wavernn_b200.h"
+#include "engine_internal.h"
+
+using namespace wrnn;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+constexpr int kResBlocks = 10;
+constexpr int kCondLayers = 2 + 2 * kResBlocks;   // conv_in, 20 1x1, conv_out
+
+}  // namespace
+
+struct wrnn_engine {
+    int device = 0, bits = 9, mode = 0, C = 512, Cpad = 512, CR = 4;
+    std::string err;
+    std::map<std::string, HostTensor> tensors;
+    int64_t step = 0;
+    bool finalized = false;
+    double sparsity = 0.0;
+    int64_t launches = 0;
+    cudaStream_t stream = nullptr;
+    size_t smem_limit = 0;
+    // weights on device
+    DevBuf wLoop;    // all loop weights, one allocation
+    float *dWhh1 = nullptr, *dWih2a = nullptr, *dWhh2 = nullptr, *dWfc1a = nullptr, *dWfc2a = nullptr, *dWfc3 = nullptr;
+    float *dv1 = nullptr, *dwI0 = nullptr, *dbhn1 = nullptr, *dbhn2 = nullptr, *dbfc3 = nullptr, *dcoef = nullptr;
+    DevBuf wCond;    // conditioning weights
+    float* dCW[kCondLayers] = {};
+    float* dCB[kCondLayers] = {};
+    float *dMA1 = nullptr, *dbA1 = nullptr, *dMA2 = nullptr, *dbA2 = nullptr, *dMA3 = nullptr, *dbA3 = nullptr, *dMQ = nullptr;
+    std::vector<float> hcoef;
+    // grow-only work buffers
+    DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTA3, bTQ, bFolds, bExch, bSamples, bLogits, bForced;
+    DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
+    int* dAbort = nullptr;
+    int* hProgress = nullptr;   // mapped pinned
+    int* dProgress = nullptr;
+    int fade_overlap = -1;
+    cudaEvent_t ev[8] = {};
+};
+
+namespace {
+
+int fail(wrnn_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _err = (call);                                                                 \
+        if (_err != cudaSuccess)                                                                   \
+            return fail(e, WRNN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));   \
+    } while (0)
+
+const HostTensor* get(wrnn_engine* e, const char* name, std::initializer_list<int64_t> shape) {
+    auto it = e->tensors.find(name);
+    if (it == e->tensors.end()) { e->err = std::string("missing tensor '") + name + "'"; return nullptr; }
+    const HostTensor& t = it->second;
+    if (t.shape.size() != shape.size() || !std::equal(shape.begin(), shape.end(), t.shape.begin())) {
+        e->err = std::string("shape mismatch for '") + name + "'";
+        return nullptr;
+    }
+    return &t;
+}
+
+// numpy.linspace(start, stop, num) in float64 (the reference builds its fades with it, :385, :252)
+void np_linspace(double start, double stop, int num, std::vector<double>& out) {
+    out.resize(num);
+    if (num == 1) { out[0] = start; return; }
+    const double step = (stop - start) / (double)(num - 1);
+    for (int i = 0; i < num; ++i) {
+        volatile double prod = (double)i * step;   // no FMA contraction: numpy does mul then add
+        out[i] = prod + start;
+    }
+    out[num - 1] = stop;
+}
+
+// composite interpolation weights of the three Stretch2d+Conv2d layers (fatchord_version.py:66-75,82-84):
+// coef[phase][d] multiplies padded mel frame (n/200 + d) for output sample n with n%200 == phase.
+void build_coef(const float* w5a, const float* w5b, const float* w8, std::vector<float>& coef) {
+    const int L = 8, scales[3] = {5, 5, 8};
+    const float* ws[3] = {w5a, w5b, w8};
+    std::vector<double> x(L, 0.0);
+    x[3] = 1.0;
+    for (int s = 0; s < 3; ++s) {
+        const int sc = scales[s], n = (int)x.size() * sc, k = 2 * sc + 1;
+        std::vector<double> st(n), y(n, 0.0);
+        for (int i = 0; i < n; ++i) st[i] = x[i / sc];
+        for (int i = 0; i < n; ++i) {
+            double a = 0.0;
+            for (int j = 0; j < k; ++j) {
+                const int q = i + j - sc;
+                if (q >= 0 && q < n) a += (double)ws[s][j] * st[q];
+            }
+            y[i] = a;
+        }
+        x.swap(y);
+    }
+    coef.assign(kHop * kTaps, 0.f);
+    for (int ph = 0; ph < kHop; ++ph)
+        for (int d = 0; d < kTaps; ++d) coef[ph * kTaps + d] = (float)x[1000 - 200 * d + ph];
+}
+
+int python_floordiv(int64_t a, int64_t b) { int64_t q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return (int)q; }
+
+}  // namespace
+
+extern "C" {
+
+int wrnn_fold_plan(int64_t total_len, int64_t target, int64_t overlap, int64_t* num_folds, int64_t* padded_len) {
+    if (target + overlap <= 0 || target < 0 || overlap < 0) return WRNN_ERR_INVALID;
+    int64_t nf = python_floordiv(total_len - overlap, target + overlap);
+    const int64_t extended = nf * (overlap + target) + overlap;
+    const int64_t remaining = total_len - extended;
+    int64_t padded = total_len;
+    if (remaining != 0) {
+        nf += 1;
+        padded = total_len + target + 2 * overlap - remaining;
+    }
+    if (num_folds) *num_folds = nf;
+    if (padded_len) *padded_len = padded;
+    return WRNN_OK;
+}
+
+int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
+    if (!out) return WRNN_ERR_INVALID;
+    *out = nullptr;
+    if (mode != WRNN_MODE_RAW && mode != WRNN_MODE_MOL) return WRNN_ERR_INVALID;
+    if (mode == WRNN_MODE_RAW && (bits < 8 || bits > 10)) return WRNN_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return WRNN_ERR_CUDA;
+    wrnn_engine* e = new wrnn_engine();
+    e->device = device;
+    e->bits = bits;
+    e->mode = mode;
+    e->C = (mode == WRNN_MODE_RAW) ? (1 << bits) : 30;
+    e->Cpad = (e->C + 1) & ~1;
+    e->CR = (e->C + kCtasF32 - 1) / kCtasF32;
+    cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    int smem = 0;
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    e->smem_limit = (size_t)smem;
+    if (err == cudaSuccess) err = cudaMalloc(&e->dAbort, sizeof(int));
+    if (err == cudaSuccess) err = cudaHostAlloc(&e->hProgress, sizeof(int), cudaHostAllocMapped);
+    if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->dProgress, e->hProgress, 0);
+    for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
+    if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
+    *out = e;
+    return WRNN_OK;
+}
+
+int wrnn_destroy(wrnn_engine* e) {
+    if (!e) return WRNN_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
+                      &e->bTA1, &e->bTA2, &e->bTA3, &e->bTQ, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor};
+    for (DevBuf* b : bufs) b->release();
+    if (e->dAbort) cudaFree(e->dAbort);
+    if (e->hProgress) cudaFreeHost(e->hProgress);
+    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return WRNN_OK;
+}
+
+const char* wrnn_last_error(const wrnn_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int wrnn_set_tensor(wrnn_engine* e, const char* name, const float* data, const int64_t* shape, int ndim) {
+    if (!e || !name || !data || ndim < 0 || ndim > 4) return fail(e, WRNN_ERR_INVALID, "wrnn_set_tensor: bad argument");
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+    t.data.assign(data, data + n);
+    e->tensors[name] = std::move(t);
+    e->finalized = false;
+    return WRNN_OK;
+}
+int wrnn_set_step(wrnn_engine* e, int64_t step) { if (!e) return WRNN_ERR_INVALID; e->step = step; return WRNN_OK; }
+int64_t wrnn_get_step(const wrnn_engine* e) { return e ? e->step : -1; }
+double wrnn_sparsity(const wrnn_engine* e) { return e ? e->sparsity : 0.0; }
+int64_t wrnn_launch_count(const wrnn_engine* e) { return e ? e->launches : 0; }
+
+int wrnn_finalize(wrnn_engine* e) {
+    if (!e) return WRNN_ERR_INVALID;
+    CU(cudaSetDevice(e->device));
+    const int H = kRnn, C = e->C;
+#define GET(var, name, ...)                                   \
+    const HostTensor* var = get(e, name, {__VA_ARGS__});      \
+    if (!var) return WRNN_ERR_SHAPE;
+    GET(tI, "I.weight", H, 112)
+    GET(tIb, "I.bias", H)
+    GET(r1ih, "rnn1.weight_ih_l0", 3 * H, H)
+    GET(r1hh, "rnn1.weight_hh_l0", 3 * H, H)
+    GET(r1bi, "rnn1.bias_ih_l0", 3 * H)
+    GET(r1bh, "rnn1.bias_hh_l0", 3 * H)
+    GET(r2ih, "rnn2.weight_ih_l0", 3 * H, H + kAux)
+    GET(r2hh, "rnn2.weight_hh_l0", 3 * H, H)
+    GET(r2bi, "rnn2.bias_ih_l0", 3 * H)
+    GET(r2bh, "rnn2.bias_hh_l0", 3 * H)
+    GET(f1w, "fc1.weight", H, H + kAux)
+    GET(f1b, "fc1.bias", H)
+    GET(f2w, "fc2.weight", H, H + kAux)
+    GET(f2b, "fc2.bias", H)
+    GET(f3w, "fc3.weight", C, H)
+    GET(f3b, "fc3.bias", C)
+    GET(cin, "upsample.resnet.conv_in.weight", 128, kFeat, 5)
+    GET(cout, "upsample.resnet.conv_out.weight", 128, 128, 1)
+    GET(coutb, "upsample.resnet.conv_out.bias", 128)
+    GET(up1, "upsample.up_layers.1.weight", 1, 1, 1, 11)
+    GET(up3, "upsample.up_layers.3.weight", 1, 1, 1, 11)
+    GET(up5, "upsample.up_layers.5.weight", 1, 1, 1, 17)
+
+    // ---- loop weights ------------------------------------------------------------------------------------
+    const size_t nLoop = (size_t)3 * (3 * H) * H + (size_t)2 * H * H + (size_t)C * H + 3 * H + 3 * H + 1024 + kHop * kTaps + 64;
+    std::vector<float> hl(nLoop, 0.f);
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 3) & ~(size_t)3; return o; };
+    const size_t oWhh1 = take((size_t)3 * H * H), oWih2a = take((size_t)3 * H * H), oWhh2 = take((size_t)3 * H * H);
+    const size_t oWfc1a = take((size_t)H * H), oWfc2a = take((size_t)H * H), oWfc3 = take((size_t)C * H);
+    const size_t ov1 = take(3 * H), owI0 = take(H), obhn1 = take(H), obhn2 = take(H), obfc3 = take(C), ocoef = take(kHop * kTaps);
+    std::copy(r1hh->data.begin(), r1hh->data.end(), hl.begin() + oWhh1);
+    std::copy(r2hh->data.begin(), r2hh->data.end(), hl.begin() + oWhh2);
+    for (int r = 0; r < 3 * H; ++r)
+        std::copy(r2ih->data.begin() + (size_t)r * (H + kAux), r2ih->data.begin() + (size_t)r * (H + kAux) + H,
+                  hl.begin() + oWih2a + (size_t)r * H);
+    for (int r = 0; r < H; ++r) {
+        std::copy(f1w->data.begin() + (size_t)r * (H + kAux), f1w->data.begin() + (size_t)r * (H + kAux) + H,
+                  hl.begin() + oWfc1a + (size_t)r * H);
+        std::copy(f2w->data.begin() + (size_t)r * (H + kAux), f2w->data.begin() + (size_t)r * (H + kAux) + H,
+                  hl.begin() + oWfc2a + (size_t)r * H);
+    }
+    std::copy(f3w->data.begin(), f3w->data.end(), hl.begin() + oWfc3);
+    std::copy(f3b->data.begin(), f3b->data.end(), hl.begin() + obfc3);
+    for (int j = 0; j < H; ++j) {
+        hl[owI0 + j] = tI->data[(size_t)j * 112];
+        hl[obhn1 + j] = r1bh->data[2 * H + j];
+        hl[obhn2 + j] = r2bh->data[2 * H + j];
+    }
+    for (int r = 0; r < 3 * H; ++r) {
+        double a = 0.0;
+        for (int k = 0; k < H; ++k) a += (double)r1ih->data[(size_t)r * H + k] * (double)tI->data[(size_t)k * 112];
+        hl[ov1 + r] = (float)a;
+    }
+    build_coef(up1->data.data(), up3->data.data(), up5->data.data(), e->hcoef);
+    std::copy(e->hcoef.begin(), e->hcoef.end(), hl.begin() + ocoef);
+
+    // sparsity of a pruned checkpoint (vocoder/pruner.py leaves zeros in 1x4 column groups)
+    {
+        size_t zero = 0, total = 0;
+        auto scan = [&](const std::vector<float>& w, int cols, int c0, int c1) {
+            const size_t rows = w.size() / cols;
+            for (size_t r = 0; r < rows; ++r)
+                for (int c = c0; c + 3 < c1; c += 4) {
+                    const float* q = &w[r * cols + c];
+                    ++total;
+                    if (q[0] == 0.f && q[1] == 0.f && q[2] == 0.f && q[3] == 0.f) ++zero;
+                }
+        };
+        scan(r1hh->data, H, 0, H); scan(r2ih->data, H + kAux, 0, H + kAux); scan(r2hh->data, H, 0, H);
+        scan(f1w->data, H + kAux, 0, H + kAux); scan(f2w->data, H + kAux, 0, H + kAux); scan(f3w->data, H, 0, H);
+        e->sparsity = total ? (double)zero / (double)total : 0.0;
+    }
+    CU(e->wLoop.ensure(hl.size() * sizeof(float)));
+    CU(cudaMemcpy(e->wLoop.p, hl.data(), hl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    float* base = e->wLoop.as<float>();
+    e->dWhh1 = base + oWhh1; e->dWih2a = base + oWih2a; e->dWhh2 = base + oWhh2;
+    e->dWfc1a = base + oWfc1a; e->dWfc2a = base + oWfc2a; e->dWfc3 = base + oWfc3;
+    e->dv1 = base + ov1; e->dwI0 = base + owI0; e->dbhn1 = base + obhn1; e->dbhn2 = base + obhn2;
+    e->dbfc3 = base + obfc3; e->dcoef = base + ocoef;
+
+    // ---- conditioning weights: BatchNorm folded (eval: (x-mean)*rsqrt(var+eps)*gamma+beta, eps=1e-5) ------
+    std::vector<float> hc;
+    std::vector<size_t> oW(kCondLayers), oB(kCondLayers);
+    auto push = [&](size_t n) { size_t o = hc.size(); hc.resize(o + ((n + 3) & ~(size_t)3), 0.f); return o; };
+    auto bn_fold = [&](const std::string& conv, const std::string& bn, int K, size_t& ow, size_t& ob) -> bool {
+        const HostTensor* w = nullptr;
+        auto it = e->tensors.find(conv + ".weight");
+        if (it == e->tensors.end() || (int64_t)it->second.data.size() != (int64_t)128 * K) { e->err = "missing/bad " + conv; return false; }
+        w = &it->second;
+        const char* parts[4] = {".weight", ".bias", ".running_mean", ".running_var"};
+        const HostTensor* q[4];
+        for (int i = 0; i < 4; ++i) {
+            auto jt = e->tensors.find(bn + parts[i]);
+            if (jt == e->tensors.end() || jt->second.data.size() != 128) { e->err = "missing/bad " + bn + parts[i]; return false; }
+            q[i] = &jt->second;
+        }
+        ow = push((size_t)128 * K);
+        ob = push(128);
+        for (int o = 0; o < 128; ++o) {
+            const double sc = (double)q[0]->data[o] / std::sqrt((double)q[3]->data[o] + 1e-5);
+            for (int k = 0; k < K; ++k) hc[ow + (size_t)o * K + k] = (float)((double)w->data[(size_t)o * K + k] * sc);
+            hc[ob + o] = (float)((double)q[1]->data[o] - (double)q[2]->data[o] * sc);
+        }
+        return true;
+    };
+    (void)cin;
+    if (!bn_fold("upsample.resnet.conv_in", "upsample.resnet.batch_norm", kFeat * 5, oW[0], oB[0])) return WRNN_ERR_SHAPE;
+    for (int i = 0; i < kResBlocks; ++i) {
+        const std::string p = "upsample.resnet.layers." + std::to_string(i);
+        if (!bn_fold(p + ".conv1", p + ".batch_norm1", 128, oW[1 + 2 * i], oB[1 + 2 * i])) return WRNN_ERR_SHAPE;
+        if (!bn_fold(p + ".conv2", p + ".batch_norm2", 128, oW[2 + 2 * i], oB[2 + 2 * i])) return WRNN_ERR_SHAPE;
+    }
+    oW[kCondLayers - 1] = push(128 * 128);
+    oB[kCondLayers - 1] = push(128);
+    std::copy(cout->data.begin(), cout->data.end(), hc.begin() + oW[kCondLayers - 1]);
+    std::copy(coutb->data.begin(), coutb->data.end(), hc.begin() + oB[kCondLayers - 1]);
+
+    // projection matrices (unit-major, 4 values per hidden unit j): see engine_internal.h LoopParams
+    const size_t oMA1 = push((size_t)4 * H * 128), obA1 = push(4 * H), oMA2 = push((size_t)4 * H * 128), obA2 = push(4 * H);
+    const size_t oMA3 = push((size_t)H * 128), obA3 = push(H), oMQ = push((size_t)4 * H * kFeat);
+    {
+        // P = W_ih1 (1536x512) @ I.weight (512x112) in float64, plus W_ih1 @ I.bias
+        std::vector<double> P((size_t)3 * H * 112, 0.0), Pb(3 * H, 0.0);
+        for (int r = 0; r < 3 * H; ++r) {
+            const float* wr = &r1ih->data[(size_t)r * H];
+            double* pr = &P[(size_t)r * 112];
+            double pb = 0.0;
+            for (int k = 0; k < H; ++k) {
+                const double w = wr[k];
+                const float* ik = &tI->data[(size_t)k * 112];
+                for (int c = 0; c < 112; ++c) pr[c] += w * (double)ik[c];
+                pb += w * (double)tIb->data[k];
+            }
+            Pb[r] = pb;
+        }
+        for (int j = 0; j < H; ++j) {
+            for (int g = 0; g < 4; ++g) {
+                const size_t rowA1 = oMA1 + (size_t)(j * 4 + g) * 128, rowQ = oMQ + (size_t)(j * 4 + g) * kFeat;
+                const size_t rowA2 = oMA2 + (size_t)(j * 4 + g) * 128;
+                if (g < 3) {
+                    const int r = g * H + j;
+                    for (int c = 0; c < kAux - 1; ++c) hc[rowA1 + c] = (float)P[(size_t)r * 112 + 81 + c];   // a1[:31], Q5
+                    for (int c = 0; c < kFeat; ++c) hc[rowQ + c] = (float)P[(size_t)r * 112 + 1 + c];
+                    hc[obA1 + j * 4 + g] = (float)(Pb[r] + (double)r1bi->data[r] + (g < 2 ? (double)r1bh->data[r] : 0.0));
+                    for (int c = 0; c < kAux; ++c) hc[rowA2 + kAux + c] = r2ih->data[(size_t)r * (H + kAux) + H + c];   // a2
+                    hc[obA2 + j * 4 + g] = r2bi->data[r] + (g < 2 ? r2bh->data[r] : 0.f);
+                } else {
+                    for (int c = 0; c < kAux - 1; ++c) hc[rowA1 + c] = tI->data[(size_t)j * 112 + 81 + c];
+                    for (int c = 0; c < kFeat; ++c) hc[rowQ + c] = tI->data[(size_t)j * 112 + 1 + c];
+                    hc[obA1 + j * 4 + g] = tIb->data[j];
+                    for (int c = 0; c < kAux; ++c) hc[rowA2 + 2 * kAux + c] = f1w->data[(size_t)j * (H + kAux) + H + c];  // a3
+                    hc[obA2 + j * 4 + g] = f1b->data[j];
+                }
+            }
+            for (int c = 0; c < kAux; ++c) hc[oMA3 + (size_t)j * 128 + 3 * kAux + c] = f2w->data[(size_t)j * (H + kAux) + H + c];  // a4
+            hc[obA3 + j] = f2b->data[j];
+        }
+    }
+    CU(e->wCond.ensure(hc.size() * sizeof(float)));
+    CU(cudaMemcpy(e->wCond.p, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    float* cb = e->wCond.as<float>();
+    for (int i = 0; i < kCondLayers; ++i) { e->dCW[i] = cb + oW[i]; e->dCB[i] = cb + oB[i]; }
+    e->dMA1 = cb + oMA1; e->dbA1 = cb + obA1; e->dMA2 = cb + oMA2; e->dbA2 = cb + obA2;
+    e->dMA3 = cb + oMA3; e->dbA3 = cb + obA3; e->dMQ = cb + oMQ;
+    e->finalized = true;
+    return WRNN_OK;
+#undef GET
+}
+
+}  // extern "C"
+
+namespace {
+
+// Runs the conditioning front end for the utterances described by `utts` (already on device in bUtt).
+int run_conditioning(wrnn_engine* e, int n_utts, int ta_rows, int tq_rows) {
+    CU(e->bX0.ensure((size_t)ta_rows * 400 * sizeof(float)));
+    CU(e->bMP.ensure((size_t)tq_rows * kFeat * sizeof(float)));
+    for (int i = 0; i < 3; ++i) CU(e->bH[i].ensure((size_t)ta_rows * 128 * sizeof(float)));
+    CU(e->bAux.ensure((size_t)ta_rows * 128 * sizeof(float)));
+    CU(e->bTA1.ensure((size_t)ta_rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTA2.ensure((size_t)ta_rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTA3.ensure((size_t)ta_rows * kRnn * sizeof(float)));
+    CU(e->bTQ.ensure((size_t)tq_rows * 4 * kRnn * sizeof(float)));
+    cudaStream_t st = e->stream;
+    const UttDesc* du = e->bUtt.as<UttDesc>();
+    CU(launch_im2col(e->bMel.as<float>(), du, n_utts, ta_rows, tq_rows, e->bX0.as<float>(), e->bMP.as<float>(), st));
+    float* h[3] = {e->bH[0].as<float>(), e->bH[1].as<float>(), e->bH[2].as<float>()};
+    CU(launch_gemm_f32(e->bX0.as<float>(), e->dCW[0], e->dCB[0], nullptr, h[0], ta_rows, 128, 400, 1, st));
+    int cur = 0;
+    for (int i = 0; i < kResBlocks; ++i) {
+        const int mid = (cur + 1) % 3, nxt = (cur + 2) % 3;
+        CU(launch_gemm_f32(h[cur], e->dCW[1 + 2 * i], e->dCB[1 + 2 * i], nullptr, h[mid], ta_rows, 128, 128, 1, st));
+        CU(launch_gemm_f32(h[mid], e->dCW[2 + 2 * i], e->dCB[2 + 2 * i], h[cur], h[nxt], ta_rows, 128, 128, 0, st));
+        cur = nxt;
+    }
+    CU(launch_gemm_f32(h[cur], e->dCW[kCondLayers - 1], e->dCB[kCondLayers - 1], nullptr, e->bAux.as<float>(), ta_rows, 128, 128, 0, st));
+    CU(launch_zero_rows(e->bAux.as<float>(), du, n_utts, st));
+    CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA1, e->dbA1, nullptr, e->bTA1.as<float>(), ta_rows, 4 * kRnn, 128, 0, st));
+    CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA2, e->dbA2, nullptr, e->bTA2.as<float>(), ta_rows, 4 * kRnn, 128, 0, st));
+    CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA3, e->dbA3, nullptr, e->bTA3.as<float>(), ta_rows, kRnn, 128, 0, st));
+    CU(launch_gemm_f32(e->bMP.as<float>(), e->dMQ, nullptr, nullptr, e->bTQ.as<float>(), tq_rows, 4 * kRnn, kFeat, 0, st));
+    e->launches += 3 + 2 * kResBlocks + 1 + 4;
+    return WRNN_OK;
+}
+
+int upload_utts(wrnn_engine* e, const float* const* mels, const int32_t* T, int n_utts, int mels_on_device,
+                std::vector<UttDesc>& utts, int& ta_rows, int& tq_rows) {
+    utts.resize(n_utts);
+    long long mel_off = 0;
+    ta_rows = 0;
+    tq_rows = 0;
+    for (int i = 0; i < n_utts; ++i) {
+        utts[i].mel_off = mel_off;
+        utts[i].T = T[i];
+        utts[i].ta_row0 = ta_rows;
+        utts[i].tq_row0 = tq_rows;
+        utts[i].pad_ = 0;
+        mel_off += (long long)kFeat * T[i];
+        ta_rows += T[i] + 1;
+        tq_rows += T[i] + 2 * kPad;
+    }
+    CU(e->bMel.ensure((size_t)mel_off * sizeof(float)));
+    CU(e->bUtt.ensure(utts.size() * sizeof(UttDesc)));
+    for (int i = 0; i < n_utts; ++i)
+        CU(cudaMemcpyAsync(e->bMel.as<float>() + utts[i].mel_off, mels[i], (size_t)kFeat * T[i] * sizeof(float),
+                           mels_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->bUtt.p, utts.data(), utts.size() * sizeof(UttDesc), cudaMemcpyHostToDevice, e->stream));
+    return WRNN_OK;
+}
+
+int ensure_fades(wrnn_engine* e, int overlap) {
+    if (e->fade_overlap == overlap) return WRNN_OK;
+    // fatchord_version.py:381-391
+    const int silence_len = overlap / 2, fade_len = overlap - silence_len;
+    std::vector<double> t, fin(overlap, 0.0), fout(overlap, 0.0);
+    if (fade_len > 0) np_linspace(-1.0, 1.0, fade_len, t);
+    for (int i = 0; i < fade_len; ++i) {
+        fin[silence_len + i] = std::sqrt(0.5 * (1.0 + t[i]));
+        fout[i] = std::sqrt(0.5 * (1.0 - t[i]));
+    }
+    CU(e->bFade.ensure((size_t)std::max(1, 2 * overlap) * sizeof(double)));
+    if (overlap > 0) {
+        CU(cudaMemcpyAsync(e->bFade.p, fin.data(), overlap * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(e->bFade.as<double>() + overlap, fout.data(), overlap * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));   // host vectors go out of scope
+    }
+    e->fade_overlap = overlap;
+    return WRNN_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
+    if (!e || !rq) return WRNN_ERR_INVALID;
+    if (!e->finalized) return fail(e, WRNN_ERR_NOT_LOADED, "Please load Wave-RNN in memory before using it");
+    if (rq->n_utts < 1 || !rq->mels || !rq->T) return fail(e, WRNN_ERR_INVALID, "wrnn_generate: no utterances");
+    if (rq->precision != WRNN_PREC_F32) return fail(e, WRNN_ERR_INVALID, "wrnn_generate: precision not available in this build");
+    CU(cudaSetDevice(e->device));
+    const int n_utts = rq->n_utts;
+    const bool partial = (rq->fold_begin != 0 || rq->fold_end != 0);
+    if ((partial || rq->forced || rq->samples || rq->logits) && n_utts != 1)
+        return fail(e, WRNN_ERR_INVALID, "fold ranges / forced / samples / logits need n_utts == 1");
+    const bool want_wav = rq->wav != nullptr && !partial && rq->max_steps == 0;
+    for (int i = 0; i < n_utts; ++i) {
+        if (rq->T[i] < 1) return fail(e, WRNN_ERR_INVALID, "empty mel");
+        if (want_wav && rq->T[i] <= 20)
+            return fail(e, WRNN_ERR_TOO_SHORT, "operands could not be broadcast together: mel has <= 20 frames "
+                                                "(fade-out needs 4000 samples, fatchord_version.py:253-255)");
+    }
+    const int target = rq->target, overlap = rq->overlap;
+    if (rq->batched) {
+        if (target < 0 || overlap < 0 || target + overlap <= 0) return fail(e, WRNN_ERR_INVALID, "bad target/overlap");
+        if (overlap == 0 && want_wav)
+            return fail(e, WRNN_ERR_INVALID, "overlap == 0: xfade_and_unfold raises ValueError (fatchord_version.py:394)");
+    }
+    const int mu_law = (e->mode == WRNN_MODE_RAW) ? rq->mu_law : 0;   // fatchord_version.py:156
+
+    cudaStream_t st = e->stream;
+    CU(cudaEventRecord(e->ev[0], st));
+    std::vector<UttDesc> utts;
+    int ta_rows = 0, tq_rows = 0;
+    int rc = upload_utts(e, rq->mels, rq->T, n_utts, rq->mels_on_device, utts, ta_rows, tq_rows);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev[1], st));
+    rc = run_conditioning(e, n_utts, ta_rows, tq_rows);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev[2], st));
+
+    // ---- fold plan (fatchord_version.py:315-340): integer arithmetic on the host, O(folds) -------------------
+    std::vector<FoldDesc> folds;
+    std::vector<PostUtt> putts(n_utts);
+    int S = 0;
+    long long wav_total = 0;
+    int max_wave_len = 0;
+    for (int i = 0; i < n_utts; ++i) {
+        const int N = utts[i].T * kHop;
+        int64_t F = 1, padded = N;
+        if (rq->batched) {
+            wrnn_fold_plan(N, target, overlap, &F, &padded);
+            if (F < 1) return fail(e, WRNN_ERR_INVALID, "utterance shorter than the fold overlap");
+            S = target + 2 * overlap;
+        } else {
+            S = std::max(S, N);
+        }
+        int f0 = 0, f1 = (int)F;
+        if (partial) { f0 = std::max(0, rq->fold_begin); f1 = std::min((int)F, rq->fold_end); }
+        putts[i].samp_off = (long long)folds.size();   // fold index for now; scaled by S below
+        putts[i].F = (int)F;
+        putts[i].wave_len = (utts[i].T - 1) * kHop;
+        putts[i].wav_off = wav_total;
+        wav_total += putts[i].wave_len;
+        max_wave_len = std::max(max_wave_len, putts[i].wave_len);
+        for (int f = f0; f < f1; ++f) {
+            FoldDesc d;
+            d.ta_row0 = utts[i].ta_row0; d.tq_row0 = utts[i].tq_row0; d.T = utts[i].T; d.N = N;
+            d.n0 = rq->batched ? f * (target + overlap) : 0;
+            d.utt = rq->utt_index0 + i; d.fold = f; d.pad_ = 0;
+            folds.push_back(d);
+        }
+    }
+    const int S_full = S;
+    if (rq->max_steps > 0) S = std::min(S, rq->max_steps);
+    const int Btot = (int)folds.size();
+    if (Btot < 1) return fail(e, WRNN_ERR_INVALID, "empty fold range");
+    for (int i = 0; i < n_utts; ++i) putts[i].samp_off *= S;
+    if (rq->wav_offsets) {
+        for (int i = 0; i < n_utts; ++i) rq->wav_offsets[i] = putts[i].wav_off;
+        rq->wav_offsets[n_utts] = wav_total;
+    }
+    if (want_wav && rq->wav_capacity < wav_total) return fail(e, WRNN_ERR_INVALID, "wav buffer too small");
+
+    CU(e->bFolds.ensure(folds.size() * sizeof(FoldDesc)));
+    CU(cudaMemcpyAsync(e->bFolds.p, folds.data(), folds.size() * sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
+    CU(e->bSamples.ensure((size_t)Btot * S * sizeof(float)));
+    if (rq->logits) CU(e->bLogits.ensure((size_t)Btot * S * e->C * sizeof(float)));
+    if (rq->forced) {
+        CU(e->bForced.ensure((size_t)Btot * S_full * sizeof(float)));
+        // forced is (F,S_full) on the host; the kernel indexes [b][S] with the launch S
+        if (S == S_full) {
+            CU(cudaMemcpyAsync(e->bForced.p, rq->forced, (size_t)Btot * S * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else {
+            CU(cudaMemcpy2DAsync(e->bForced.p, (size_t)S * sizeof(float), rq->forced, (size_t)S_full * sizeof(float),
+                                 (size_t)S * sizeof(float), Btot, cudaMemcpyHostToDevice, st));
+        }
+    }
+
+    // ---- the loop: waves of <= kMaxFoldsPerLaunch folds -----------------------------------------------------
+    rq->n_launches = 0;
+    const size_t words_per_fold = (size_t)6 * kRnn + e->Cpad + 2;
+    *e->hProgress = 0;
+    auto t_start = std::chrono::steady_clock::now();
+    for (int w0 = 0; w0 < Btot; w0 += kMaxFoldsPerLaunch) {
+        const int B = std::min(kMaxFoldsPerLaunch, Btot - w0);
+        const int FB = loop_f32_pick_fb(B, e->CR, e->smem_limit);
+        if (FB < 1) return fail(e, WRNN_ERR_INVALID, "shared memory budget exceeded");
+        CU(e->bExch.ensure(words_per_fold * B * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(e->bExch.p, 0, words_per_fold * B * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
+        LoopParams p;
+        memset(&p, 0, sizeof(p));
+        p.Whh1 = e->dWhh1; p.Wih2a = e->dWih2a; p.Whh2 = e->dWhh2; p.Wfc1a = e->dWfc1a; p.Wfc2a = e->dWfc2a; p.Wfc3 = e->dWfc3;
+        p.v1 = e->dv1; p.wI0 = e->dwI0; p.bhn1 = e->dbhn1; p.bhn2 = e->dbhn2; p.bfc3 = e->dbfc3;
+        p.TA1 = e->bTA1.as<float4>(); p.TA2 = e->bTA2.as<float4>(); p.TA3 = e->bTA3.as<float>(); p.TQ = e->bTQ.as<float4>();
+        p.coef = e->dcoef;
+        p.folds = e->bFolds.as<FoldDesc>() + w0;
+        p.B = B; p.S = S; p.C = e->C; p.Cpad = e->Cpad; p.CR = e->CR; p.FB = FB; p.mode = e->mode;
+        p.seed = rq->seed;
+        unsigned long long* x = e->bExch.as<unsigned long long>();
+        p.bX1 = x; x += (size_t)B * kRnn; p.bH1 = x; x += (size_t)B * kRnn; p.bX2 = x; x += (size_t)B * kRnn;
+        p.bH2 = x; x += (size_t)B * kRnn; p.bF1 = x; x += (size_t)B * kRnn; p.bF2 = x; x += (size_t)B * kRnn;
+        p.bLG = x; x += (size_t)B * e->Cpad; p.bX = x;
+        p.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+        p.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+        p.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+        p.progress = e->dProgress;
+        p.abort_flag = e->dAbort;
+        CU(launch_loop_f32(p, st));
+        CU(cudaEventRecord(e->ev[7], st));
+        e->launches += 1;
+        rq->n_launches += 1;
+        // progress_callback(i, seq_len, b_size, gen_rate) -- fatchord_version.py:234-236
+        if (rq->progress) {
+            int last = -1;
+            while (cudaEventQuery(e->ev[7]) == cudaErrorNotReady) {
+                const int i = *reinterpret_cast<volatile int*>(e->hProgress);
+                if (i != last) {
+                    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+                    rq->progress(i, S, B, (double)(i + 1) / std::max(dt, 1e-9) * B / 1000.0, rq->progress_user);
+                    last = i;
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(500));
+            }
+        }
+        int aborted = 0;
+        CU(cudaMemcpyAsync(&aborted, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (aborted) return fail(e, WRNN_ERR_TIMEOUT, "sample loop deadlock guard fired (an exchange word never arrived)");
+        if (rq->progress) {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+            rq->progress(S - 1, S, B, (double)S / std::max(dt, 1e-9) * B / 1000.0, rq->progress_user);
+        }
+    }
+    CU(cudaEventRecord(e->ev[3], st));
+
+    // ---- post chain + copies back -----------------------------------------------------------------------------
+    if (want_wav) {
+        rc = ensure_fades(e, rq->batched ? overlap : 0);
+        if (rc) return rc;
+        CU(e->bPostUtt.ensure(putts.size() * sizeof(PostUtt)));
+        CU(cudaMemcpyAsync(e->bPostUtt.p, putts.data(), putts.size() * sizeof(PostUtt), cudaMemcpyHostToDevice, st));
+        CU(e->bScratch.ensure((size_t)wav_total * sizeof(double)));
+        double* dwav = rq->wav;
+        if (!rq->wav_on_device) {
+            CU(e->bWav.ensure((size_t)wav_total * sizeof(double)));
+            dwav = e->bWav.as<double>();
+        }
+        const int ov = rq->batched ? overlap : 0;
+        CU(launch_post(e->bSamples.as<float>(), e->bPostUtt.as<PostUtt>(), n_utts, max_wave_len, S, rq->batched, target, ov,
+                       e->bFade.as<double>(), e->bFade.as<double>() + ov, mu_law, e->C, rq->apply_preemphasis,
+                       e->bScratch.as<double>(), dwav, st));
+        e->launches += 2;
+        CU(cudaEventRecord(e->ev[4], st));
+        if (!rq->wav_on_device)
+            CU(cudaMemcpyAsync(rq->wav, dwav, (size_t)wav_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+        CU(cudaEventRecord(e->ev[4], st));
+    }
+    if (rq->samples) CU(cudaMemcpyAsync(rq->samples, e->bSamples.p, (size_t)Btot * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rq->logits) CU(cudaMemcpyAsync(rq->logits, e->bLogits.p, (size_t)Btot * S * e->C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(e->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    rq->ms_h2d = elapsed(e->ev[0], e->ev[1]);
+    rq->ms_cond = elapsed(e->ev[1], e->ev[2]);
+    rq->ms_loop = elapsed(e->ev[2], e->ev[3]);
+    rq->ms_post = elapsed(e->ev[3], e->ev[4]);
+    rq->ms_d2h = elapsed(e->ev[4], e->ev[5]);
+    rq->n_folds = Btot;
+    rq->n_steps = S;
+    return WRNN_OK;
+}
+
+int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames, float* mels_up) {
+    if (!e || !mel || T < 1) return WRNN_ERR_INVALID;
+    if (!e->finalized) return fail(e, WRNN_ERR_NOT_LOADED, "Please load Wave-RNN in memory before using it");
+    CU(cudaSetDevice(e->device));
+    std::vector<UttDesc> utts;
+    int ta_rows = 0, tq_rows = 0;
+    const float* mels[1] = {mel};
+    int rc = upload_utts(e, mels, &T, 1, 0, utts, ta_rows, tq_rows);
+    if (rc) return rc;
+    rc = run_conditioning(e, 1, ta_rows, tq_rows);
+    if (rc) return rc;
+    if (aux_frames) CU(cudaMemcpyAsync(aux_frames, e->bAux.p, (size_t)T * 128 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (mels_up) {
+        // debug view of the interpolation table: mels_up[n][c] = sum_d coef[n%200][d] * melpad[c][n/200 + d]
+        for (int n = 0; n < T * kHop; ++n) {
+            const int q0 = n / kHop, ph = n % kHop;
+            for (int c = 0; c < kFeat; ++c) {
+                float a = 0.f;
+                for (int d = 0; d < kTaps; ++d) {
+                    const int t = q0 + d - kPad;
+                    if (t >= 0 && t < T) a = fmaf(e->hcoef[ph * kTaps + d], mel[(size_t)c * T + t], a);
+                }
+                mels_up[(size_t)n * kFeat + c] = a;
+            }
+        }
+    }
+    return WRNN_OK;
+}
+
+int wrnn_postprocess(wrnn_engine* e, const float* samples, int64_t num_folds, int64_t S, int32_t batched, int32_t overlap,
+                     int32_t T, int32_t mu_law, int32_t apply_preemphasis, double* wav) {
+    if (!e || !samples || !wav || num_folds < 1 || S < 1) return WRNN_ERR_INVALID;
+    if (T <= 20) return fail(e, WRNN_ERR_TOO_SHORT, "mel has <= 20 frames (fatchord_version.py:253-255)");
+    if (batched && overlap <= 0) return fail(e, WRNN_ERR_INVALID, "overlap == 0 (fatchord_version.py:394)");
+    CU(cudaSetDevice(e->device));
+    const int target = batched ? (int)S - 2 * overlap : 0;
+    PostUtt u;
+    u.samp_off = 0; u.wav_off = 0; u.F = (int)num_folds; u.wave_len = (T - 1) * kHop;
+    const int64_t total_len = batched ? num_folds * (target + overlap) + overlap : S;
+    if (u.wave_len > total_len) return fail(e, WRNN_ERR_INVALID, "samples shorter than (T-1)*hop");
+    int rc = ensure_fades(e, batched ? overlap : 0);
+    if (rc) return rc;
+    cudaStream_t st = e->stream;
+    CU(e->bSamples.ensure((size_t)num_folds * S * sizeof(float)));
+    CU(cudaMemcpyAsync(e->bSamples.p, samples, (size_t)num_folds * S * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(e->bPostUtt.ensure(sizeof(PostUtt)));
+    CU(cudaMemcpyAsync(e->bPostUtt.p, &u, sizeof(PostUtt), cudaMemcpyHostToDevice, st));
+    CU(e->bScratch.ensure((size_t)u.wave_len * sizeof(double)));
+    CU(e->bWav.ensure((size_t)u.wave_len * sizeof(double)));
+    const int ov = batched ? overlap : 0;
+    CU(launch_post(e->bSamples.as<float>(), e->bPostUtt.as<PostUtt>(), 1, u.wave_len, (int)S, batched, target, ov,
+                   e->bFade.as<double>(), e->bFade.as<double>() + ov, (e->mode == WRNN_MODE_RAW) ? mu_law : 0, e->C,
+                   apply_preemphasis, e->bScratch.as<double>(), e->bWav.as<double>(), st));
+    e->launches += 2;
+    CU(cudaMemcpyAsync(wav, e->bWav.p, (size_t)u.wave_len * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return WRNN_OK;
+}
+
+int wrnn_xfade_unfold(wrnn_engine* e, const double* y, int64_t num_folds, int64_t S, int32_t overlap, double* out) {
+    if (!e || !y || !out || num_folds < 1 || S < 1) return WRNN_ERR_INVALID;
+    if (overlap <= 0 || 2 * (int64_t)overlap > S)
+        return fail(e, WRNN_ERR_INVALID, "overlap must be in [1, S/2] (overlap == 0 raises ValueError at fatchord_version.py:394)");
+    CU(cudaSetDevice(e->device));
+    int rc = ensure_fades(e, overlap);
+    if (rc) return rc;
+    const long long total_len = num_folds * (S - overlap) + overlap;
+    cudaStream_t st = e->stream;
+    CU(e->bScratch.ensure((size_t)num_folds * S * sizeof(double)));
+    CU(e->bWav.ensure((size_t)total_len * sizeof(double)));
+    CU(cudaMemcpyAsync(e->bScratch.p, y, (size_t)num_folds * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(launch_xfade_unfold_f64(e->bScratch.as<double>(), (int)num_folds, (int)S, overlap, e->bFade.as<double>(),
+                               e->bFade.as<double>() + overlap, total_len, e->bWav.as<double>(), st));
+    e->launches += 1;
+    CU(cudaMemcpyAsync(out, e->bWav.p, (size_t)total_len * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return WRNN_OK;
+}
+
+int wrnn_barrier_floor(wrnn_engine* e, int32_t rounds, float* ll_us, float* counter_us) {
+    if (!e || rounds < 1) return WRNN_ERR_INVALID;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    CU(e->bFloor.ensure(4 * kRnn * sizeof(unsigned long long) + 64));
+    unsigned long long* buf = e->bFloor.as<unsigned long long>();
+    for (int variant = 0; variant < 2; ++variant) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            CU(cudaMemsetAsync(e->bFloor.p, 0, e->bFloor.cap, st));
+            CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
+            CU(cudaEventRecord(e->ev[0], st));
+            if (variant == 0) CU(launch_floor_ll(buf, rounds, e->dAbort, st));
+            else CU(launch_floor_counter(reinterpret_cast<unsigned int*>(buf + 3 * kRnn), reinterpret_cast<float*>(buf), rounds, e->dAbort, st));
+            CU(cudaEventRecord(e->ev[1], st));
+            int aborted = 0;
+            CU(cudaMemcpyAsync(&aborted, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            e->launches += 1;
+            if (aborted) return fail(e, WRNN_ERR_TIMEOUT, "exchange-floor kernel timed out");
+            best = std::min(best, elapsed(e->ev[0], e->ev[1]) * 1000.f / rounds);
+        }
+        if (variant == 0 && ll_us) *ll_us = best;
+        if (variant == 1 && counter_us) *counter_us = best;
+    }
+    return WRNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// engine_internal.h -- declarations shared by the engine's translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "common.cuh"
+
+namespace wrnn {
+
+constexpr int kUnitsF32 = 4;              // hidden units per CTA in the fp32 loop
+constexpr int kCtasF32 = kRnn / kUnitsF32;  // 128 CTAs, one per SM (148 available)
+constexpr int kMaxFoldsPerLaunch = 256;
+
+// Arguments of the persistent loop kernels.
+struct LoopParams {
+    // GEMV weights, row-major [rows][512] fp32 (device)
+    const float* Whh1;    // rnn1.weight_hh_l0            [1536][512]
+    const float* Wih2a;   // rnn2.weight_ih_l0[:, :512]   [1536][512]
+    const float* Whh2;    // rnn2.weight_hh_l0            [1536][512]
+    const float* Wfc1a;   // fc1.weight[:, :512]          [512][512]
+    const float* Wfc2a;   // fc2.weight[:, :512]          [512][512]
+    const float* Wfc3;    // fc3.weight                   [C][512]
+    const float* v1;      // rnn1.weight_ih_l0 @ I.weight[:, 0]   [1536]
+    const float* wI0;     // I.weight[:, 0]               [512]
+    const float* bhn1;    // rnn1.bias_hh_l0[1024:]       [512]
+    const float* bhn2;    // rnn2.bias_hh_l0[1024:]       [512]
+    const float* bfc3;    // fc3.bias                     [C]
+    // per-frame conditioning tables written by the front end (cond.cu)
+    const float4* TA1;    // [rows][512] {gi1_r, gi1_z, gi1_n, xI}    from aux a1 (+ biases)
+    const float4* TA2;    // [rows][512] {gi2_r, gi2_z, gi2_n, fc1}   from aux a2, a3 (+ biases)
+    const float* TA3;     // [rows][512] fc2                          from aux a4 (+ bias)
+    const float4* TQ;     // [rows][512] {gi1_r, gi1_z, gi1_n, xI}    from one padded mel frame
+    const float* coef;    // [200][kTaps] upsample interpolation weights (phase, padded-frame tap)
+    const FoldDesc* folds;
+    int B, S, C, Cpad, CR, FB, mode;
+    unsigned long long seed;
+    // exchange buffers, {value, tag} words
+    unsigned long long *bX1, *bH1, *bX2, *bH2, *bF1, *bF2;   // [B][512]
+    unsigned long long* bLG;                                  // [B][Cpad]
+    unsigned long long* bX;                                   // [B]
+    float* samples;          // [B][S] value fed back at each step
+    float* logits_out;       // optional [B][S][C]
+    const float* forced;     // optional [B][S]
+    int* progress;           // mapped host int, written every 100 steps
+    int* abort_flag;         // device int
+};
+
+size_t loop_f32_smem_bytes(int B, int FB, int CR);
+int loop_f32_pick_fb(int B, int CR, size_t smem_limit);
+cudaError_t launch_loop_f32(const LoopParams& p, cudaStream_t stream);
+
+// ---- conditioning front end (cond.cu) ---------------------------------------------------------------
+struct UttDesc {
+    long long mel_off;   // float offset of this utterance's (80,T) block in the device mel buffer
+    int T;
+    int ta_row0;         // first of T+1 rows in the aux-row space
+    int tq_row0;         // first of T+4 rows in the padded-frame space
+    int pad_;
+};
+// X0[ta_row][400] = im2col of the zero-padded mel for conv_in (k=5); MP[tq_row][80] = padded mel, time-major
+cudaError_t launch_im2col(const float* mel, const UttDesc* utts, int n_utts, int ta_rows, int tq_rows,
+                          float* X0, float* MP, cudaStream_t stream);
+// C[M][N] = act(A[M][K] W[N][K]^T + bias) (+ R)   ; fp32 ; K % 16 == 0 ; N % 64 == 0
+cudaError_t launch_gemm_f32(const float* A, const float* W, const float* bias, const float* R, float* C,
+                            int M, int N, int K, int relu, cudaStream_t stream);
+cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream);
+
+// ---- post chain (post.cu) ----------------------------------------------------------------------------
+struct PostUtt {
+    long long samp_off;   // float offset of this utterance's (F,S) block in the samples buffer
+    long long wav_off;    // double offset of its output in the wav buffer
+    int F;                // folds (1 when not batched)
+    int wave_len;         // (T-1)*200
+};
+cudaError_t launch_post(const float* samples, const PostUtt* utts, int n_utts, int max_wave_len, int S, int batched,
+                        int target, int overlap, const double* fade_in, const double* fade_out, int mu_law, int n_classes,
+                        int preemph, double* scratch, double* wav, cudaStream_t stream);
+
+cudaError_t launch_xfade_unfold_f64(const double* y, int F, int S, int overlap, const double* fade_in,
+                                    const double* fade_out, long long total_len, double* out, cudaStream_t stream);
+
+// ---- exchange-floor microbenchmark (bench_floor.cu) -----------------------------------------------------
+cudaError_t launch_floor_ll(unsigned long long* buf, int rounds, int* abort_flag, cudaStream_t stream);
+cudaError_t launch_floor_counter(unsigned int* counter, float* data, int rounds, int* abort_flag, cudaStream_t stream);
+
+}  // namespace wrnn

@@ -1,0 +1,507 @@
+// loop_f32.cu -- the autoregressive sample loop (reference: WaveRNN.generate body,
+// vocoder/models/fatchord_version.py:192-236) as ONE persistent cooperative kernel, fp32 parity mode.
+//
+// Design:
+//  * weight-stationary: the 128 CTAs (one per SM) each own 4 of the 512 hidden units of every layer;
+//    their rows of W_hh1, W_ih2[:, :512], W_hh2, fc1[:, :512], fc2[:, :512] and fc3 stay in shared
+//    memory (fp32, ~100 KB/SM) for the whole sequence -- weights are never re-read from HBM/L2.
+//  * the I layer, W_ih1 and every mel/aux column of the other layers are folded into per-frame
+//    conditioning tables by the front end (cond.cu), so a step has four dependent GEMV stages
+//    (W_ih2, fc1, fc2, fc3) plus two off-critical-path ones (W_hh1 h1, W_hh2 h2 for the next step).
+//  * activations travel between SMs as {value, step-tag} 8-byte words through L2 (common.cuh):
+//    consumers spin on the data itself; there is no grid barrier, fence or atomic on the path.
+//  * sampling (softmax + inverse CDF, or mixture-of-logistics) is fused; noise is Philox(step, fold,
+//    utterance) so the run can be replayed on the reference (oracle/philox.py).
+//  * every spin has a deadline; a miss raises a global abort flag and all CTAs leave (no GPU hang).
+#include "engine_internal.h"
+
+namespace wrnn {
+
+namespace {
+
+constexpr int NT = 512;         // threads per CTA
+constexpr int NW = NT / 32;     // warps
+constexpr int U = kUnitsF32;    // hidden units per CTA (4)
+constexpr int G = 3 * U;        // gate rows per CTA per GRU matrix (12)
+constexpr long long kSpinDeadline = 1500000000LL;  // ~0.8 s of SM clocks
+
+struct Smem {
+    float* Whh1;   // [G][512]   rows g*U+u
+    float* Wih2;   // [G][512]
+    float* Whh2;   // [G][512]
+    float* Wfc1;   // [U][512]
+    float* Wfc2;   // [U][512]
+    float* Wfc3;   // [CR][512]
+    float* act;    // [FB][512]  gathered activations of the current chunk
+    float* tmp;    // [FB][G]    GEMV results of the current chunk
+    float* h1;     // [B][U]
+    float* h2;     // [B][U]
+    float* x1;     // [B][U]
+    float* gh1;    // [B][G]     W_hh1 h1 for the next step
+    float* gh2;    // [B][G]
+    float* x;      // [B]        previous sample of every fold
+    float* v1;     // [3][U]     (W_ih1 W_I[:,0]) rows of my units
+    float* wI0;    // [U]
+    float* bhn1;   // [U]
+    float* bhn2;   // [U]
+    float* bfc3;   // [CR]
+    float* coef;   // [200][kTaps]
+};
+
+__device__ __forceinline__ Smem carve(float* base, int B, int FB, int CR) {
+    Smem s;
+    float* p = base;
+    s.Whh1 = p; p += G * kRnn;
+    s.Wih2 = p; p += G * kRnn;
+    s.Whh2 = p; p += G * kRnn;
+    s.Wfc1 = p; p += U * kRnn;
+    s.Wfc2 = p; p += U * kRnn;
+    s.Wfc3 = p; p += CR * kRnn;
+    s.act = p;  p += FB * kRnn;
+    s.tmp = p;  p += FB * G;
+    s.h1 = p;   p += B * U;
+    s.h2 = p;   p += B * U;
+    s.x1 = p;   p += B * U;
+    s.gh1 = p;  p += B * G;
+    s.gh2 = p;  p += B * G;
+    s.x = p;    p += (B + 3) & ~3;
+    s.v1 = p;   p += 3 * U;
+    s.wI0 = p;  p += U;
+    s.bhn1 = p; p += U;
+    s.bhn2 = p; p += U;
+    s.bfc3 = p; p += 8;
+    s.coef = p; p += kHop * kTaps;
+    return s;
+}
+
+// Spin until every {value, tag} word of rows [b0, b0+nb) of `buf` carries `tag`; copy the values into
+// act[nb][512].  Returns nonzero (CTA-uniform) if the deadline passed or another CTA aborted.
+__device__ __noinline__ int gather(const unsigned long long* __restrict__ buf, int b0, int nb, float* __restrict__ act,
+                                   uint32_t tag, int* abort_flag) {
+    constexpr int MAXI = 8;
+    const int tid = threadIdx.x;
+    const int npairs = nb * (kRnn / 2);
+    const unsigned long long* src = buf + (size_t)b0 * kRnn;
+    int failed = 0;
+    for (int base = 0; base < npairs; base += NT * MAXI) {
+        uint32_t pending = 0;
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i)
+            if (base + tid + i * NT < npairs) pending |= 1u << i;
+        long long t0 = 0;
+        int spins = 0;
+        while (pending) {
+            unsigned long long a[MAXI], b[MAXI];
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i)
+                if ((pending >> i) & 1u) ll_load2(src + 2 * (size_t)(base + tid + i * NT), a[i], b[i]);
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i)
+                if ((pending >> i) & 1u) {
+                    if (ll_tag(a[i]) == tag && ll_tag(b[i]) == tag) {
+                        *reinterpret_cast<float2*>(act + 2 * (size_t)(base + tid + i * NT)) =
+                            make_float2(ll_val(a[i]), ll_val(b[i]));
+                        pending &= ~(1u << i);
+                    }
+                }
+            if (pending && ((++spins) & 63) == 0) {
+                if (t0 == 0) t0 = clock64();
+                if (clock64() - t0 > kSpinDeadline || ld_volatile_i32(abort_flag) != 0) { failed = 1; break; }
+            }
+        }
+        if (failed) break;
+    }
+    return __syncthreads_or(failed);
+}
+
+// out[f][r] = sum_k W[r][k] * act[f][k] for r < R, f < nb.  Warp tasks of RT rows x FT folds; lanes
+// split K (float4, conflict-free) and reduce with shuffles.  Ends with __syncthreads().
+template <int RT, int FT>
+__device__ __noinline__ void dots(const float* __restrict__ sW, int R, const float* __restrict__ act, int nb,
+                     float* __restrict__ out, int ldo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nrg = (R + RT - 1) / RT, nfg = (nb + FT - 1) / FT;
+    for (int task = warp; task < nrg * nfg; task += NW) {
+        const int r0 = (task % nrg) * RT, f0 = (task / nrg) * FT;
+        float acc[RT][FT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int f = 0; f < FT; ++f) acc[r][f] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kRnn / 128; ++kk) {
+            const int k = kk * 128 + lane * 4;
+            float4 w[RT], a[FT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) w[r] = *reinterpret_cast<const float4*>(sW + min(r0 + r, R - 1) * kRnn + k);
+#pragma unroll
+            for (int f = 0; f < FT; ++f) a[f] = *reinterpret_cast<const float4*>(act + min(f0 + f, nb - 1) * kRnn + k);
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+#pragma unroll
+                for (int f = 0; f < FT; ++f) {
+                    acc[r][f] = fmaf(w[r].x, a[f].x, acc[r][f]);
+                    acc[r][f] = fmaf(w[r].y, a[f].y, acc[r][f]);
+                    acc[r][f] = fmaf(w[r].z, a[f].z, acc[r][f]);
+                    acc[r][f] = fmaf(w[r].w, a[f].w, acc[r][f]);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int f = 0; f < FT; ++f) {
+                float v = warp_sum(acc[r][f]);
+                if (lane == r * FT + f && r0 + r < R && f0 + f < nb) out[(f0 + f) * ldo + r0 + r] = v;
+            }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void dots_any(bool single, const float* sW, int R, const float* act, int nb, float* out, int ldo) {
+    if (single) dots<1, 1>(sW, R, act, nb, out, ldo);
+    else dots<4, 4>(sW, R, act, nb, out, ldo);
+}
+
+// spin on one word
+__device__ __forceinline__ bool wait_word(const unsigned long long* p, uint32_t tag, float& v, int* abort_flag) {
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        unsigned long long w = ll_load(p);
+        if (ll_tag(w) == tag) { v = ll_val(w); return true; }
+        if (((++spins) & 63) == 0) {
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > kSpinDeadline || ld_volatile_i32(abort_flag) != 0) return false;
+        }
+    }
+}
+
+// RAW: softmax + inverse CDF of one fold's logits row by one warp (rule: oracle sample_raw).
+// Lane l owns classes [l*SEG, (l+1)*SEG).  Returns class index (warp-uniform) or -1 on timeout.
+template <int SEG>
+__device__ __noinline__ int sample_raw_warp(const unsigned long long* __restrict__ row, uint32_t tag, float u, int* abort_flag) {
+    const int lane = threadIdx.x & 31;
+    float l[SEG];
+    bool ok = true;
+    {
+        const unsigned long long* src = row + lane * SEG;
+        uint32_t pending = (SEG / 2 >= 32) ? 0xffffffffu : ((1u << (SEG / 2)) - 1u);
+        long long t0 = 0;
+        int spins = 0;
+        while (pending) {
+#pragma unroll
+            for (int i = 0; i < SEG / 2; ++i)
+                if ((pending >> i) & 1u) {
+                    unsigned long long a, b;
+                    ll_load2(src + 2 * i, a, b);
+                    if (ll_tag(a) == tag && ll_tag(b) == tag) {
+                        l[2 * i] = ll_val(a);
+                        l[2 * i + 1] = ll_val(b);
+                        pending &= ~(1u << i);
+                    }
+                }
+            if (pending && ((++spins) & 63) == 0) {
+                if (t0 == 0) t0 = clock64();
+                if (clock64() - t0 > kSpinDeadline || ld_volatile_i32(abort_flag) != 0) { ok = false; break; }
+            }
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) return -1;
+    float m = l[0];
+#pragma unroll
+    for (int i = 1; i < SEG; ++i) m = fmaxf(m, l[i]);
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) { l[i] = expf(l[i] - m); s += l[i]; }
+    const float total = warp_sum(s);
+    float ls = 0.f;
+#pragma unroll
+    for (int i = 0; i < SEG; ++i) { l[i] = l[i] / total; ls += l[i]; }
+    float incl = ls;   // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float excl = incl - ls;
+    const unsigned hit = __ballot_sync(0xffffffffu, incl >= u);
+    int k = SEG * 32 - 1;
+    if (hit) {
+        const int L = __ffs(hit) - 1;
+        int kk = SEG - 1;
+        if (lane == L) {
+            float c = excl;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                c += l[i];
+                if (c >= u) { kk = i; break; }
+            }
+            kk += L * SEG;
+        }
+        k = __shfl_sync(0xffffffffu, kk, L);
+    }
+    return k;
+}
+
+// MOL: vocoder/distribution.py:104-140 on one fold's 30 outputs by one warp.
+__device__ __noinline__ float sample_mol_warp(const unsigned long long* __restrict__ row, uint32_t tag, uint2 key, uint32_t step,
+                                 const FoldDesc& fd, int* abort_flag, bool& ok_out) {
+    const int lane = threadIdx.x & 31;
+    float lg = 0.f;
+    bool ok = true;
+    if (lane < 30) ok = wait_word(row + lane, tag, lg, abort_flag);
+    ok_out = __all_sync(0xffffffffu, ok);
+    if (!ok_out) return 0.f;
+    float score = -INFINITY;
+    if (lane < 10) {
+        uint4 r = philox4x32_10(make_uint4(step, (uint32_t)fd.fold, (uint32_t)fd.utt, (uint32_t)(lane >> 2)), key);
+        float um = 1e-5f + u01(word_of(r, lane & 3)) * (1.0f - 2e-5f);
+        score = lg - logf(-logf(um));
+    }
+    int idx = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float os = __shfl_xor_sync(0xffffffffu, score, o);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (os > score || (os == score && oi < idx)) { score = os; idx = oi; }
+    }
+    const float mean = __shfl_sync(0xffffffffu, lg, 10 + idx);
+    const float lsc = fmaxf(__shfl_sync(0xffffffffu, lg, 20 + idx), -32.23619130191664f);
+    uint4 r2 = philox4x32_10(make_uint4(step, (uint32_t)fd.fold, (uint32_t)fd.utt, 2u), key);
+    const float ul = 1e-5f + u01(r2.z) * (1.0f - 2e-5f);
+    float x = mean + expf(lsc) * (logf(ul) - logf(1.0f - ul));
+    return fminf(fmaxf(x, -1.0f), 1.0f);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = p.B, FB = p.FB, C = p.C, CR = p.CR;
+    const int j0 = cta * U;
+    Smem s = carve(smem_f, B, FB, CR);
+    const bool single = (B == 1);
+
+    // ---- one-time: my weight rows into shared memory ------------------------------------------------
+    for (int i = tid; i < G * (kRnn / 4); i += NT) {
+        const int row = i / (kRnn / 4), k4 = i % (kRnn / 4);
+        const int g = row / U, u = row % U;
+        const size_t src = ((size_t)(g * kRnn + j0 + u) * kRnn) / 4 + k4;
+        reinterpret_cast<float4*>(s.Whh1)[i] = reinterpret_cast<const float4*>(p.Whh1)[src];
+        reinterpret_cast<float4*>(s.Wih2)[i] = reinterpret_cast<const float4*>(p.Wih2a)[src];
+        reinterpret_cast<float4*>(s.Whh2)[i] = reinterpret_cast<const float4*>(p.Whh2)[src];
+    }
+    for (int i = tid; i < U * (kRnn / 4); i += NT) {
+        const size_t src = ((size_t)j0 * kRnn) / 4 + i;
+        reinterpret_cast<float4*>(s.Wfc1)[i] = reinterpret_cast<const float4*>(p.Wfc1a)[src];
+        reinterpret_cast<float4*>(s.Wfc2)[i] = reinterpret_cast<const float4*>(p.Wfc2a)[src];
+    }
+    for (int i = tid; i < CR * (kRnn / 4); i += NT) {
+        const int row = i / (kRnn / 4), cls = cta * CR + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cls < C) v = reinterpret_cast<const float4*>(p.Wfc3)[(size_t)cls * (kRnn / 4) + i % (kRnn / 4)];
+        reinterpret_cast<float4*>(s.Wfc3)[i] = v;
+    }
+    if (tid < 3 * U) s.v1[tid] = p.v1[(tid / U) * kRnn + j0 + tid % U];
+    if (tid < U) {
+        s.wI0[tid] = p.wI0[j0 + tid];
+        s.bhn1[tid] = p.bhn1[j0 + tid];
+        s.bhn2[tid] = p.bhn2[j0 + tid];
+    }
+    if (tid < CR) s.bfc3[tid] = (cta * CR + tid < C) ? p.bfc3[cta * CR + tid] : 0.f;
+    for (int i = tid; i < kHop * kTaps; i += NT) s.coef[i] = p.coef[i];
+    for (int i = tid; i < B * U; i += NT) { s.h1[i] = 0.f; s.h2[i] = 0.f; s.x1[i] = 0.f; }
+    for (int i = tid; i < B * G; i += NT) { s.gh1[i] = 0.f; s.gh2[i] = 0.f; }   // W_hh * 0
+    for (int i = tid; i < B; i += NT) s.x[i] = 0.f;                              // x_0 = 0, fatchord_version.py:183
+    __syncthreads();
+
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const int nchunks = (B + FB - 1) / FB;
+
+    for (int t = 0; t < p.S; ++t) {
+        const uint32_t tag = (uint32_t)t + 1u;
+
+        // ---- A: wait x_{t-1}; GRU1 update for my units; publish x1, h1 ---------------------------------
+        {
+            int failed = 0;
+            if (t > 0) {
+                for (int b = tid; b < B; b += NT) {
+                    float v;
+                    if (!wait_word(p.bX + b, (uint32_t)t, v, p.abort_flag)) failed = 1;
+                    s.x[b] = v;
+                }
+            }
+            if (__syncthreads_or(failed)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            for (int e = tid; e < B * U; e += NT) {
+                const int b = e / U, u = e % U, j = j0 + u;
+                const FoldDesc fd = p.folds[b];
+                const int n = fd.n0 + t;
+                const bool valid = n < fd.N;
+                const int q0 = valid ? n / kHop : 0;
+                float4 acc = __ldg(p.TA1 + (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j);
+                if (valid) {
+                    const float* cf = s.coef + (n - q0 * kHop) * kTaps;
+#pragma unroll
+                    for (int d = 0; d < kTaps; ++d) {
+                        const float c = cf[d];
+                        if (c != 0.f) {
+                            const float4 q = __ldg(p.TQ + (size_t)(fd.tq_row0 + q0 + d) * kRnn + j);
+                            acc.x = fmaf(c, q.x, acc.x); acc.y = fmaf(c, q.y, acc.y);
+                            acc.z = fmaf(c, q.z, acc.z); acc.w = fmaf(c, q.w, acc.w);
+                        }
+                    }
+                }
+                const float x = s.x[b];
+                const float* gh = s.gh1 + b * G;
+                const float r = sigmoid_acc(fmaf(s.v1[0 * U + u], x, acc.x) + gh[0 * U + u]);
+                const float z = sigmoid_acc(fmaf(s.v1[1 * U + u], x, acc.y) + gh[1 * U + u]);
+                const float nn = tanhf(fmaf(s.v1[2 * U + u], x, acc.z) + r * (gh[2 * U + u] + s.bhn1[u]));
+                const float h = (1.0f - z) * nn + z * s.h1[e];
+                const float xI = fmaf(s.wI0[u], x, acc.w);
+                const float x1 = xI + h;
+                s.h1[e] = h;
+                s.x1[e] = x1;
+                ll_store(p.bX1 + (size_t)b * kRnn + j, x1, tag);
+                ll_store(p.bH1 + (size_t)b * kRnn + j, h, tag);
+            }
+        }
+
+        // ---- B: gi2 = W_ih2[:, :512] x1 ; GRU2 update ; publish x2, h2 ------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bX1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            dots_any(single, s.Wih2, G, s.act, nb, s.tmp, G);
+            for (int e = tid; e < nb * U; e += NT) {
+                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
+                const FoldDesc fd = p.folds[b];
+                const int n = fd.n0 + t;
+                const float4 ta = __ldg(p.TA2 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
+                const float* gi = s.tmp + bl * G;
+                const float* gh = s.gh2 + b * G;
+                const float r = sigmoid_acc(gi[0 * U + u] + ta.x + gh[0 * U + u]);
+                const float z = sigmoid_acc(gi[1 * U + u] + ta.y + gh[1 * U + u]);
+                const float nn = tanhf(gi[2 * U + u] + ta.z + r * (gh[2 * U + u] + s.bhn2[u]));
+                const float h = (1.0f - z) * nn + z * s.h2[b * U + u];
+                s.h2[b * U + u] = h;
+                ll_store(p.bX2 + (size_t)b * kRnn + j, s.x1[b * U + u] + h, tag);
+                ll_store(p.bH2 + (size_t)b * kRnn + j, h, tag);
+            }
+            __syncthreads();
+        }
+        // ---- B2 (off the critical path): gh1 = W_hh1 h1 for step t+1 -----------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bH1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            dots_any(single, s.Whh1, G, s.act, nb, s.gh1 + b0 * G, G);
+        }
+        // ---- C: f1 = relu(fc1[:, :512] x2 + PF1) ; publish ----------------------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bX2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            dots_any(single, s.Wfc1, U, s.act, nb, s.tmp, G);
+            for (int e = tid; e < nb * U; e += NT) {
+                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
+                const FoldDesc fd = p.folds[b];
+                const int n = fd.n0 + t;
+                const float4 ta = __ldg(p.TA2 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
+                ll_store(p.bF1 + (size_t)b * kRnn + j, fmaxf(s.tmp[bl * G + u] + ta.w, 0.f), tag);
+            }
+            __syncthreads();
+        }
+        // ---- C2 (off the critical path): gh2 = W_hh2 h2 for step t+1 -----------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bH2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            dots_any(single, s.Whh2, G, s.act, nb, s.gh2 + b0 * G, G);
+        }
+        // ---- D: f2 = relu(fc2[:, :512] f1 + PF2) ; publish ----------------------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bF1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            dots_any(single, s.Wfc2, U, s.act, nb, s.tmp, G);
+            for (int e = tid; e < nb * U; e += NT) {
+                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
+                const FoldDesc fd = p.folds[b];
+                const int n = fd.n0 + t;
+                const float pf2 = __ldg(p.TA3 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
+                ll_store(p.bF2 + (size_t)b * kRnn + j, fmaxf(s.tmp[bl * G + u] + pf2, 0.f), tag);
+            }
+            __syncthreads();
+        }
+        // ---- E: my classes of logits = fc3 f2 + b ; publish ---------------------------------------------------
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * FB, nb = min(FB, B - b0);
+            if (gather(p.bF2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+            if (cta * CR < C) {
+                dots_any(single, s.Wfc3, CR, s.act, nb, s.tmp, G);
+                for (int e = tid; e < nb * CR; e += NT) {
+                    const int bl = e / CR, r = e % CR, b = b0 + bl, cls = cta * CR + r;
+                    if (cls < C) {
+                        const float v = s.tmp[bl * G + r] + s.bfc3[r];
+                        ll_store(p.bLG + (size_t)b * p.Cpad + cls, v, tag);
+                        if (p.logits_out) p.logits_out[((size_t)b * p.S + t) * C + cls] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- F: sample the folds assigned to this CTA ; publish x_t ----------------------------------------
+        {
+            int failed = 0;
+            for (int b = cta + gridDim.x * warp; b < B; b += gridDim.x * NW) {
+                const FoldDesc fd = p.folds[b];
+                const unsigned long long* row = p.bLG + (size_t)b * p.Cpad;
+                float xs;
+                if (p.mode == 1) {
+                    bool ok;
+                    xs = sample_mol_warp(row, tag, key, (uint32_t)t, fd, p.abort_flag, ok);
+                    if (!ok) { failed = 1; break; }
+                } else {
+                    uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 0u), key);
+                    const float u = u01(r.x);
+                    int k;
+                    if (C == 512) k = sample_raw_warp<16>(row, tag, u, p.abort_flag);
+                    else k = sample_raw_warp<32>(row, tag, u, p.abort_flag);
+                    if (k < 0) { failed = 1; break; }
+                    xs = 2.0f * (float)k / ((float)C - 1.0f) - 1.0f;     // fatchord_version.py:228 (fp32, Q10)
+                }
+                if (lane == 0) {
+                    p.samples[(size_t)b * p.S + t] = xs;
+                    const float fed = p.forced ? p.forced[(size_t)b * p.S + t] : xs;
+                    ll_store(p.bX + b, fed, tag);
+                }
+            }
+            if (__syncthreads_or(failed)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
+        }
+        if (cta == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
+            *reinterpret_cast<volatile int*>(p.progress) = t;
+            __threadfence_system();
+        }
+    }
+}
+
+size_t loop_f32_smem_bytes(int B, int FB, int CR) {
+    size_t f = (size_t)3 * G * kRnn + 2 * U * kRnn + (size_t)CR * kRnn + (size_t)FB * kRnn + (size_t)FB * G +
+               (size_t)B * (3 * U + 2 * G) + ((B + 3) & ~3) + 3 * U + 3 * U + 8 + kHop * kTaps;
+    return f * sizeof(float);
+}
+
+int loop_f32_pick_fb(int B, int CR, size_t smem_limit) {
+    int fb = B < 32 ? B : 32;
+    while (fb > 1 && loop_f32_smem_bytes(B, fb, CR) > smem_limit) --fb;
+    return loop_f32_smem_bytes(B, fb, CR) <= smem_limit ? fb : 0;
+}
+
+cudaError_t launch_loop_f32(const LoopParams& p, cudaStream_t stream) {
+    const size_t smem = loop_f32_smem_bytes(p.B, p.FB, p.CR);
+    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    LoopParams pp = p;
+    void* args[] = {&pp};
+    // cooperative launch: guarantees the 128 CTAs are co-resident (they wait on one another)
+    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_f32_kernel, dim3(kCtasF32), dim3(NT), args, smem, stream);
+}
+
+}  // namespace wrnn

@@ -1,0 +1,171 @@
+"""Vocoder facade: drop-in for the reference's vocoder/inference.py (load_model :11-53, is_loaded :56-57,
+infer_waveform :59-95, set_seed :97-101) with the B200 engine behind it.  Same names, positional order,
+defaults, return dtype (np.float64, length (T-1)*hop) and exception types/messages."""
+import numpy as np
+
+from ..config.hparams import sp, wavernn_fatchord
+from .models import base
+
+_model = None        # list of per-GPU WaveRNN objects once loaded
+_model_type = None
+_seed = 0
+_calls = 0
+
+
+def _devices(devices):
+    if devices is None:
+        return [0]
+    return [int(str(d).split(":")[-1]) if not isinstance(d, int) else d for d in devices]
+
+
+def load_state(state_dict, model_type=base.MODEL_TYPE_FATCHORD, devices=None, override_hp_fatchord=None, verbose=False):
+    """Builds the engine(s) from an in-memory state_dict (what load_model does after torch.load)."""
+    global _model, _model_type
+    models = []
+    for d in _devices(devices):
+        m, _ = base.init_voc_model(model_type, d, override_hp_fatchord=override_hp_fatchord)
+        m.eval()
+        m.load_state_dict(state_dict)
+        models.append(m)
+    _model, _model_type = models, model_type
+    if verbose:
+        print("Model has been trained to step %d." % models[0].get_step())
+    return models[0]
+
+
+def load_model(weights_fpath, voc_type=base.VOC_TYPE_PYTORCH, verbose=True, devices=None):
+    """inference.py:11.  voc_type 'pytorch' and 'b200' both select this engine (it replaces the PyTorch
+    path); 'libwavernn' .bin files are SURVEY.md section 8(f) "next"."""
+    global _model, _model_type
+    if voc_type in (base.VOC_TYPE_PYTORCH, base.VOC_TYPE_B200):
+        import torch  # checkpoint I/O only
+        checkpoint = torch.load(weights_fpath, map_location="cpu")
+        model_type = base.MODEL_TYPE_FATCHORD
+        if "model_type" in checkpoint:
+            model_type = checkpoint["model_type"]
+        state = checkpoint["model_state"] if "model_state" in checkpoint else checkpoint   # legacy bare dict, :417-424
+        try:
+            load_state(state, model_type, devices=devices)
+        except NotImplementedError as e:      # inference.py:27-32 prints and returns
+            print(str(e))
+            return
+        if verbose:
+            print("Loaded vocoder of model '%s' at path '%s'." % (_model_type, weights_fpath))
+            print("Model has been trained to step %d." % (_model[0].get_step()))
+    elif voc_type == base.VOC_TYPE_CPP:
+        raise NotImplementedError("libwavernn .bin checkpoints are not handled by the B200 engine yet; "
+                                  "load the .pt checkpoint instead")
+    else:
+        raise NotImplementedError("Invalid vocoder of type '%s' provided. Aborting..." % voc_type)
+
+
+def unload():
+    global _model, _model_type
+    _model, _model_type = None, None
+
+
+def is_loaded():
+    return _model is not None
+
+
+def set_seed(seed):
+    """inference.py:97: the reference seeds torch's global RNG; here the seed keys the Philox stream."""
+    global _seed, _calls
+    _seed, _calls = int(seed), 0
+
+
+def _next_seed():
+    global _calls
+    s = (_seed + 0x9E3779B97F4A7C15 * _calls) & 0xFFFFFFFFFFFFFFFF   # successive calls draw fresh noise
+    _calls += 1
+    return s
+
+
+def _hp():
+    if _model_type == base.MODEL_TYPE_FATCHORD:
+        return wavernn_fatchord
+    raise NotImplementedError("Invalid model of type '%s' provided. Aborting..." % _model_type)
+
+
+def infer_waveform(mel, normalize=True, batched=True, target=None, overlap=None, progress_callback=None):
+    """inference.py:59.  mel: (80, T) float32 in the synthesizer's range.  With several engines loaded
+    (load_model(..., devices=[...])) the folds of the utterance are split into contiguous ranges, one
+    per GPU, run concurrently from host threads, gathered on the host and cross-faded on GPU 0 -- no
+    collective is involved."""
+    if _model is None or _model_type is None:
+        raise Exception("Please load Wave-RNN in memory before using it")
+    hp_wavernn = _hp()
+    if target is None:
+        target = hp_wavernn.gen_target
+    if overlap is None:
+        overlap = hp_wavernn.gen_overlap
+    if normalize:
+        mel = mel / sp.max_abs_value
+    mel = np.ascontiguousarray(mel, dtype=np.float32)
+    seed = _next_seed()
+    if len(_model) == 1 or not batched:
+        m = _model[0]
+        m.seed = seed
+        return m.generate(mel[None, ...], batched, target, overlap, hp_wavernn.mu_law, sp.preemphasize, progress_callback)
+    return _infer_sharded(mel, target, overlap, hp_wavernn.mu_law, sp.preemphasize, seed)
+
+
+def _infer_sharded(mel, target, overlap, mu_law, preemph, seed):
+    from concurrent.futures import ThreadPoolExecutor
+    from .. import _native
+    T = mel.shape[1]
+    F, _ = _native.fold_plan(T * sp.hop_size, target, overlap)
+    n = min(len(_model), F)
+    bounds = [F * i // n for i in range(n + 1)]
+
+    def work(i):
+        return _model[i].generate_debug(mel, True, target, overlap, fold_begin=bounds[i], fold_end=bounds[i + 1],
+                                        seed=seed)["samples"]
+    with ThreadPoolExecutor(max_workers=n) as ex:
+        parts = list(ex.map(work, range(n)))
+    samples = np.concatenate(parts, axis=0)
+    return _model[0].postprocess(samples, True, overlap, T, mu_law, preemph)
+
+
+def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=None, utt_index0=0):
+    """Many utterances: sharded by utterance across the loaded engines (BASELINE config 5); inside one
+    engine all folds share persistent-loop launches.  Returns a list of float64 arrays."""
+    if _model is None or _model_type is None:
+        raise Exception("Please load Wave-RNN in memory before using it")
+    from concurrent.futures import ThreadPoolExecutor
+    hp_wavernn = _hp()
+    target = hp_wavernn.gen_target if target is None else target
+    overlap = hp_wavernn.gen_overlap if overlap is None else overlap
+    mels = [np.ascontiguousarray(m / sp.max_abs_value if normalize else m, dtype=np.float32) for m in mels]
+    seed = _next_seed()
+    n = min(len(_model), len(mels))
+    # balance by total frames: longest first onto the lightest shard
+    order = sorted(range(len(mels)), key=lambda i: -mels[i].shape[1])
+    shards, load = [[] for _ in range(n)], [0] * n
+    for i in order:
+        k = load.index(min(load))
+        shards[k].append(i)
+        load[k] += mels[i].shape[1]
+    out = [None] * len(mels)
+
+    def work(k):
+        m = _model[k]
+        m.seed = seed
+        res = []
+        for i in sorted(shards[k]):       # one call per utterance index keeps utt counters global
+            res.append((i, None))
+        idx = sorted(shards[k])
+        # contiguous runs share a call; non-contiguous indices need their own utt_index0
+        runs, start = [], 0
+        for j in range(1, len(idx) + 1):
+            if j == len(idx) or idx[j] != idx[j - 1] + 1:
+                runs.append(idx[start:j])
+                start = j
+        for run in runs:
+            wavs = m.generate_batch([mels[i] for i in run], batched, target, overlap, hp_wavernn.mu_law,
+                                    sp.preemphasize, utt_index0=utt_index0 + run[0])
+            for i, w in zip(run, wavs):
+                out[i] = w
+    with ThreadPoolExecutor(max_workers=n) as ex:
+        list(ex.map(work, range(n)))
+    return out

@@ -1,0 +1,75 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, and the
+host-only entry points agree with the oracle.  No CUDA calls."""
+import os
+import re
+
+import numpy as np
+
+from oracle import wavernn_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    import __graft_entry__ as g
+    g.build()
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    return _native, _native.load()
+
+
+def test_library_exports_every_declared_symbol():
+    _native, lib = _lib()
+    header = open(os.path.join(ROOT, "include", "wavernn_b200.h")).read()
+    declared = set(re.findall(r"\b(wrnn_[a-z0-9_]+)\s*\(", header)) - {"wrnn_progress_fn"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_native.EXPORTS)
+
+
+def test_fold_plan_matches_oracle():
+    _native, _ = _lib()
+    rng = np.random.default_rng(0)
+    cases = [(160000, 8000, 800), (960000, 6000, 1000), (960000, 3000, 1500), (4800, 1000, 200), (1000, 1000, 200)]
+    cases += [(int(rng.integers(300, 200000)), int(rng.integers(1, 9000)), int(rng.integers(1, 2000))) for _ in range(300)]
+    for N, tg, ov in cases:
+        if N < ov:
+            continue
+        assert _native.fold_plan(N, tg, ov) == orc.fold_plan(N, tg, ov), (N, tg, ov)
+
+
+def test_drop_in_surface():
+    import inspect
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200.vocoder import inference
+    from rtvc_b200.vocoder.models import base
+    from rtvc_b200.vocoder.models.fatchord_version import WaveRNN
+    sig = inspect.signature(inference.infer_waveform)
+    assert list(sig.parameters)[:6] == ["mel", "normalize", "batched", "target", "overlap", "progress_callback"]
+    assert [p.default for p in sig.parameters.values()][:6] == [inspect._empty, True, True, None, None, None]
+    assert list(inspect.signature(WaveRNN.generate).parameters)[1:] == [
+        "mels", "batched", "target", "overlap", "mu_law", "apply_preemphasis", "progress_callback"]
+    assert list(inspect.signature(inference.load_model).parameters)[:3] == ["weights_fpath", "voc_type", "verbose"]
+    assert (base.VOC_TYPE_CPP, base.VOC_TYPE_PYTORCH, base.MODEL_TYPE_FATCHORD) == ("libwavernn", "pytorch", "fatchord-wavernn")
+    assert not inference.is_loaded()
+    try:
+        inference.infer_waveform(np.zeros((80, 30), np.float32))
+        raise AssertionError("expected the not-loaded exception")
+    except Exception as e:
+        assert str(e) == "Please load Wave-RNN in memory before using it"
+    for bad in ("geneing-wavernn", "nope"):
+        try:
+            base.init_voc_model(bad, 0)
+            raise AssertionError
+        except NotImplementedError:
+            pass
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "real-time-voice-cloning_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
