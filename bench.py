@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 WaveRNN vocoder engine (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3] [--precision f32|f16]
+    python bench.py --impl reference ...      # CPU arm: torch-CPU port of the reference loop (oracle/torch_port.py)
+
+One "step" = one pass of the hot path (infer_waveform: conditioning -> fold -> sample loop -> xfade ->
+mu-law -> de-emphasis) over one batch of synthetic mel input.  Metric = BASELINE.json's: vocoder output
+samples/sec (x real-time = / 16000).  N GPUs: every rank vocodes its own utterance(s) (weak scaling, no
+collective on the data path; torch.distributed/NCCL is used only for the timing barrier and max).
+  value : inputs already resident in HBM, output left in HBM, timed with CUDA events on the engine's stream
+  e2e   : the public call rtvc_b200.vocoder.inference.infer_waveform with HOST buffers (pinned), copies timed
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (mode, bits, seconds, batched, target, overlap)  -- BASELINE.json configs / SURVEY.md section 8(d)
+    "cfg1": ("RAW", 9, 10, True, 8000, 800),      # 19 folds x 9600 steps
+    "cfg2": ("RAW", 9, 3, False, 0, 0),           # 1 x 48000 steps (per-step latency)
+    "cfg3": ("MOL", 9, 60, True, 6000, 1000),     # 137 folds x 8000 steps  <- the config the target is quoted on
+    "cfg3b": ("MOL", 9, 60, True, 3000, 1500),    # 213 folds x 6000 steps
+    "cfg1x60": ("RAW", 9, 60, True, 6000, 1000),  # RAW at the cfg3 shape
+}
+PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def macs_per_row_step(C):
+    """Algorithmic MACs of the REFERENCE's step per fold: I + rnn1 + rnn2 + fc1 + fc2 + fc3."""
+    return 57344 + 1572864 + 1622016 + 278528 + 278528 + 512 * C
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p, "measured"
+    except Exception:
+        return PEAKS_FALLBACK, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, wl):
+    """CPU arm: the reference's loop restated with torch CPU ops, bounded sample, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import weights
+    from oracle.torch_port import time_generate
+    import torch
+    mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
+    sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
+    mel = weights.synthetic_mel(80 * seconds, seed=1) / np.float32(4.0)
+    threads = os.cpu_count()
+    budget = float(args.cpu_seconds) / max(1, args.steps + args.warmup)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = time_generate(sd, mode, mel, batched, target, overlap, threads=threads, time_budget_s=budget, seed=1)
+        if i >= args.warmup:
+            vals.append(r)
+    est = float(np.mean([r["est_total_seconds"] for r in vals]))
+    out_samples = vals[0]["out_samples"]
+    value = out_samples / est
+    sample = "%d of %d loop steps x %d folds per step-sample, conditioning in full; extrapolated linearly" % (
+        vals[0]["steps_done"], vals[0]["steps_total"], vals[0]["folds"])
+    line = {
+        "impl": "reference", "metric": "vocoder_output_samples_per_sec", "value": value, "unit": "samples/s",
+        "x_realtime": value / 16000.0, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl):
+    mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
+    return {"workload": "%s: WaveRNN fatchord %s%s, %d s synthetic 80-mel @16 kHz, %s" % (
+        wl, mode, (" %d-bit" % bits) if mode == "RAW" else "", seconds,
+        ("batched target=%d overlap=%d" % (target, overlap)) if batched else "unbatched (single fold)"),
+        "weights": "random-init rnn_dims=512 fc_dims=512 hop=200", "cache": "L2 flushed (256 MiB write) between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    if args.impl == "reference":
+        return reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as entry
+    entry.build()
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    from rtvc_b200.config import hparams
+    from rtvc_b200.vocoder import inference
+    from oracle import weights      # deterministic synthetic weights / mels only
+
+    mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
+    hp = copy.deepcopy(hparams.wavernn_fatchord)
+    hp.bits, hp.mode = bits, mode
+    hparams.wavernn_fatchord.bits, hparams.wavernn_fatchord.mode = bits, mode   # infer_waveform reads the globals
+    sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
+    model = inference.load_state(sd, devices=[local_rank], override_hp_fatchord=hp)
+    model.precision = {"f32": _native.PREC_F32, "f16": _native.PREC_F16}[args.precision]
+    T = 80 * seconds
+    mel_raw = weights.synthetic_mel(T, seed=1 + rank)                       # synthesizer range [-4, 4]
+    mel_host = torch.from_numpy(mel_raw).pin_memory()
+    mel_dev = (mel_host / 4.0).cuda()
+    out_samples = (T - 1) * 200
+    wav_dev = torch.empty(out_samples, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    C = model.n_classes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        rq, arrs, wav, offsets, keep = model._request([np.zeros((80, T), np.float32)], batched, target, overlap,
+                                                      hp.mu_law, True, None, want_wav=False, utt_index0=rank)
+        import ctypes as Ct
+        ptr = (Ct.c_void_p * 1)(mel_dev.data_ptr())
+        rq.mels = Ct.cast(ptr, Ct.POINTER(Ct.c_void_p))
+        rq.mels_on_device = 1
+        rq.wav = wav_dev.data_ptr()
+        rq.wav_capacity = out_samples
+        rq.wav_on_device = 1
+        model._run(rq)
+        t = model.last_timings
+        return t["ms_h2d"] + t["ms_cond"] + t["ms_loop"] + t["ms_post"] + t["ms_d2h"], dict(t)
+
+    def step_e2e():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        wav = inference.infer_waveform(mel_host.numpy(), normalize=True, batched=batched, target=target, overlap=overlap)
+        dt = time.perf_counter() - t0
+        assert wav.shape[0] == out_samples
+        return dt * 1e3
+
+    sampler = ClockSampler(local_rank)
+    # ---- value: HBM-resident ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler.start()
+    launches0 = model.launch_count
+    per_step, loop_ms, last_t = [], [], None
+    for _ in range(args.steps):
+        ms, last_t = step_resident()
+        per_step.append(ms)
+        loop_ms.append(last_t["ms_loop"])
+    barrier()
+    launches = model.launch_count - launches0
+    total_ms = float(sum(per_step))
+    # ---- e2e: public API, host buffers ----------------------------------------------------------------------
+    step_e2e()
+    barrier()
+    e2e_ms = [step_e2e() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.finish()
+    e2e_total = float(sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * out_samples * args.steps / (total_ms / 1e3)
+    e2e_value = world * out_samples * args.steps / (e2e_total / 1e3)
+    pk, pk_kind = peaks()
+    F, S = last_t["n_folds"], last_t["n_steps"]
+    flops = 2.0 * macs_per_row_step(C) * F * S
+    loop_s = float(np.mean(loop_ms)) / 1e3
+    achieved = flops / loop_s / 1e12
+    peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    floor = model.barrier_floor(20000)
+    n_exch = 6 if mode == "RAW" else 6
+    line = {
+        "metric": "vocoder_output_samples_per_sec", "value": value, "unit": "samples/s", "x_realtime": value / 16000.0,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "f32" else "f16 (fp32 accumulate/state)", "data": "synthetic",
+        "config": dict(workload_config(wl), folds=F, loop_steps=S, per_gpu="one utterance per GPU, independent"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "x_realtime": e2e_value / 16000.0,
+                "h2d_bytes_per_step": int(mel_raw.nbytes), "d2h_bytes_per_step": int(out_samples * 8),
+                "ms_per_step": e2e_total / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "wrnn_loop_f32_kernel" if args.precision == "f32" else "wrnn_loop_tc_kernel",
+                     "peak_source": pk_kind + " bf16_tflops_sustained", "kernel_ms": loop_s * 1e3,
+                     "algorithmic_flops_per_launch": flops},
+        "loop": {"us_per_step": loop_s * 1e6 / S, "exchanges_per_step": n_exch, "exchange_floor_us": floor["ll_us"],
+                 "counter_barrier_floor_us": floor["counter_us"],
+                 "step_over_floor": (loop_s * 1e6 / S) / (n_exch * floor["ll_us"])},
+        "phases_ms": {k: last_t[k] for k in ("ms_h2d", "ms_cond", "ms_loop", "ms_post", "ms_d2h")},
+    }
+    if not args.no_cpu_baseline:
+        from oracle.torch_port import time_generate
+        r = time_generate(sd, mode, mel_raw / np.float32(4.0), batched, target, overlap, threads=os.cpu_count(),
+                          time_budget_s=args.cpu_seconds, seed=1)
+        line["cpu_baseline"] = {"value": r["out_samples"] / r["est_total_seconds"], "unit": "samples/s",
+                                "cores": r["threads"], "kind": "port",
+                                "sample": "%d of %d loop steps x %d folds (torch CPU port of the reference loop), "
+                                          "conditioning in full; extrapolated linearly" % (r["steps_done"], r["steps_total"], r["folds"])}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -180,6 +181,8 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     if (err == cudaSuccess) err = cudaHostAlloc(&e->hProgress, sizeof(int), cudaHostAllocMapped);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->dProgress, e->hProgress, 0);
     for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
+    if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))   // profilers slow the loop down: let them widen the guard
+        if (err == cudaSuccess) err = set_spin_deadline((long long)(atof(dl) * 1.9e6));
     if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
     *out = e;
     return WRNN_OK;
@@ -624,7 +627,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                     rq->progress(i, S, B, (double)(i + 1) / std::max(dt, 1e-9) * B / 1000.0, rq->progress_user);
                     last = i;
                 }
-                std::this_thread::sleep_for(std::chrono::microseconds(500));
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
             }
         }
         int aborted = 0;

@@ -49,6 +49,7 @@ struct LoopParams {
 size_t loop_f32_smem_bytes(int B, int FB, int CR);
 int loop_f32_pick_fb(int B, int CR, size_t smem_limit);
 cudaError_t launch_loop_f32(const LoopParams& p, cudaStream_t stream);
+cudaError_t set_spin_deadline(long long cycles);
 
 // ---- conditioning front end (cond.cu) ---------------------------------------------------------------
 struct UttDesc {

@@ -23,7 +23,8 @@ constexpr int NT = 512;         // threads per CTA
 constexpr int NW = NT / 32;     // warps
 constexpr int U = kUnitsF32;    // hidden units per CTA (4)
 constexpr int G = 3 * U;        // gate rows per CTA per GRU matrix (12)
-constexpr long long kSpinDeadline = 1500000000LL;  // ~0.8 s of SM clocks
+__device__ long long g_spin_deadline = 1500000000LL;   // SM clocks (~0.8 s); host-settable
+#define kSpinDeadline g_spin_deadline
 
 struct Smem {
     float* Whh1;   // [G][512]   rows g*U+u
@@ -493,6 +494,8 @@ int loop_f32_pick_fb(int B, int CR, size_t smem_limit) {
     while (fb > 1 && loop_f32_smem_bytes(B, fb, CR) > smem_limit) --fb;
     return loop_f32_smem_bytes(B, fb, CR) <= smem_limit ? fb : 0;
 }
+
+cudaError_t set_spin_deadline(long long cycles) { return cudaMemcpyToSymbol(g_spin_deadline, &cycles, sizeof(cycles)); }
 
 cudaError_t launch_loop_f32(const LoopParams& p, cudaStream_t stream) {
     const size_t smem = loop_f32_smem_bytes(p.B, p.FB, p.CR);
