@@ -160,6 +160,8 @@ def test_torch_port_matches_oracle():
                          max_steps=60)
     assert done == 60 and (s == tr["samples"]).mean() >= 0.99
     sdm = weights.make_state_dict(seed=12, bits=9, mode="MOL")
+    mels, aux = orc.upsample_network(mel, sdm)
+    mels, aux = orc.fold_with_overlap(mels, 1000, 200), orc.fold_with_overlap(aux, 1000, 200)
     s, _, _ = TorchPort(sdm, "MOL").loop(mels, aux, seed=3, max_steps=40)
     _, tr = orc.generate(mel, sdm, mode="MOL", batched=True, target=1000, overlap=200, seed=3, return_trace=True,
                          max_steps=40)
