@@ -81,6 +81,11 @@ cudaError_t launch_post(const float* samples, const PostUtt* utts, int n_utts, i
 cudaError_t launch_xfade_unfold_f64(const double* y, int F, int S, int overlap, const double* fade_in,
                                     const double* fade_out, long long total_len, double* out, cudaStream_t stream);
 
+// ---- tensor-core building blocks (tma_host.cu, tc_gemm_test.cu) ----------------------------------------
+cudaError_t make_tmap_f16_2d(void* tmap_out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                             uint32_t box_cols);
+cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream);
+
 // ---- exchange-floor microbenchmark (bench_floor.cu) -----------------------------------------------------
 cudaError_t launch_floor_ll(unsigned long long* buf, int rounds, int* abort_flag, cudaStream_t stream);
 cudaError_t launch_floor_counter(unsigned int* counter, float* data, int rounds, int* abort_flag, cudaStream_t stream);

@@ -1,0 +1,117 @@
+// tc_gemm_test.cu -- self-test of the tensor-core building blocks used by the fp16 loop kernel:
+// C[128][N] = A[128][512] * W[N][512]^T with A arriving by TMA (128B swizzle) through a 4-slot mbarrier
+// ring, W staged once in shared memory in the canonical K-major SWIZZLE_128B layout, tcgen05.mma
+// accumulating in TMEM and tcgen05.ld bringing the tile back.  One CTA; exposed as wrnn_debug_tc_gemm.
+#include "engine_internal.h"
+#include "tc_common.cuh"
+
+namespace wrnn {
+namespace {
+using namespace tc;
+
+constexpr int kM = 128, kK = 512, kKB = 64, kNKB = kK / kKB, kSlots = 4;
+constexpr long long kDeadline = 400000000LL;
+
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity) {
+    long long t0 = 0;
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++spins) & 255) == 0) {
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > kDeadline) return false;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(const __grid_constant__ CUtensorMap tmapA,
+                                                              const __half* __restrict__ W, int N, float* __restrict__ C,
+                                                              int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                                   // kSlots x [128 rows x 128 B]
+    uint8_t* sW = sA + kSlots * kM * 128;                 // kNKB x [N rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kNKB * N * 128);
+    uint64_t* full = bars;                                // [kSlots]
+    uint64_t* empty = bars + kSlots;                      // [kSlots]
+    uint64_t* accfull = bars + 2 * kSlots;                // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // stage W (generic proxy) in the swizzled layout
+    for (int i = tid; i < N * kNKB * 8; i += blockDim.x) {
+        const int n = i / (kNKB * 8), rem = i % (kNKB * 8), kb = rem / 8, c = rem % 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(W + (size_t)n * kK + kb * kKB + c * 8);
+        *reinterpret_cast<uint4*>(sW + kb * N * 128 + sw128_offset(n, c)) = v;
+    }
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(accfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 64);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {                       // ---- TMA producer ----
+        if (lane == 0) {
+            tma_prefetch_desc(&tmapA);
+            for (int kb = 0; kb < kNKB; ++kb) {
+                const int slot = kb % kSlots, round = kb / kSlots;
+                if (round > 0 && !wait_bar(&empty[slot], (round - 1) & 1)) { atomicExch(status, 2); break; }
+                mbar_arrive_expect_tx(&full[slot], kM * 128);
+                tma_load_2d(sA + slot * kM * 128, &tmapA, &full[slot], kb * kKB, 0);
+            }
+        }
+    } else if (warp == 5) {                // ---- MMA issuer ----
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(kM, N);
+            for (int kb = 0; kb < kNKB; ++kb) {
+                const int slot = kb % kSlots, round = kb / kSlots;
+                if (!wait_bar(&full[slot], round & 1)) { atomicExch(status, 3); break; }
+                tcgen05_fence_after();
+                const uint32_t a0 = smem_u32(sA + slot * kM * 128), b0 = smem_u32(sW + kb * N * 128);
+#pragma unroll
+                for (int j = 0; j < kKB / 16; ++j)
+                    umma_f16(tmem, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(b0 + j * 32), idesc, (kb | j) ? 1u : 0u);
+                umma_commit(&empty[slot]);
+            }
+            umma_commit(accfull);
+        }
+    } else {                               // ---- epilogue warps 0..3: TMEM lanes 32*warp .. +31 ----
+        const bool ok = wait_bar(accfull, 0);
+        tcgen05_fence_after();
+        if (!ok) { if (lane == 0) atomicExch(status, 4); }
+        else {
+            const int row = warp * 32 + lane;
+            for (int c0 = 0; c0 < N; c0 += 8) {
+                float v[8];
+                tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) C[(size_t)row * N + c0 + i] = v[i];
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+}  // namespace
+
+cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream) {
+    if (N % 16 != 0 || N < 16 || N > 64) return cudaErrorInvalidValue;
+    alignas(64) CUtensorMap tmap;
+    cudaError_t e = make_tmap_f16_2d(&tmap, A_dev, kM, kK, kM, kKB);
+    if (e != cudaSuccess) return e;
+    const size_t smem = 1024 + (size_t)kSlots * kM * 128 + (size_t)kNKB * N * 128 + 256;
+    e = cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc_gemm_test_kernel<<<1, 192, smem, stream>>>(tmap, reinterpret_cast<const __half*>(W_dev), N, C_dev, status_dev);
+    return cudaGetLastError();
+}
+
+}  // namespace wrnn

@@ -313,6 +313,17 @@ class WaveRNN(object):
             _raise(self._lib, self._h, rc)
         return dict(ll_us=ll.value, counter_us=cnt.value)
 
+    def debug_tc_gemm(self, A, W):
+        """Self-test of the tcgen05/TMA building blocks: A (128,512), W (N,512) float16 -> (128,N) float32."""
+        A = np.ascontiguousarray(A, dtype=np.float16)
+        W = np.ascontiguousarray(W, dtype=np.float16)
+        assert A.shape == (128, 512) and W.shape[1] == 512
+        out = np.zeros((128, W.shape[0]), np.float32)
+        rc = self._lib.wrnn_debug_tc_gemm(self._h, A.ctypes.data, W.ctypes.data, W.shape[0], out.ctypes.data)
+        if rc != _native.OK:
+            _raise(self._lib, self._h, rc)
+        return out
+
     def gen_display(self, i, seq_len, b_size, gen_rate):
         """Default progress line (fatchord_version.py:262-265)."""
         done = int(16 * i // max(1, seq_len))
