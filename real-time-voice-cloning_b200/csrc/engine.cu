@@ -59,14 +59,14 @@ struct wrnn_engine {
     // weights on device
     DevBuf wLoop;    // all loop weights, one allocation
     float *dWhh1 = nullptr, *dWih2a = nullptr, *dWhh2 = nullptr, *dWfc1a = nullptr, *dWfc2a = nullptr, *dWfc3 = nullptr;
-    float *dv1 = nullptr, *dwI0 = nullptr, *dbhn1 = nullptr, *dbhn2 = nullptr, *dbfc3 = nullptr, *dcoef = nullptr;
+    float *dv1 = nullptr, *dv2 = nullptr, *dv3 = nullptr, *dbhn1 = nullptr, *dbhn2 = nullptr, *dbfc3 = nullptr, *dcoef = nullptr;
     DevBuf wCond;    // conditioning weights
     float* dCW[kCondLayers] = {};
     float* dCB[kCondLayers] = {};
-    float *dMA1 = nullptr, *dbA1 = nullptr, *dMA2 = nullptr, *dbA2 = nullptr, *dMA3 = nullptr, *dbA3 = nullptr, *dMQ = nullptr;
+    float *dMA1 = nullptr, *dbA1 = nullptr, *dMA2 = nullptr, *dbA2 = nullptr, *dMQ1 = nullptr, *dMQ2 = nullptr;
     std::vector<float> hcoef;
     // grow-only work buffers
-    DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTA3, bTQ, bFolds, bExch, bSamples, bLogits, bForced;
+    DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
     int* dAbort = nullptr;
     int* hProgress = nullptr;   // mapped pinned
@@ -193,7 +193,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
-                      &e->bTA1, &e->bTA2, &e->bTA3, &e->bTQ, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
+                      &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
                       &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
@@ -252,13 +252,14 @@ int wrnn_finalize(wrnn_engine* e) {
     GET(up5, "upsample.up_layers.5.weight", 1, 1, 1, 17)
 
     // ---- loop weights ------------------------------------------------------------------------------------
-    const size_t nLoop = (size_t)3 * (3 * H) * H + (size_t)2 * H * H + (size_t)C * H + 3 * H + 3 * H + 1024 + kHop * kTaps + 64;
-    std::vector<float> hl(nLoop, 0.f);
+    std::vector<float> hl;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off += (n + 3) & ~(size_t)3; return o; };
     const size_t oWhh1 = take((size_t)3 * H * H), oWih2a = take((size_t)3 * H * H), oWhh2 = take((size_t)3 * H * H);
     const size_t oWfc1a = take((size_t)H * H), oWfc2a = take((size_t)H * H), oWfc3 = take((size_t)C * H);
-    const size_t ov1 = take(3 * H), owI0 = take(H), obhn1 = take(H), obhn2 = take(H), obfc3 = take(C), ocoef = take(kHop * kTaps);
+    const size_t ov1 = take(3 * H), ov2 = take(3 * H), ov3 = take(H), obhn1 = take(H), obhn2 = take(H), obfc3 = take(C),
+                 ocoef = take(kHop * kTaps);
+    hl.assign(off, 0.f);
     std::copy(r1hh->data.begin(), r1hh->data.end(), hl.begin() + oWhh1);
     std::copy(r2hh->data.begin(), r2hh->data.end(), hl.begin() + oWhh2);
     for (int r = 0; r < 3 * H; ++r)
@@ -273,15 +274,34 @@ int wrnn_finalize(wrnn_engine* e) {
     std::copy(f3w->data.begin(), f3w->data.end(), hl.begin() + oWfc3);
     std::copy(f3b->data.begin(), f3b->data.end(), hl.begin() + obfc3);
     for (int j = 0; j < H; ++j) {
-        hl[owI0 + j] = tI->data[(size_t)j * 112];
         hl[obhn1 + j] = r1bh->data[2 * H + j];
         hl[obhn2 + j] = r2bh->data[2 * H + j];
     }
+    // The I layer feeds rnn1 (W_ih1), rnn2 (through the residual x1 = xI + h1) and fc1 (x2 = xI + h1 + h2),
+    // always linearly, so its contribution is pre-multiplied in float64:
+    //   P1 = W_ih1 @ [I.weight | I.bias],  P2 = W_ih2[:, :512] @ [...],  P3 = fc1[:, :512] @ [...]
+    // column 0 (the previous sample) becomes the rank-1 coefficients v1/v2/v3 used inside the loop,
+    // columns 1..80 (mel) and 81..111 (aux a1[:31]) go into the per-frame conditioning projections.
+    std::vector<double> P1((size_t)3 * H * 113, 0.0), P2((size_t)3 * H * 113, 0.0), P3((size_t)H * 113, 0.0);
+    auto premul = [&](const float* W, int ldw, int rows, std::vector<double>& P) {
+        for (int r = 0; r < rows; ++r) {
+            double* pr = &P[(size_t)r * 113];
+            for (int k = 0; k < H; ++k) {
+                const double w = W[(size_t)r * ldw + k];
+                const float* ik = &tI->data[(size_t)k * 112];
+                for (int c = 0; c < 112; ++c) pr[c] += w * (double)ik[c];
+                pr[112] += w * (double)tIb->data[k];
+            }
+        }
+    };
+    premul(r1ih->data.data(), H, 3 * H, P1);
+    premul(r2ih->data.data(), H + kAux, 3 * H, P2);
+    premul(f1w->data.data(), H + kAux, H, P3);
     for (int r = 0; r < 3 * H; ++r) {
-        double a = 0.0;
-        for (int k = 0; k < H; ++k) a += (double)r1ih->data[(size_t)r * H + k] * (double)tI->data[(size_t)k * 112];
-        hl[ov1 + r] = (float)a;
+        hl[ov1 + r] = (float)P1[(size_t)r * 113];
+        hl[ov2 + r] = (float)P2[(size_t)r * 113];
     }
+    for (int j = 0; j < H; ++j) hl[ov3 + j] = (float)P3[(size_t)j * 113];
     build_coef(up1->data.data(), up3->data.data(), up5->data.data(), e->hcoef);
     std::copy(e->hcoef.begin(), e->hcoef.end(), hl.begin() + ocoef);
 
@@ -306,7 +326,7 @@ int wrnn_finalize(wrnn_engine* e) {
     float* base = e->wLoop.as<float>();
     e->dWhh1 = base + oWhh1; e->dWih2a = base + oWih2a; e->dWhh2 = base + oWhh2;
     e->dWfc1a = base + oWfc1a; e->dWfc2a = base + oWfc2a; e->dWfc3 = base + oWfc3;
-    e->dv1 = base + ov1; e->dwI0 = base + owI0; e->dbhn1 = base + obhn1; e->dbhn2 = base + obhn2;
+    e->dv1 = base + ov1; e->dv2 = base + ov2; e->dv3 = base + ov3; e->dbhn1 = base + obhn1; e->dbhn2 = base + obhn2;
     e->dbfc3 = base + obfc3; e->dcoef = base + ocoef;
 
     // ---- conditioning weights: BatchNorm folded (eval: (x-mean)*rsqrt(var+eps)*gamma+beta, eps=1e-5) ------
@@ -346,45 +366,35 @@ int wrnn_finalize(wrnn_engine* e) {
     std::copy(cout->data.begin(), cout->data.end(), hc.begin() + oW[kCondLayers - 1]);
     std::copy(coutb->data.begin(), coutb->data.end(), hc.begin() + oB[kCondLayers - 1]);
 
-    // projection matrices (unit-major, 4 values per hidden unit j): see engine_internal.h LoopParams
+    // Projection matrices, unit-major with 4 values per hidden unit j (engine_internal.h, LoopParams):
+    //   TA1[f][j] = {c1_r, c1_z, c1_n, c3}   TA2[f][j] = {c2_r, c2_z, c2_n, c4}      from aux[f] (128) + biases
+    //   TQ1[q][j] = {q1_r, q1_z, q1_n, q3}   TQ2[q][j] = {q2_r, q2_z, q2_n, 0}       from padded mel frame q (80)
+    // c1/q1: rnn1 input gates, c2/q2: rnn2 input gates, c3/q3: fc1, c4: fc2.  b_hh of the r,z gates is folded
+    // in (it is added outside the r* product); b_hn stays in the loop.  a1 drops its last channel (Q5).
     const size_t oMA1 = push((size_t)4 * H * 128), obA1 = push(4 * H), oMA2 = push((size_t)4 * H * 128), obA2 = push(4 * H);
-    const size_t oMA3 = push((size_t)H * 128), obA3 = push(H), oMQ = push((size_t)4 * H * kFeat);
-    {
-        // P = W_ih1 (1536x512) @ I.weight (512x112) in float64, plus W_ih1 @ I.bias
-        std::vector<double> P((size_t)3 * H * 112, 0.0), Pb(3 * H, 0.0);
-        for (int r = 0; r < 3 * H; ++r) {
-            const float* wr = &r1ih->data[(size_t)r * H];
-            double* pr = &P[(size_t)r * 112];
-            double pb = 0.0;
-            for (int k = 0; k < H; ++k) {
-                const double w = wr[k];
-                const float* ik = &tI->data[(size_t)k * 112];
-                for (int c = 0; c < 112; ++c) pr[c] += w * (double)ik[c];
-                pb += w * (double)tIb->data[k];
+    const size_t oMQ1 = push((size_t)4 * H * kFeat), oMQ2 = push((size_t)4 * H * kFeat);
+    for (int j = 0; j < H; ++j) {
+        for (int g = 0; g < 4; ++g) {
+            const size_t rowA1 = oMA1 + (size_t)(j * 4 + g) * 128, rowA2 = oMA2 + (size_t)(j * 4 + g) * 128;
+            const size_t rowQ1 = oMQ1 + (size_t)(j * 4 + g) * kFeat, rowQ2 = oMQ2 + (size_t)(j * 4 + g) * kFeat;
+            if (g < 3) {
+                const int r = g * H + j;
+                const double* p1 = &P1[(size_t)r * 113];
+                const double* p2 = &P2[(size_t)r * 113];
+                for (int c = 0; c < kAux - 1; ++c) { hc[rowA1 + c] = (float)p1[81 + c]; hc[rowA2 + c] = (float)p2[81 + c]; }
+                for (int c = 0; c < kFeat; ++c) { hc[rowQ1 + c] = (float)p1[1 + c]; hc[rowQ2 + c] = (float)p2[1 + c]; }
+                for (int c = 0; c < kAux; ++c) hc[rowA2 + kAux + c] = r2ih->data[(size_t)r * (H + kAux) + H + c];   // a2
+                hc[obA1 + j * 4 + g] = (float)(p1[112] + (double)r1bi->data[r] + (g < 2 ? (double)r1bh->data[r] : 0.0));
+                hc[obA2 + j * 4 + g] = (float)(p2[112] + (double)r2bi->data[r] + (g < 2 ? (double)r2bh->data[r] : 0.0));
+            } else {
+                const double* p3 = &P3[(size_t)j * 113];
+                for (int c = 0; c < kAux - 1; ++c) hc[rowA1 + c] = (float)p3[81 + c];
+                for (int c = 0; c < kFeat; ++c) hc[rowQ1 + c] = (float)p3[1 + c];
+                for (int c = 0; c < kAux; ++c) hc[rowA1 + 2 * kAux + c] = f1w->data[(size_t)j * (H + kAux) + H + c];   // a3
+                hc[obA1 + j * 4 + g] = (float)(p3[112] + (double)f1b->data[j]);
+                for (int c = 0; c < kAux; ++c) hc[rowA2 + 3 * kAux + c] = f2w->data[(size_t)j * (H + kAux) + H + c];   // a4
+                hc[obA2 + j * 4 + g] = f2b->data[j];
             }
-            Pb[r] = pb;
-        }
-        for (int j = 0; j < H; ++j) {
-            for (int g = 0; g < 4; ++g) {
-                const size_t rowA1 = oMA1 + (size_t)(j * 4 + g) * 128, rowQ = oMQ + (size_t)(j * 4 + g) * kFeat;
-                const size_t rowA2 = oMA2 + (size_t)(j * 4 + g) * 128;
-                if (g < 3) {
-                    const int r = g * H + j;
-                    for (int c = 0; c < kAux - 1; ++c) hc[rowA1 + c] = (float)P[(size_t)r * 112 + 81 + c];   // a1[:31], Q5
-                    for (int c = 0; c < kFeat; ++c) hc[rowQ + c] = (float)P[(size_t)r * 112 + 1 + c];
-                    hc[obA1 + j * 4 + g] = (float)(Pb[r] + (double)r1bi->data[r] + (g < 2 ? (double)r1bh->data[r] : 0.0));
-                    for (int c = 0; c < kAux; ++c) hc[rowA2 + kAux + c] = r2ih->data[(size_t)r * (H + kAux) + H + c];   // a2
-                    hc[obA2 + j * 4 + g] = r2bi->data[r] + (g < 2 ? r2bh->data[r] : 0.f);
-                } else {
-                    for (int c = 0; c < kAux - 1; ++c) hc[rowA1 + c] = tI->data[(size_t)j * 112 + 81 + c];
-                    for (int c = 0; c < kFeat; ++c) hc[rowQ + c] = tI->data[(size_t)j * 112 + 1 + c];
-                    hc[obA1 + j * 4 + g] = tIb->data[j];
-                    for (int c = 0; c < kAux; ++c) hc[rowA2 + 2 * kAux + c] = f1w->data[(size_t)j * (H + kAux) + H + c];  // a3
-                    hc[obA2 + j * 4 + g] = f1b->data[j];
-                }
-            }
-            for (int c = 0; c < kAux; ++c) hc[oMA3 + (size_t)j * 128 + 3 * kAux + c] = f2w->data[(size_t)j * (H + kAux) + H + c];  // a4
-            hc[obA3 + j] = f2b->data[j];
         }
     }
     CU(e->wCond.ensure(hc.size() * sizeof(float)));
@@ -392,7 +402,7 @@ int wrnn_finalize(wrnn_engine* e) {
     float* cb = e->wCond.as<float>();
     for (int i = 0; i < kCondLayers; ++i) { e->dCW[i] = cb + oW[i]; e->dCB[i] = cb + oB[i]; }
     e->dMA1 = cb + oMA1; e->dbA1 = cb + obA1; e->dMA2 = cb + oMA2; e->dbA2 = cb + obA2;
-    e->dMA3 = cb + oMA3; e->dbA3 = cb + obA3; e->dMQ = cb + oMQ;
+    e->dMQ1 = cb + oMQ1; e->dMQ2 = cb + oMQ2;
     e->finalized = true;
     return WRNN_OK;
 #undef GET
@@ -410,8 +420,8 @@ int run_conditioning(wrnn_engine* e, int n_utts, int ta_rows, int tq_rows) {
     CU(e->bAux.ensure((size_t)ta_rows * 128 * sizeof(float)));
     CU(e->bTA1.ensure((size_t)ta_rows * 4 * kRnn * sizeof(float)));
     CU(e->bTA2.ensure((size_t)ta_rows * 4 * kRnn * sizeof(float)));
-    CU(e->bTA3.ensure((size_t)ta_rows * kRnn * sizeof(float)));
-    CU(e->bTQ.ensure((size_t)tq_rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTQ1.ensure((size_t)tq_rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTQ2.ensure((size_t)tq_rows * 4 * kRnn * sizeof(float)));
     cudaStream_t st = e->stream;
     const UttDesc* du = e->bUtt.as<UttDesc>();
     CU(launch_im2col(e->bMel.as<float>(), du, n_utts, ta_rows, tq_rows, e->bX0.as<float>(), e->bMP.as<float>(), st));
@@ -428,9 +438,9 @@ int run_conditioning(wrnn_engine* e, int n_utts, int ta_rows, int tq_rows) {
     CU(launch_zero_rows(e->bAux.as<float>(), du, n_utts, st));
     CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA1, e->dbA1, nullptr, e->bTA1.as<float>(), ta_rows, 4 * kRnn, 128, 0, st));
     CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA2, e->dbA2, nullptr, e->bTA2.as<float>(), ta_rows, 4 * kRnn, 128, 0, st));
-    CU(launch_gemm_f32(e->bAux.as<float>(), e->dMA3, e->dbA3, nullptr, e->bTA3.as<float>(), ta_rows, kRnn, 128, 0, st));
-    CU(launch_gemm_f32(e->bMP.as<float>(), e->dMQ, nullptr, nullptr, e->bTQ.as<float>(), tq_rows, 4 * kRnn, kFeat, 0, st));
-    e->launches += 3 + 2 * kResBlocks + 1 + 4;
+    CU(launch_gemm_f32(e->bMP.as<float>(), e->dMQ1, nullptr, nullptr, e->bTQ1.as<float>(), tq_rows, 4 * kRnn, kFeat, 0, st));
+    CU(launch_gemm_f32(e->bMP.as<float>(), e->dMQ2, nullptr, nullptr, e->bTQ2.as<float>(), tq_rows, 4 * kRnn, kFeat, 0, st));
+    e->launches += 3 + 2 * kResBlocks + 1 + 4;   // im2col, conv_in, 20 res convs, conv_out, zero_rows, 4 projections
     return WRNN_OK;
 }
 
@@ -585,7 +595,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
 
     // ---- the loop: waves of <= kMaxFoldsPerLaunch folds -----------------------------------------------------
     rq->n_launches = 0;
-    const size_t words_per_fold = (size_t)6 * kRnn + e->Cpad + 2;
+    const size_t words_per_fold = (size_t)4 * kRnn + e->Cpad + 2;
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
     for (int w0 = 0; w0 < Btot; w0 += kMaxFoldsPerLaunch) {
@@ -598,15 +608,15 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         LoopParams p;
         memset(&p, 0, sizeof(p));
         p.Whh1 = e->dWhh1; p.Wih2a = e->dWih2a; p.Whh2 = e->dWhh2; p.Wfc1a = e->dWfc1a; p.Wfc2a = e->dWfc2a; p.Wfc3 = e->dWfc3;
-        p.v1 = e->dv1; p.wI0 = e->dwI0; p.bhn1 = e->dbhn1; p.bhn2 = e->dbhn2; p.bfc3 = e->dbfc3;
-        p.TA1 = e->bTA1.as<float4>(); p.TA2 = e->bTA2.as<float4>(); p.TA3 = e->bTA3.as<float>(); p.TQ = e->bTQ.as<float4>();
+        p.v1 = e->dv1; p.v2 = e->dv2; p.v3 = e->dv3; p.bhn1 = e->dbhn1; p.bhn2 = e->dbhn2; p.bfc3 = e->dbfc3;
+        p.TA1 = e->bTA1.as<float4>(); p.TA2 = e->bTA2.as<float4>(); p.TQ1 = e->bTQ1.as<float4>(); p.TQ2 = e->bTQ2.as<float4>();
         p.coef = e->dcoef;
         p.folds = e->bFolds.as<FoldDesc>() + w0;
         p.B = B; p.S = S; p.C = e->C; p.Cpad = e->Cpad; p.CR = e->CR; p.FB = FB; p.mode = e->mode;
         p.seed = rq->seed;
         unsigned long long* x = e->bExch.as<unsigned long long>();
-        p.bX1 = x; x += (size_t)B * kRnn; p.bH1 = x; x += (size_t)B * kRnn; p.bX2 = x; x += (size_t)B * kRnn;
-        p.bH2 = x; x += (size_t)B * kRnn; p.bF1 = x; x += (size_t)B * kRnn; p.bF2 = x; x += (size_t)B * kRnn;
+        p.bH1 = x; x += (size_t)B * kRnn; p.bH2 = x; x += (size_t)B * kRnn;
+        p.bF1 = x; x += (size_t)B * kRnn; p.bF2 = x; x += (size_t)B * kRnn;
         p.bLG = x; x += (size_t)B * e->Cpad; p.bX = x;
         p.samples = e->bSamples.as<float>() + (size_t)w0 * S;
         p.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;

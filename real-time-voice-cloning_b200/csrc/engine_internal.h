@@ -21,22 +21,23 @@ struct LoopParams {
     const float* Wfc1a;   // fc1.weight[:, :512]          [512][512]
     const float* Wfc2a;   // fc2.weight[:, :512]          [512][512]
     const float* Wfc3;    // fc3.weight                   [C][512]
-    const float* v1;      // rnn1.weight_ih_l0 @ I.weight[:, 0]   [1536]
-    const float* wI0;     // I.weight[:, 0]               [512]
+    const float* v1;      // rnn1.weight_ih_l0 @ I.weight[:, 0]          [1536]  (rank-1 term of the previous sample)
+    const float* v2;      // rnn2.weight_ih_l0[:, :512] @ I.weight[:, 0] [1536]
+    const float* v3;      // fc1.weight[:, :512] @ I.weight[:, 0]        [512]
     const float* bhn1;    // rnn1.bias_hh_l0[1024:]       [512]
     const float* bhn2;    // rnn2.bias_hh_l0[1024:]       [512]
     const float* bfc3;    // fc3.bias                     [C]
     // per-frame conditioning tables written by the front end (cond.cu)
-    const float4* TA1;    // [rows][512] {gi1_r, gi1_z, gi1_n, xI}    from aux a1 (+ biases)
-    const float4* TA2;    // [rows][512] {gi2_r, gi2_z, gi2_n, fc1}   from aux a2, a3 (+ biases)
-    const float* TA3;     // [rows][512] fc2                          from aux a4 (+ bias)
-    const float4* TQ;     // [rows][512] {gi1_r, gi1_z, gi1_n, xI}    from one padded mel frame
+    const float4* TA1;    // [rows][512] {gi1_r, gi1_z, gi1_n, fc1}   aux part + biases (incl. the I layer's share)
+    const float4* TA2;    // [rows][512] {gi2_r, gi2_z, gi2_n, fc2}
+    const float4* TQ1;    // [rows][512] {gi1_r, gi1_z, gi1_n, fc1}   share of one padded mel frame
+    const float4* TQ2;    // [rows][512] {gi2_r, gi2_z, gi2_n, 0}
     const float* coef;    // [200][kTaps] upsample interpolation weights (phase, padded-frame tap)
     const FoldDesc* folds;
     int B, S, C, Cpad, CR, FB, mode;
     unsigned long long seed;
     // exchange buffers, {value, tag} words
-    unsigned long long *bX1, *bH1, *bX2, *bH2, *bF1, *bF2;   // [B][512]
+    unsigned long long *bH1, *bH2, *bF1, *bF2;               // [B][512]
     unsigned long long* bLG;                                  // [B][Cpad]
     unsigned long long* bX;                                   // [B]
     float* samples;          // [B][S] value fed back at each step

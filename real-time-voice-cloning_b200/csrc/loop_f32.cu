@@ -6,8 +6,9 @@
 //    their rows of W_hh1, W_ih2[:, :512], W_hh2, fc1[:, :512], fc2[:, :512] and fc3 stay in shared
 //    memory (fp32, ~100 KB/SM) for the whole sequence -- weights are never re-read from HBM/L2.
 //  * the I layer, W_ih1 and every mel/aux column of the other layers are folded into per-frame
-//    conditioning tables by the front end (cond.cu), so a step has four dependent GEMV stages
-//    (W_ih2, fc1, fc2, fc3) plus two off-critical-path ones (W_hh1 h1, W_hh2 h2 for the next step).
+//    conditioning tables by the front end (cond.cu); the residuals x1 = xI + h1, x2 = x1 + h2 are
+//    expanded algebraically (W x1 = W xI + W h1), so only h1, h2, f1, f2 ever travel between SMs and a
+//    step is five exchanges: h1 -> [W_hh1;W_ih2;W_fc1] -> h2 -> [W_hh2;W_fc1] -> f1 -> fc2 -> f2 -> fc3 -> x.
 //  * activations travel between SMs as {value, step-tag} 8-byte words through L2 (common.cuh):
 //    consumers spin on the data itself; there is no grid barrier, fence or atomic on the path.
 //  * sampling (softmax + inverse CDF, or mixture-of-logistics) is fused; noise is Philox(step, fold,
@@ -26,48 +27,54 @@ constexpr int G = 3 * U;        // gate rows per CTA per GRU matrix (12)
 __device__ long long g_spin_deadline = 1500000000LL;   // SM clocks (~0.8 s); host-settable
 #define kSpinDeadline g_spin_deadline
 
+constexpr int RB = 2 * G + U;   // rows of stage B: W_hh1 (gh1 for the next step) | W_ih2a | W_fc1a        (28)
+constexpr int RC = G + U;       // rows of stage C: W_hh2 (gh2 for the next step) | W_fc1a                  (16)
+constexpr int LDT = RB;         // leading dimension of the per-chunk GEMV result buffer
+
 struct Smem {
-    float* Whh1;   // [G][512]   rows g*U+u
-    float* Wih2;   // [G][512]
-    float* Whh2;   // [G][512]
-    float* Wfc1;   // [U][512]
-    float* Wfc2;   // [U][512]
-    float* Wfc3;   // [CR][512]
+    float* WB;     // [RB][512]
+    float* WC;     // [RC][512]
+    float* WD;     // [U][512]   fc2[:, :512]
+    float* WE;     // [CR][512]  fc3
     float* act;    // [FB][512]  gathered activations of the current chunk
-    float* tmp;    // [FB][G]    GEMV results of the current chunk
+    float* tmp;    // [FB][LDT]  GEMV results of the current chunk
     float* h1;     // [B][U]
     float* h2;     // [B][U]
-    float* x1;     // [B][U]
+    float* p3;     // [B][U]     fc1 partial  W_fc1a h1
     float* gh1;    // [B][G]     W_hh1 h1 for the next step
     float* gh2;    // [B][G]
+    float4* c1;    // [B][U]     {gi1_r, gi1_z, gi1_n, fc1} conditioning of this step
+    float4* c2;    // [B][U]     {gi2_r, gi2_z, gi2_n, fc2}
     float* x;      // [B]        previous sample of every fold
-    float* v1;     // [3][U]     (W_ih1 W_I[:,0]) rows of my units
-    float* wI0;    // [U]
+    float* v1;     // [3][U]
+    float* v2;     // [3][U]
+    float* v3;     // [U]
     float* bhn1;   // [U]
     float* bhn2;   // [U]
-    float* bfc3;   // [CR]
+    float* bfc3;   // [8]
     float* coef;   // [200][kTaps]
 };
 
 __device__ __forceinline__ Smem carve(float* base, int B, int FB, int CR) {
     Smem s;
     float* p = base;
-    s.Whh1 = p; p += G * kRnn;
-    s.Wih2 = p; p += G * kRnn;
-    s.Whh2 = p; p += G * kRnn;
-    s.Wfc1 = p; p += U * kRnn;
-    s.Wfc2 = p; p += U * kRnn;
-    s.Wfc3 = p; p += CR * kRnn;
+    s.WB = p;   p += RB * kRnn;
+    s.WC = p;   p += RC * kRnn;
+    s.WD = p;   p += U * kRnn;
+    s.WE = p;   p += CR * kRnn;
     s.act = p;  p += FB * kRnn;
-    s.tmp = p;  p += FB * G;
+    s.tmp = p;  p += FB * LDT;
+    s.c1 = reinterpret_cast<float4*>(p); p += B * U * 4;
+    s.c2 = reinterpret_cast<float4*>(p); p += B * U * 4;
     s.h1 = p;   p += B * U;
     s.h2 = p;   p += B * U;
-    s.x1 = p;   p += B * U;
+    s.p3 = p;   p += B * U;
     s.gh1 = p;  p += B * G;
     s.gh2 = p;  p += B * G;
     s.x = p;    p += (B + 3) & ~3;
     s.v1 = p;   p += 3 * U;
-    s.wI0 = p;  p += U;
+    s.v2 = p;   p += 3 * U;
+    s.v3 = p;   p += U;
     s.bhn1 = p; p += U;
     s.bhn2 = p; p += U;
     s.bfc3 = p; p += 8;
@@ -290,30 +297,35 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
         const int row = i / (kRnn / 4), k4 = i % (kRnn / 4);
         const int g = row / U, u = row % U;
         const size_t src = ((size_t)(g * kRnn + j0 + u) * kRnn) / 4 + k4;
-        reinterpret_cast<float4*>(s.Whh1)[i] = reinterpret_cast<const float4*>(p.Whh1)[src];
-        reinterpret_cast<float4*>(s.Wih2)[i] = reinterpret_cast<const float4*>(p.Wih2a)[src];
-        reinterpret_cast<float4*>(s.Whh2)[i] = reinterpret_cast<const float4*>(p.Whh2)[src];
+        reinterpret_cast<float4*>(s.WB)[i] = reinterpret_cast<const float4*>(p.Whh1)[src];
+        reinterpret_cast<float4*>(s.WB)[G * (kRnn / 4) + i] = reinterpret_cast<const float4*>(p.Wih2a)[src];
+        reinterpret_cast<float4*>(s.WC)[i] = reinterpret_cast<const float4*>(p.Whh2)[src];
     }
     for (int i = tid; i < U * (kRnn / 4); i += NT) {
         const size_t src = ((size_t)j0 * kRnn) / 4 + i;
-        reinterpret_cast<float4*>(s.Wfc1)[i] = reinterpret_cast<const float4*>(p.Wfc1a)[src];
-        reinterpret_cast<float4*>(s.Wfc2)[i] = reinterpret_cast<const float4*>(p.Wfc2a)[src];
+        const float4 w1 = reinterpret_cast<const float4*>(p.Wfc1a)[src];
+        reinterpret_cast<float4*>(s.WB)[2 * G * (kRnn / 4) + i] = w1;
+        reinterpret_cast<float4*>(s.WC)[G * (kRnn / 4) + i] = w1;
+        reinterpret_cast<float4*>(s.WD)[i] = reinterpret_cast<const float4*>(p.Wfc2a)[src];
     }
     for (int i = tid; i < CR * (kRnn / 4); i += NT) {
         const int row = i / (kRnn / 4), cls = cta * CR + row;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cls < C) v = reinterpret_cast<const float4*>(p.Wfc3)[(size_t)cls * (kRnn / 4) + i % (kRnn / 4)];
-        reinterpret_cast<float4*>(s.Wfc3)[i] = v;
+        reinterpret_cast<float4*>(s.WE)[i] = v;
     }
-    if (tid < 3 * U) s.v1[tid] = p.v1[(tid / U) * kRnn + j0 + tid % U];
+    if (tid < 3 * U) {
+        s.v1[tid] = p.v1[(tid / U) * kRnn + j0 + tid % U];
+        s.v2[tid] = p.v2[(tid / U) * kRnn + j0 + tid % U];
+    }
     if (tid < U) {
-        s.wI0[tid] = p.wI0[j0 + tid];
+        s.v3[tid] = p.v3[j0 + tid];
         s.bhn1[tid] = p.bhn1[j0 + tid];
         s.bhn2[tid] = p.bhn2[j0 + tid];
     }
     if (tid < CR) s.bfc3[tid] = (cta * CR + tid < C) ? p.bfc3[cta * CR + tid] : 0.f;
     for (int i = tid; i < kHop * kTaps; i += NT) s.coef[i] = p.coef[i];
-    for (int i = tid; i < B * U; i += NT) { s.h1[i] = 0.f; s.h2[i] = 0.f; s.x1[i] = 0.f; }
+    for (int i = tid; i < B * U; i += NT) { s.h1[i] = 0.f; s.h2[i] = 0.f; s.p3[i] = 0.f; }
     for (int i = tid; i < B * G; i += NT) { s.gh1[i] = 0.f; s.gh2[i] = 0.f; }   // W_hh * 0
     for (int i = tid; i < B; i += NT) s.x[i] = 0.f;                              // x_0 = 0, fatchord_version.py:183
     __syncthreads();
@@ -324,7 +336,33 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
     for (int t = 0; t < p.S; ++t) {
         const uint32_t tag = (uint32_t)t + 1u;
 
-        // ---- A: wait x_{t-1}; GRU1 update for my units; publish x1, h1 ---------------------------------
+        // ---- conditioning of this step for my units (independent of the exchange: issued before the wait) ----
+        for (int e = tid; e < B * U; e += NT) {
+            const int b = e / U, j = j0 + e % U;
+            const FoldDesc fd = p.folds[b];
+            const int n = fd.n0 + t;
+            const bool valid = n < fd.N;                 // positions past the utterance are fold tail padding (Q9)
+            const int q0 = valid ? n / kHop : 0;
+            const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
+            float4 a1 = __ldg(p.TA1 + ra), a2 = __ldg(p.TA2 + ra);
+            if (valid) {
+                const float* cf = s.coef + (n - q0 * kHop) * kTaps;
+#pragma unroll
+                for (int d = 0; d < kTaps; ++d) {
+                    const float c = cf[d];
+                    if (c != 0.f) {
+                        const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
+                        const float4 q1 = __ldg(p.TQ1 + rq), q2 = __ldg(p.TQ2 + rq);
+                        a1.x = fmaf(c, q1.x, a1.x); a1.y = fmaf(c, q1.y, a1.y); a1.z = fmaf(c, q1.z, a1.z); a1.w = fmaf(c, q1.w, a1.w);
+                        a2.x = fmaf(c, q2.x, a2.x); a2.y = fmaf(c, q2.y, a2.y); a2.z = fmaf(c, q2.z, a2.z);
+                    }
+                }
+            }
+            s.c1[e] = a1;
+            s.c2[e] = a2;
+        }
+
+        // ---- A: wait x_{t-1}; GRU1 update for my units; publish h1 -------------------------------------------
         {
             int failed = 0;
             if (t > 0) {
@@ -336,98 +374,62 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
             }
             if (__syncthreads_or(failed)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
             for (int e = tid; e < B * U; e += NT) {
-                const int b = e / U, u = e % U, j = j0 + u;
-                const FoldDesc fd = p.folds[b];
-                const int n = fd.n0 + t;
-                const bool valid = n < fd.N;
-                const int q0 = valid ? n / kHop : 0;
-                float4 acc = __ldg(p.TA1 + (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j);
-                if (valid) {
-                    const float* cf = s.coef + (n - q0 * kHop) * kTaps;
-#pragma unroll
-                    for (int d = 0; d < kTaps; ++d) {
-                        const float c = cf[d];
-                        if (c != 0.f) {
-                            const float4 q = __ldg(p.TQ + (size_t)(fd.tq_row0 + q0 + d) * kRnn + j);
-                            acc.x = fmaf(c, q.x, acc.x); acc.y = fmaf(c, q.y, acc.y);
-                            acc.z = fmaf(c, q.z, acc.z); acc.w = fmaf(c, q.w, acc.w);
-                        }
-                    }
-                }
+                const int b = e / U, u = e % U;
                 const float x = s.x[b];
+                const float4 c = s.c1[e];
                 const float* gh = s.gh1 + b * G;
-                const float r = sigmoid_acc(fmaf(s.v1[0 * U + u], x, acc.x) + gh[0 * U + u]);
-                const float z = sigmoid_acc(fmaf(s.v1[1 * U + u], x, acc.y) + gh[1 * U + u]);
-                const float nn = tanhf(fmaf(s.v1[2 * U + u], x, acc.z) + r * (gh[2 * U + u] + s.bhn1[u]));
+                const float r = sigmoid_acc(fmaf(s.v1[0 * U + u], x, c.x) + gh[0 * U + u]);
+                const float z = sigmoid_acc(fmaf(s.v1[1 * U + u], x, c.y) + gh[1 * U + u]);
+                const float nn = tanhf(fmaf(s.v1[2 * U + u], x, c.z) + r * (gh[2 * U + u] + s.bhn1[u]));
                 const float h = (1.0f - z) * nn + z * s.h1[e];
-                const float xI = fmaf(s.wI0[u], x, acc.w);
-                const float x1 = xI + h;
                 s.h1[e] = h;
-                s.x1[e] = x1;
-                ll_store(p.bX1 + (size_t)b * kRnn + j, x1, tag);
-                ll_store(p.bH1 + (size_t)b * kRnn + j, h, tag);
+                ll_store(p.bH1 + (size_t)b * kRnn + j0 + u, h, tag);
             }
         }
 
-        // ---- B: gi2 = W_ih2[:, :512] x1 ; GRU2 update ; publish x2, h2 ------------------------------------
-        for (int c = 0; c < nchunks; ++c) {
-            const int b0 = c * FB, nb = min(FB, B - b0);
-            if (gather(p.bX1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
-            dots_any(single, s.Wih2, G, s.act, nb, s.tmp, G);
-            for (int e = tid; e < nb * U; e += NT) {
-                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
-                const FoldDesc fd = p.folds[b];
-                const int n = fd.n0 + t;
-                const float4 ta = __ldg(p.TA2 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
-                const float* gi = s.tmp + bl * G;
-                const float* gh = s.gh2 + b * G;
-                const float r = sigmoid_acc(gi[0 * U + u] + ta.x + gh[0 * U + u]);
-                const float z = sigmoid_acc(gi[1 * U + u] + ta.y + gh[1 * U + u]);
-                const float nn = tanhf(gi[2 * U + u] + ta.z + r * (gh[2 * U + u] + s.bhn2[u]));
-                const float h = (1.0f - z) * nn + z * s.h2[b * U + u];
-                s.h2[b * U + u] = h;
-                ll_store(p.bX2 + (size_t)b * kRnn + j, s.x1[b * U + u] + h, tag);
-                ll_store(p.bH2 + (size_t)b * kRnn + j, h, tag);
-            }
-            __syncthreads();
-        }
-        // ---- B2 (off the critical path): gh1 = W_hh1 h1 for step t+1 -----------------------------------------
+        // ---- B: [gh1' ; W_ih2a h1 ; W_fc1a h1] ; GRU2 update ; publish h2 --------------------------------------
         for (int c = 0; c < nchunks; ++c) {
             const int b0 = c * FB, nb = min(FB, B - b0);
             if (gather(p.bH1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
-            dots_any(single, s.Whh1, G, s.act, nb, s.gh1 + b0 * G, G);
-        }
-        // ---- C: f1 = relu(fc1[:, :512] x2 + PF1) ; publish ----------------------------------------------------
-        for (int c = 0; c < nchunks; ++c) {
-            const int b0 = c * FB, nb = min(FB, B - b0);
-            if (gather(p.bX2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
-            dots_any(single, s.Wfc1, U, s.act, nb, s.tmp, G);
+            dots_any(single, s.WB, RB, s.act, nb, s.tmp, LDT);
             for (int e = tid; e < nb * U; e += NT) {
-                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
-                const FoldDesc fd = p.folds[b];
-                const int n = fd.n0 + t;
-                const float4 ta = __ldg(p.TA2 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
-                ll_store(p.bF1 + (size_t)b * kRnn + j, fmaxf(s.tmp[bl * G + u] + ta.w, 0.f), tag);
+                const int bl = e / U, u = e % U, b = b0 + bl;
+                const float* r_ = s.tmp + bl * LDT;
+                const float x = s.x[b];
+                const float4 cc = s.c2[b * U + u];
+                const float* gh = s.gh2 + b * G;
+                const float r = sigmoid_acc(r_[G + 0 * U + u] + fmaf(s.v2[0 * U + u], x, cc.x) + gh[0 * U + u]);
+                const float z = sigmoid_acc(r_[G + 1 * U + u] + fmaf(s.v2[1 * U + u], x, cc.y) + gh[1 * U + u]);
+                const float nn = tanhf(r_[G + 2 * U + u] + fmaf(s.v2[2 * U + u], x, cc.z) + r * (gh[2 * U + u] + s.bhn2[u]));
+                const float h = (1.0f - z) * nn + z * s.h2[b * U + u];
+                s.h2[b * U + u] = h;
+                s.p3[b * U + u] = r_[2 * G + u];
+                ll_store(p.bH2 + (size_t)b * kRnn + j0 + u, h, tag);
             }
+            for (int e = tid; e < nb * G; e += NT) s.gh1[(b0 + e / G) * G + e % G] = s.tmp[(e / G) * LDT + e % G];
             __syncthreads();
         }
-        // ---- C2 (off the critical path): gh2 = W_hh2 h2 for step t+1 -----------------------------------------
+        // ---- C: [gh2' ; W_fc1a h2] ; f1 = relu(fc1) ; publish ----------------------------------------------------
         for (int c = 0; c < nchunks; ++c) {
             const int b0 = c * FB, nb = min(FB, B - b0);
             if (gather(p.bH2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
-            dots_any(single, s.Whh2, G, s.act, nb, s.gh2 + b0 * G, G);
+            dots_any(single, s.WC, RC, s.act, nb, s.tmp, LDT);
+            for (int e = tid; e < nb * U; e += NT) {
+                const int bl = e / U, u = e % U, b = b0 + bl;
+                const float v = s.p3[b * U + u] + s.tmp[bl * LDT + G + u] + fmaf(s.v3[u], s.x[b], s.c1[b * U + u].w);
+                ll_store(p.bF1 + (size_t)b * kRnn + j0 + u, fmaxf(v, 0.f), tag);
+            }
+            for (int e = tid; e < nb * G; e += NT) s.gh2[(b0 + e / G) * G + e % G] = s.tmp[(e / G) * LDT + e % G];
+            __syncthreads();
         }
-        // ---- D: f2 = relu(fc2[:, :512] f1 + PF2) ; publish ----------------------------------------------------
+        // ---- D: f2 = relu(fc2[:, :512] f1 + c4) ; publish -------------------------------------------------------
         for (int c = 0; c < nchunks; ++c) {
             const int b0 = c * FB, nb = min(FB, B - b0);
             if (gather(p.bF1, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
-            dots_any(single, s.Wfc2, U, s.act, nb, s.tmp, G);
+            dots_any(single, s.WD, U, s.act, nb, s.tmp, LDT);
             for (int e = tid; e < nb * U; e += NT) {
-                const int bl = e / U, u = e % U, b = b0 + bl, j = j0 + u;
-                const FoldDesc fd = p.folds[b];
-                const int n = fd.n0 + t;
-                const float pf2 = __ldg(p.TA3 + (size_t)(fd.ta_row0 + (n < fd.N ? n / kHop : fd.T)) * kRnn + j);
-                ll_store(p.bF2 + (size_t)b * kRnn + j, fmaxf(s.tmp[bl * G + u] + pf2, 0.f), tag);
+                const int bl = e / U, u = e % U, b = b0 + bl;
+                ll_store(p.bF2 + (size_t)b * kRnn + j0 + u, fmaxf(s.tmp[bl * LDT + u] + s.c2[b * U + u].w, 0.f), tag);
             }
             __syncthreads();
         }
@@ -436,11 +438,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
             const int b0 = c * FB, nb = min(FB, B - b0);
             if (gather(p.bF2, b0, nb, s.act, tag, p.abort_flag)) { if (tid == 0) atomicExch(p.abort_flag, 1); return; }
             if (cta * CR < C) {
-                dots_any(single, s.Wfc3, CR, s.act, nb, s.tmp, G);
+                dots_any(single, s.WE, CR, s.act, nb, s.tmp, LDT);
                 for (int e = tid; e < nb * CR; e += NT) {
                     const int bl = e / CR, r = e % CR, b = b0 + bl, cls = cta * CR + r;
                     if (cls < C) {
-                        const float v = s.tmp[bl * G + r] + s.bfc3[r];
+                        const float v = s.tmp[bl * LDT + r] + s.bfc3[r];
                         ll_store(p.bLG + (size_t)b * p.Cpad + cls, v, tag);
                         if (p.logits_out) p.logits_out[((size_t)b * p.S + t) * C + cls] = v;
                     }
@@ -463,7 +465,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
                     uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 0u), key);
                     const float u = u01(r.x);
                     int k;
-                    if (C == 512) k = sample_raw_warp<16>(row, tag, u, p.abort_flag);
+                    if (C == 256) k = sample_raw_warp<8>(row, tag, u, p.abort_flag);
+                    else if (C == 512) k = sample_raw_warp<16>(row, tag, u, p.abort_flag);
                     else k = sample_raw_warp<32>(row, tag, u, p.abort_flag);
                     if (k < 0) { failed = 1; break; }
                     xs = 2.0f * (float)k / ((float)C - 1.0f) - 1.0f;     // fatchord_version.py:228 (fp32, Q10)
@@ -484,8 +487,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_f32_kernel(LoopParams p) {
 }
 
 size_t loop_f32_smem_bytes(int B, int FB, int CR) {
-    size_t f = (size_t)3 * G * kRnn + 2 * U * kRnn + (size_t)CR * kRnn + (size_t)FB * kRnn + (size_t)FB * G +
-               (size_t)B * (3 * U + 2 * G) + ((B + 3) & ~3) + 3 * U + 3 * U + 8 + kHop * kTaps;
+    size_t f = (size_t)(RB + RC + U) * kRnn + (size_t)CR * kRnn + (size_t)FB * kRnn + (size_t)FB * LDT +
+               (size_t)B * (8 * U + 3 * U + 2 * G) + ((B + 3) & ~3) + 6 * U + 3 * U + 8 + kHop * kTaps;
     return f * sizeof(float);
 }
 
