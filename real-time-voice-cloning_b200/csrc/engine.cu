@@ -68,6 +68,7 @@ struct wrnn_engine {
     // grow-only work buffers
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
+    DevBuf wTc, bTcExch, bCS;   // tensor-core loop: per-CTA fp16 weight images, exchange buffers, per-sample conditioning
     int* dAbort = nullptr;
     int* hProgress = nullptr;   // mapped pinned
     int* dProgress = nullptr;
@@ -183,6 +184,8 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))   // profilers slow the loop down: let them widen the guard
         if (err == cudaSuccess) err = set_spin_deadline((long long)(atof(dl) * 1.9e6));
+    if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
+        if (err == cudaSuccess) err = set_tc_deadline((long long)(atof(dl) * 1.9e6));
     if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
     *out = e;
     return WRNN_OK;
@@ -194,7 +197,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -328,6 +331,54 @@ int wrnn_finalize(wrnn_engine* e) {
     e->dWfc1a = base + oWfc1a; e->dWfc2a = base + oWfc2a; e->dWfc3 = base + oWfc3;
     e->dv1 = base + ov1; e->dv2 = base + ov2; e->dv3 = base + ov3; e->dbhn1 = base + obhn1; e->dbhn2 = base + obhn2;
     e->dbfc3 = base + obfc3; e->dcoef = base + ocoef;
+
+    // ---- tensor-core loop: per-CTA fp16 weight images, already in the shared-memory layout of loop_tc.cu ----
+    // Stage tiles are K-major SWIZZLE_128B: per 64-column k-block, rows of 128 bytes, 16-byte chunk c of row r
+    // stored at chunk (c ^ (r & 7)).  Row order inside a stage groups the two hidden units of an epilogue thread.
+    if (C == 30 || C == 512 || C == 1024) {
+        const size_t img = loop_tc_weight_image_bytes();
+        std::vector<unsigned char> hw((size_t)kTcCtas * img, 0);
+        auto put = [&](unsigned char* stage, int nrows, int r, const float* src) {
+            for (int kb = 0; kb < kRnn / 64; ++kb)
+                for (int c = 0; c < 8; ++c) {
+                    __half* dst = reinterpret_cast<__half*>(stage + (size_t)kb * nrows * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+                    for (int i = 0; i < 8; ++i) dst[i] = __float2half_rn(src[kb * 64 + c * 8 + i]);
+                }
+        };
+        const float* Wih2a = hl.data() + oWih2a;
+        const float* Wfc1a = hl.data() + oWfc1a;
+        const float* Wfc2a = hl.data() + oWfc2a;
+        for (int cta = 0; cta < kTcCtas; ++cta) {
+            unsigned char* base_img = hw.data() + (size_t)cta * img;
+            unsigned char* sB = base_img;                           // 64 rows
+            unsigned char* sC = sB + (size_t)64 * 128 * 8;          // 32 rows
+            unsigned char* sD = sC + (size_t)32 * 128 * 8;          // 16 rows
+            unsigned char* sE = sD + (size_t)16 * 128 * 8;          // 16 (RAW) or 32 (MOL) rows
+            for (int up = 0; up < 4; ++up)
+                for (int u = 0; u < 2; ++u) {
+                    const int j = cta * kTcUnits + 2 * up + u;
+                    for (int gt = 0; gt < 3; ++gt) {
+                        put(sB, 64, 16 * up + 2 * gt + u, Wih2a + (size_t)(gt * H + j) * H);              // p2
+                        put(sB, 64, 16 * up + 8 + 2 * gt + u, r1hh->data.data() + (size_t)(gt * H + j) * H);  // gh1'
+                        put(sC, 32, 8 * up + 2 * gt + u, r2hh->data.data() + (size_t)(gt * H + j) * H);       // gh2'
+                    }
+                    put(sB, 64, 16 * up + 6 + u, Wfc1a + (size_t)j * H);                                   // p3
+                    put(sC, 32, 8 * up + 6 + u, Wfc1a + (size_t)j * H);                                    // q3
+                    put(sD, 16, 2 * up + u, Wfc2a + (size_t)j * H);
+                }
+            if (C == 30) {
+                if (cta == 0)
+                    for (int c = 0; c < 30; ++c) put(sE, 32, c, f3w->data.data() + (size_t)c * H);
+            } else {
+                const int cpu = C / (kTcCtas * 4);
+                for (int up = 0; up < 4; ++up)
+                    for (int i = 0; i < cpu; ++i)
+                        put(sE, 16, cpu * up + i, f3w->data.data() + (size_t)(cta * cpu * 4 + cpu * up + i) * H);
+            }
+        }
+        CU(e->wTc.ensure(hw.size()));
+        CU(cudaMemcpy(e->wTc.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+    }
 
     // ---- conditioning weights: BatchNorm folded (eval: (x-mean)*rsqrt(var+eps)*gamma+beta, eps=1e-5) ------
     std::vector<float> hc;
@@ -503,7 +554,10 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     if (!e || !rq) return WRNN_ERR_INVALID;
     if (!e->finalized) return fail(e, WRNN_ERR_NOT_LOADED, "Please load Wave-RNN in memory before using it");
     if (rq->n_utts < 1 || !rq->mels || !rq->T) return fail(e, WRNN_ERR_INVALID, "wrnn_generate: no utterances");
-    if (rq->precision != WRNN_PREC_F32) return fail(e, WRNN_ERR_INVALID, "wrnn_generate: precision not available in this build");
+    if (rq->precision != WRNN_PREC_F32 && rq->precision != WRNN_PREC_F16)
+        return fail(e, WRNN_ERR_INVALID, "wrnn_generate: precision not available in this build");
+    const bool use_tc = rq->precision == WRNN_PREC_F16;
+    if (use_tc && !e->wTc.p) return fail(e, WRNN_ERR_INVALID, "tensor-core loop supports RAW 9/10-bit and MOL only");
     CU(cudaSetDevice(e->device));
     const int n_utts = rq->n_utts;
     const bool partial = (rq->fold_begin != 0 || rq->fold_end != 0);
@@ -598,13 +652,53 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     const size_t words_per_fold = (size_t)4 * kRnn + e->Cpad + 2;
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
-    for (int w0 = 0; w0 < Btot; w0 += kMaxFoldsPerLaunch) {
-        const int B = std::min(kMaxFoldsPerLaunch, Btot - w0);
+    const int wave = use_tc ? kTcMaxFolds : kMaxFoldsPerLaunch;
+    for (int w0 = 0; w0 < Btot; w0 += wave) {
+        const int B = std::min(wave, Btot - w0);
+        CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
+        if (use_tc) {
+            // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
+            const int rows0 = (B + 1) / 2, Mg = rows0;
+            const size_t cs_bytes = (size_t)kTcGroups * S * Mg * 256 * 64;
+            if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
+            CU(e->bCS.ensure(cs_bytes));
+            CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
+                                  e->bFolds.as<FoldDesc>() + w0, B, rows0, S, Mg, e->bCS.as<float4>(), st));
+            const size_t actb = (size_t)kTcGroups * 128 * kRnn * sizeof(__half);
+            const size_t lgb = (size_t)kTcGroups * 128 * e->Cpad * sizeof(unsigned long long);
+            const size_t xb = (size_t)kTcGroups * 128 * sizeof(unsigned long long);
+            const size_t exch = 4 * actb + lgb + xb + 256;
+            CU(e->bTcExch.ensure(exch));
+            CU(cudaMemsetAsync(e->bTcExch.p, 0, exch, st));
+            unsigned char* xb0 = e->bTcExch.as<unsigned char>();
+            TcParams tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.wimg = e->wTc.as<unsigned char>();
+            tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
+            tp.CS = e->bCS.as<float4>(); tp.Mg = Mg;
+            tp.folds = e->bFolds.as<FoldDesc>() + w0;
+            tp.B = B; tp.rows0 = rows0; tp.S = S; tp.C = e->C; tp.Cpad = e->Cpad; tp.mode = e->mode;
+            tp.seed = rq->seed;
+            tp.H1 = reinterpret_cast<__half*>(xb0); tp.H2 = reinterpret_cast<__half*>(xb0 + actb);
+            tp.F1 = reinterpret_cast<__half*>(xb0 + 2 * actb); tp.F2 = reinterpret_cast<__half*>(xb0 + 3 * actb);
+            tp.bLG = reinterpret_cast<unsigned long long*>(xb0 + 4 * actb);
+            tp.bX = reinterpret_cast<unsigned long long*>(xb0 + 4 * actb + lgb);
+            tp.counters = reinterpret_cast<unsigned int*>(xb0 + 4 * actb + lgb + xb);
+            tp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+            tp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            tp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+            tp.progress = e->dProgress;
+            tp.abort_flag = e->dAbort;
+            alignas(64) unsigned char tmaps[4][128];
+            __half* acts[4] = {tp.H1, tp.H2, tp.F1, tp.F2};
+            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)kTcGroups * 128, kRnn, 128, 64));
+            CU(launch_loop_tc(tp, tmaps, st));
+            e->launches += 2;
+        } else {
         const int FB = loop_f32_pick_fb(B, e->CR, e->smem_limit);
         if (FB < 1) return fail(e, WRNN_ERR_INVALID, "shared memory budget exceeded");
         CU(e->bExch.ensure(words_per_fold * B * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(e->bExch.p, 0, words_per_fold * B * sizeof(unsigned long long), st));
-        CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
         LoopParams p;
         memset(&p, 0, sizeof(p));
         p.Whh1 = e->dWhh1; p.Wih2a = e->dWih2a; p.Whh2 = e->dWhh2; p.Wfc1a = e->dWfc1a; p.Wfc2a = e->dWfc2a; p.Wfc3 = e->dWfc3;
@@ -624,8 +718,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         p.progress = e->dProgress;
         p.abort_flag = e->dAbort;
         CU(launch_loop_f32(p, st));
-        CU(cudaEventRecord(e->ev[7], st));
         e->launches += 1;
+        }
+        CU(cudaEventRecord(e->ev[7], st));
         rq->n_launches += 1;
         // progress_callback(i, seq_len, b_size, gen_rate) -- fatchord_version.py:234-236
         if (rq->progress) {

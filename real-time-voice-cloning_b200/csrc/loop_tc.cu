@@ -1,0 +1,402 @@
+// loop_tc.cu -- the autoregressive sample loop on the 5th-gen tensor cores (fp16 operands, fp32 accumulate,
+// fp32 recurrent state): the batched-fold path (BASELINE configs 1, 3, 5).
+//
+// Same five-exchange step as loop_f32.cu, restructured for tcgen05:
+//  * 2 groups x 64 CTAs (one CTA per SM).  A group owns up to 128 folds (MMA M = 128: one fold per TMEM lane);
+//    each of its CTAs owns 8 hidden units of every layer.  Its weight rows -- [W_ih2a|W_fc1a|W_hh1] (stage B),
+//    [W_hh2|W_fc1a] (C), fc2 (D), fc3 (E) -- stay in shared memory as K-major SWIZZLE_128B tiles (fp16,
+//    ~144 KB) for the whole sequence and are the B operand of tcgen05.mma (N = 64/32/16/16|32).
+//  * activations h1, h2, f1, f2 travel as fp16 rows [fold][512] through L2.  A stage = publish my 8 columns,
+//    arrive on the group's counter (release), the producer thread acquires the counter, then TMA-loads the
+//    group's [128 x 512] activation matrix in eight [128 x 64] swizzled tiles through a 4-slot mbarrier ring;
+//    one thread issues 32 tcgen05.mma per stage into TMEM; 16 epilogue warps (thread = fold x 2 units) read the
+//    accumulator with tcgen05.ld and do the GRU / ReLU / sampling math in fp32.
+//  * conditioning arrives pre-interpolated per sample (cond.cu: expand_cond), 64 B per thread per step.
+//  * "soft abort": a wait that passes its deadline raises a flag; from then on every wait returns at once, so
+//    all warps still walk the same barriers and the kernel ends cleanly (never a hung GPU).
+#include "engine_internal.h"
+#include "sampling.cuh"
+#include "tc_common.cuh"
+
+namespace wrnn {
+
+__device__ long long g_tc_deadline = 1500000000LL;
+
+namespace {
+using namespace tc;
+
+constexpr int NEPI = 16;                    // epilogue warps
+constexpr int NT = (NEPI + 2) * 32;         // + TMA producer warp + MMA warp
+constexpr int kSlots = 4, kKB = 64, kNKB = kRnn / kKB;
+constexpr int kTileBytes = 128 * 128;       // one [128 rows x 64 fp16] activation tile
+constexpr int NB_ = 64, NC_ = 32, ND_ = 16; // MMA N per stage (E: 16 RAW / 32 MOL)
+constexpr int kWB = 0, kWC = kWB + NB_ * 128 * kNKB, kWD = kWC + NC_ * 128 * kNKB, kWE = kWD + ND_ * 128 * kNKB;
+constexpr int kWBytes = kWE + 32 * 128 * kNKB;          // 147456
+constexpr int kRing = kWBytes;                          // 4 x 16 KB
+constexpr int kBars = kRing + kSlots * kTileBytes;      // mbarriers + misc
+constexpr int kSmemBytes = kBars + 256;
+// TMEM columns
+constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kTmemCols = 256;
+
+struct Ctl {
+    uint64_t full[kSlots];
+    uint64_t empty[kSlots];
+    uint64_t accfull[4];
+    uint32_t tmem;
+    int abort_local;
+};
+
+__device__ __forceinline__ bool aborted(const TcParams& p, Ctl* c) {
+    return *reinterpret_cast<volatile int*>(&c->abort_local) != 0 || ld_volatile_i32(p.abort_flag) != 0;
+}
+__device__ __forceinline__ void raise_abort(const TcParams& p, Ctl* c) {
+    *reinterpret_cast<volatile int*>(&c->abort_local) = 1;
+    atomicExch(p.abort_flag, 1);
+}
+// All waits go through these: they return false (and everything keeps moving) once the abort flag is up.
+__device__ __forceinline__ bool wait_mbar(const TcParams& p, Ctl* c, uint64_t* bar, uint32_t parity) {
+    long long t0 = 0;
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++spins) & 31) == 0) {
+            if (aborted(p, c)) return false;
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool wait_counter(const TcParams& p, Ctl* c, const unsigned int* ctr, unsigned int want) {
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= want) return true;
+        if (((++spins) & 31) == 0) {
+            if (aborted(p, c)) return false;
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); return false; }
+        }
+    }
+}
+__device__ __forceinline__ bool wait_x(const TcParams& p, Ctl* c, const unsigned long long* w, uint32_t tag, float& v) {
+    long long t0 = 0;
+    int spins = 0;
+    while (true) {
+        const unsigned long long q = ll_load(w);
+        if (ll_tag(q) == tag) { v = ll_val(q); return true; }
+        if (((++spins) & 31) == 0) {
+            if (aborted(p, c)) { v = 0.f; return false; }
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); v = 0.f; return false; }
+        }
+    }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// epilogue threads only: named barrier, then one thread releases the group counter
+__device__ __forceinline__ void publish_arrive(unsigned int* ctr) {
+    asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NT, 1)
+wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
+                    const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem + kBars);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / kTcCtas, cta = blockIdx.x % kTcCtas;       // group, CTA inside the group
+    const int nrows = (g == 0) ? p.rows0 : p.B - p.rows0;                 // folds of my group
+    const int fold0 = (g == 0) ? 0 : p.rows0;                             // first fold (launch index) of my group
+    const bool has_e = (p.mode == 0) || (cta == 0);                        // MOL: only CTA 0 of a group runs fc3
+    const int NE = (p.mode == 0) ? 16 : 32;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)cta * kWBytes);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < kWBytes / 16; i += NT) dst[i] = src[i];
+        fence_proxy_async_smem();
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&ctl->accfull[i], 1);
+        ctl->abort_local = 0;
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&ctl->tmem, kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = ctl->tmem;
+    unsigned int* ctrs = p.counters + g * 4;     // H1, H2, F1, F2 of my group
+
+    if (warp == NEPI) {
+        // =================================== TMA producer ===================================================
+        if (lane == 0) {
+            const CUtensorMap* maps[4] = {&tmH1, &tmH2, &tmF1, &tmF2};
+            for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
+            uint32_t q = 0;
+            const int nph = has_e ? 4 : 3;
+            for (int t = 0; t < p.S; ++t) {
+                for (int ph = 0; ph < nph; ++ph) {
+                    const bool ok = wait_counter(p, ctl, ctrs + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
+                    fence_proxy_async();
+                    for (int kb = 0; kb < kNKB; ++kb, ++q) {
+                        const uint32_t slot = q % kSlots, round = q / kSlots;
+                        bool go = ok;
+                        if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
+                        if (go && !aborted(p, ctl)) {
+                            mbar_arrive_expect_tx(&ctl->full[slot], kTileBytes);
+                            tma_load_2d(smem + kRing + slot * kTileBytes, maps[ph], &ctl->full[slot], kb * kKB, g * 128);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == NEPI + 1) {
+        // =================================== MMA issuer =====================================================
+        if (lane == 0) {
+            const uint32_t wofs[4] = {kWB, kWC, kWD, kWE};
+            const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
+            const uint32_t acc[4] = {kAccB, kAccC, kAccD, kAccE};
+            uint32_t q = 0;
+            const int nph = has_e ? 4 : 3;
+            for (int t = 0; t < p.S; ++t) {
+                for (int ph = 0; ph < nph; ++ph) {
+                    const uint32_t idesc = umma_idesc_f16(128, (int)ncol[ph]);
+                    for (int kb = 0; kb < kNKB; ++kb, ++q) {
+                        const uint32_t slot = q % kSlots, round = q / kSlots;
+                        const bool ok = wait_mbar(p, ctl, &ctl->full[slot], round & 1);
+                        tcgen05_fence_after();
+                        if (ok) {
+                            const uint32_t a0 = smem_u32(smem + kRing + slot * kTileBytes);
+                            const uint32_t b0 = smem_u32(smem + wofs[ph] + kb * ncol[ph] * 128);
+#pragma unroll
+                            for (int j = 0; j < kKB / 16; ++j)
+                                umma_f16(tmem + acc[ph], umma_desc_sw128(a0 + j * 32), umma_desc_sw128(b0 + j * 32), idesc,
+                                         (kb | j) ? 1u : 0u);
+                        }
+                        umma_commit(&ctl->empty[slot]);
+                    }
+                    umma_commit(&ctl->accfull[ph]);
+                }
+            }
+        }
+    } else {
+        // =================================== epilogue warps =================================================
+        // thread = (fold row, unit pair up): TMEM lane = row, my units are 8*cta + 2*up + {0,1}
+        const int row = (warp & 3) * 32 + lane, up = warp >> 2;
+        const bool live = row < nrows;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int j0 = (g * 0 + cta) * kTcUnits + 2 * up;                 // first of my two hidden units
+        float v1[6], v2[6], v3[2], bh1[2], bh2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int gt = 0; gt < 3; ++gt) { v1[gt * 2 + u] = p.v1[gt * kRnn + j0 + u]; v2[gt * 2 + u] = p.v2[gt * kRnn + j0 + u]; }
+            v3[u] = p.v3[j0 + u]; bh1[u] = p.bhn1[j0 + u]; bh2[u] = p.bhn2[j0 + u];
+        }
+        float h1[2] = {0.f, 0.f}, h2[2] = {0.f, 0.f};
+        const FoldDesc fd = p.folds[fold0 + (live ? row : 0)];
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const size_t grow = (size_t)g * 128 + row;                          // row in the exchange buffers
+        __half* pH1 = p.H1 + grow * kRnn + j0;
+        __half* pH2 = p.H2 + grow * kRnn + j0;
+        __half* pF1 = p.F1 + grow * kRnn + j0;
+        __half* pF2 = p.F2 + grow * kRnn + j0;
+        const unsigned long long* pX = p.bX + grow;
+        const size_t cs_row = ((size_t)cta * 4 + up) * 4;                   // float4 index inside one (t,row) record
+        const size_t cs_rec = (size_t)kTcCtas * 4 * 4;                      // float4 per (t,row) record = 1024
+
+        for (int t = 0; t < p.S; ++t) {
+            const uint32_t par = (uint32_t)t & 1u;
+            // conditioning of this step (issued before the wait on x)
+            float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca, cc = ca, cd = ca;
+            if (live) {
+                const float4* cs = p.CS + (((size_t)g * p.S + t) * p.Mg + row) * cs_rec + cs_row;
+                ca = __ldcs(cs); cb = __ldcs(cs + 1); cc = __ldcs(cs + 2); cd = __ldcs(cs + 3);
+            }
+            // ---- A: x_{t-1}, GRU1 for my 2 units, publish h1 -----------------------------------------------
+            float x = 0.f;
+            if (t > 0 && live) wait_x(p, ctl, pX, (uint32_t)t, x);
+            float gh[8];
+            if (t > 0) { tmem_ld8(tlane + kAccB + 16 * up + 8, gh); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gh[i] = 0.f;
+            }
+            {
+                const float c1r[2] = {ca.x, ca.y}, c1z[2] = {ca.z, ca.w}, c1n[2] = {cb.x, cb.y};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float r = sigmoid_fast(fmaf(v1[0 + u], x, c1r[u]) + gh[0 + u]);
+                    const float z = sigmoid_fast(fmaf(v1[2 + u], x, c1z[u]) + gh[2 + u]);
+                    const float n = tanh_fast(fmaf(v1[4 + u], x, c1n[u]) + r * (gh[4 + u] + bh1[u]));
+                    h1[u] = (1.0f - z) * n + z * h1[u];
+                }
+                if (live) *reinterpret_cast<__half2*>(pH1) = __floats2half2_rn(h1[0], h1[1]);
+            }
+            tcgen05_fence_before();
+            publish_arrive(ctrs + 0);
+            // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 ----------------------------------------
+            float pb[8], p3[2];
+            wait_mbar(p, ctl, &ctl->accfull[0], par);
+            tcgen05_fence_after();
+            tmem_ld8(tlane + kAccB + 16 * up, pb);
+            if (t > 0) tmem_ld8(tlane + kAccC + 8 * up, gh);
+            tmem_ld_wait();
+            {
+                const float c2r[2] = {cb.z, cb.w}, c2z[2] = {cc.x, cc.y}, c2n[2] = {cc.z, cc.w};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float r = sigmoid_fast(pb[0 + u] + fmaf(v2[0 + u], x, c2r[u]) + gh[0 + u]);
+                    const float z = sigmoid_fast(pb[2 + u] + fmaf(v2[2 + u], x, c2z[u]) + gh[2 + u]);
+                    const float n = tanh_fast(pb[4 + u] + fmaf(v2[4 + u], x, c2n[u]) + r * (gh[4 + u] + bh2[u]));
+                    h2[u] = (1.0f - z) * n + z * h2[u];
+                    p3[u] = pb[6 + u];
+                }
+                if (live) *reinterpret_cast<__half2*>(pH2) = __floats2half2_rn(h2[0], h2[1]);
+            }
+            tcgen05_fence_before();
+            publish_arrive(ctrs + 1);
+            // ---- C: [gh2' | W_fc1a h2] ; f1 ; publish ---------------------------------------------------------
+            wait_mbar(p, ctl, &ctl->accfull[1], par);
+            tcgen05_fence_after();
+            tmem_ld8(tlane + kAccC + 8 * up, pb);
+            tmem_ld_wait();
+            {
+                const float f0 = fmaxf(p3[0] + pb[6] + fmaf(v3[0], x, cd.x), 0.f);
+                const float f1 = fmaxf(p3[1] + pb[7] + fmaf(v3[1], x, cd.y), 0.f);
+                if (live) *reinterpret_cast<__half2*>(pF1) = __floats2half2_rn(f0, f1);
+            }
+            tcgen05_fence_before();
+            publish_arrive(ctrs + 2);
+            // ---- D: fc2 ; publish -------------------------------------------------------------------------------
+            wait_mbar(p, ctl, &ctl->accfull[2], par);
+            tcgen05_fence_after();
+            {
+                float d[4];
+                tmem_ld4(tlane + kAccD + 2 * up, d);
+                tmem_ld_wait();
+                if (live) *reinterpret_cast<__half2*>(pF2) = __floats2half2_rn(fmaxf(d[0] + cd.z, 0.f), fmaxf(d[1] + cd.w, 0.f));
+            }
+            tcgen05_fence_before();
+            publish_arrive(ctrs + 3);
+            // ---- E: fc3 + sampling -------------------------------------------------------------------------------
+            if (p.mode == 1) {
+                // MOL: CTA 0 of the group has all 30 outputs of a fold in one TMEM lane: sample in-thread
+                if (cta == 0 && up == 0) {
+                    wait_mbar(p, ctl, &ctl->accfull[3], par);
+                    tcgen05_fence_after();
+                    float lg[32];
+                    tmem_ld8(tlane + kAccE + 0, lg); tmem_ld8(tlane + kAccE + 8, lg + 8);
+                    tmem_ld8(tlane + kAccE + 16, lg + 16); tmem_ld8(tlane + kAccE + 24, lg + 24);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 30; ++i) {
+                            lg[i] += p.bfc3[i];
+                            if (p.logits_out) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i];
+                        }
+                        float best = -INFINITY;
+                        int kbest = 0;
+#pragma unroll
+                        for (int blk = 0; blk < 3; ++blk) {
+                            const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, (uint32_t)blk), key);
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) {
+                                const int i = blk * 4 + w;
+                                if (i < 10) {
+                                    const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
+                                    const float sc = lg[i] - logf(-logf(um));
+                                    if (sc > best) { best = sc; kbest = i; }
+                                }
+                            }
+                        }
+                        float mean = 0.f, lsc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 10; ++i)
+                            if (i == kbest) { mean = lg[10 + i]; lsc = lg[20 + i]; }
+                        lsc = fmaxf(lsc, -32.23619130191664f);
+                        const uint4 r2 = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 2u), key);
+                        const float ul = 1e-5f + u01(r2.z) * (1.0f - 2e-5f);
+                        float xs = mean + expf(lsc) * (logf(ul) - logf(1.0f - ul));
+                        xs = fminf(fmaxf(xs, -1.0f), 1.0f);
+                        p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
+                        const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
+                        ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
+                    }
+                    tcgen05_fence_before();
+                }
+            } else {
+                // RAW: my CTA's classes of every fold -> exchange words; then one warp per assigned fold samples
+                wait_mbar(p, ctl, &ctl->accfull[3], par);
+                tcgen05_fence_after();
+                float d[4];
+                const int cpu = p.C / (kTcCtas * 4);                      // classes per (CTA, up): 2 (C=512) or 4 (C=1024)
+                tmem_ld4(tlane + kAccE + cpu * up, d);
+                tmem_ld_wait();
+                if (live) {
+                    for (int i = 0; i < cpu; ++i) {
+                        const int cls = cta * (cpu * 4) + cpu * up + i;
+                        const float v = d[i] + p.bfc3[cls];
+                        ll_store(p.bLG + grow * p.Cpad + cls, v, (uint32_t)t + 1u);
+                        if (p.logits_out) p.logits_out[((size_t)(fold0 + row) * p.S + t) * p.C + cls] = v;
+                    }
+                }
+                tcgen05_fence_before();
+                const int srow = cta + kTcCtas * warp;                    // warps 0,1 sample rows cta, cta+64
+                if (warp < 2 && srow < nrows && !aborted(p, ctl)) {
+                    const FoldDesc sfd = p.folds[fold0 + srow];
+                    const unsigned long long* lrow = p.bLG + ((size_t)g * 128 + srow) * p.Cpad;
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)sfd.fold, (uint32_t)sfd.utt, 0u), key);
+                    const float u = u01(r.x);
+                    int k = (p.C == 512) ? sample_raw_warp<16>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline)
+                                         : sample_raw_warp<32>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline);
+                    if (k < 0) { raise_abort(p, ctl); k = 0; }
+                    if (lane == 0) {
+                        const float xs = 2.0f * (float)k / ((float)p.C - 1.0f) - 1.0f;
+                        p.samples[(size_t)(fold0 + srow) * p.S + t] = xs;
+                        const float fed = p.forced ? p.forced[(size_t)(fold0 + srow) * p.S + t] : xs;
+                        ll_store(p.bX + (size_t)g * 128 + srow, fed, (uint32_t)t + 1u);
+                    }
+                }
+            }
+            if (blockIdx.x == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
+                *reinterpret_cast<volatile int*>(p.progress) = t;
+                __threadfence_system();
+            }
+        }
+    }
+    // ---- teardown ---------------------------------------------------------------------------------------------
+    if (aborted(p, ctl)) __nanosleep(200000);      // let any TMA still in flight land before the CTA goes away
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+cudaError_t set_tc_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc_deadline, &cycles, sizeof(cycles)); }
+size_t loop_tc_weight_image_bytes() { return kWBytes; }
+
+cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps /* 4 x CUtensorMap */, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
+    if (err != cudaSuccess) return err;
+    const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmaps);
+    TcParams pp = p;
+    void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
+    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel, dim3(kTcGroups * kTcCtas), dim3(NT), args,
+                                       kSmemBytes + 1024, stream);
+}
+
+}  // namespace wrnn

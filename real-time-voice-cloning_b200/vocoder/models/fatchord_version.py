@@ -215,12 +215,14 @@ class WaveRNN(object):
         return [wav[offsets[i]:offsets[i + 1]].copy() for i in range(len(arrs))]
 
     def generate_debug(self, mels, batched, target, overlap, forced=None, max_steps=0, want_logits=False,
-                       fold_begin=0, fold_end=0, seed=None, utt_index0=0):
+                       fold_begin=0, fold_end=0, seed=None, utt_index0=0, precision=None):
         """Parity hook: runs the loop and returns dict(samples (F,S), logits (F,S,C) or None).  `forced`
         (F,S) float32 replaces the fed-back samples (teacher forcing on the reference's samples)."""
         extra = dict(max_steps=max_steps, fold_begin=fold_begin, fold_end=fold_end, utt_index0=utt_index0)
         if seed is not None:
             extra["seed"] = seed
+        if precision is not None:
+            extra["precision"] = precision
         rq, arrs, _, _, keep = self._request([mels], batched, target, overlap, True, True, None, want_wav=False, **extra)
         T = arrs[0].shape[1]
         N = T * self.hop_length

@@ -20,3 +20,66 @@ def test_tc_gemm_self_test(model, N):
     got = model.debug_tc_gemm(A, W)
     want = A.astype(np.float32) @ W.astype(np.float32).T
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-4)
+
+
+# ---- the fp16 tensor-core loop ("bf16/fp16 weights stated separately" in the north_star) ---------------------
+# Measured on CPU by emulating fp16 rounding of weights and activations in the oracle: logits within ~4e-4
+# relative, ~99.94 % identical draws on the random-init model.  Gates used here: 1e-3 relative, 99.8 % draws.
+F16 = 1
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def test_tc_loop_raw_teacher_forced_vs_reference():
+    from oracle import wavernn_oracle as orc
+    from tests.util import golden, norm_mel
+    model, _ = make_model(seed=11, bits=9, mode="RAW")
+    g = golden("gen_raw9_batched.npz")
+    mel = norm_mel(int(g["mel_T"]), int(g["mel_seed"]))
+    ref_idx = g["index"].astype(np.int64)
+    B, Sm1 = ref_idx.shape
+    forced = np.zeros((B, Sm1 + 1), np.float32)
+    forced[:, :-1] = orc.label_to_float(ref_idx, 512)
+    out = model.generate_debug(mel, True, int(g["target"]), int(g["overlap"]), forced=forced, want_logits=True,
+                               seed=int(g["seed"]), precision=F16)
+    steps = g["logit_steps"]
+    err = _rel(out["logits"][:, steps], g["logits"])
+    mine = np.rint((out["samples"] + 1.0) * 511 / 2.0).astype(np.int64)
+    agree = float((mine[:, :-1] == ref_idx).mean())
+    print("fp16 loop: logits rel err %.2e, draw agreement %.5f" % (err, agree))
+    assert err < 1e-3
+    assert agree >= 0.998
+
+
+def test_tc_loop_mol_teacher_forced_vs_reference():
+    from tests.util import golden, norm_mel
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    g = golden("gen_mol_batched.npz")
+    mel = norm_mel(int(g["mel_T"]), int(g["mel_seed"]))
+    ref = g["samples"]
+    B, Sm1 = ref.shape
+    forced = np.zeros((B, Sm1 + 1), np.float32)
+    forced[:, :-1] = ref
+    out = model.generate_debug(mel, True, int(g["target"]), int(g["overlap"]), forced=forced, want_logits=True,
+                               seed=int(g["seed"]), precision=F16)
+    err = _rel(out["logits"][:, ::8], g["logits_sub"])
+    d = np.abs(out["samples"][:, :-1] - ref)
+    print("fp16 loop MOL: logits rel err %.2e, samples within 1e-3: %.5f" % (err, float((d < 1e-3).mean())))
+    assert err < 1e-3
+    assert float((d < 1e-3).mean()) >= 0.998
+
+
+def test_tc_loop_matches_f32_loop_many_folds():
+    """More folds than one group holds rows for in the small tests (exercises both groups, tail padding)."""
+    from tests.util import norm_mel
+    model, _ = make_model(seed=11, bits=9, mode="RAW")
+    mel = norm_mel(200, 4)
+    a = model.generate_debug(mel, True, 300, 50, want_logits=False, seed=5, max_steps=60)          # f32 loop
+    forced = np.pad(a["samples"], ((0, 0), (0, 400 - 60)))
+    b = model.generate_debug(mel, True, 300, 50, forced=forced, want_logits=True, seed=5, max_steps=60, precision=F16)
+    c = model.generate_debug(mel, True, 300, 50, forced=forced, want_logits=True, seed=5, max_steps=60)
+    assert a["samples"].shape[0] > 100
+    assert _rel(b["logits"], c["logits"]) < 1e-3
+    assert float((b["samples"] == c["samples"]).mean()) >= 0.998
