@@ -691,8 +691,28 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.abort_flag = e->dAbort;
             alignas(64) unsigned char tmaps[4][128];
             __half* acts[4] = {tp.H1, tp.H2, tp.F1, tp.F2};
-            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)kTcGroups * 128, kRnn, 128, 64));
+            const int box_rows = std::min(128, (rows0 + 7) & ~7);     // only the live folds travel
+            tp.tile_bytes = box_rows * 128;
+            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)kTcGroups * 128, kRnn, box_rows, 64));
+            const bool want_trace = getenv("WRNN_TC_TRACE") != nullptr;
+            if (want_trace) {
+                CU(e->bFloor.ensure(16 * 32 * sizeof(long long)));
+                CU(cudaMemsetAsync(e->bFloor.p, 0, 16 * 32 * sizeof(long long), st));
+                tp.trace = e->bFloor.as<long long>();
+            }
             CU(launch_loop_tc(tp, tmaps, st));
+            if (want_trace) {
+                std::vector<long long> tr(16 * 32);
+                CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (FILE* f = fopen(getenv("WRNN_TC_TRACE"), "w")) {
+                    for (int i = 0; i < 16; ++i) {
+                        for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", tr[i * 32 + j] ? tr[i * 32 + j] - tr[i * 32] : -1LL);
+                        fprintf(f, "\n");
+                    }
+                    fclose(f);
+                }
+            }
             e->launches += 2;
         } else {
         const int FB = loop_f32_pick_fb(B, e->CR, e->smem_limit);

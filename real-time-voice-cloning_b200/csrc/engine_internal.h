@@ -67,6 +67,7 @@ struct TcParams {
     int Mg;
     const FoldDesc* folds;
     int B, rows0, S, C, Cpad, mode;
+    int tile_bytes;              // bytes one TMA tile delivers: box_rows * 128
     unsigned long long seed;
     __half *H1, *H2, *F1, *F2;   // activation exchange, [kTcGroups*128][512] fp16
     unsigned int* counters;      // [kTcGroups][4] arrival counters (monotonic)
@@ -77,6 +78,7 @@ struct TcParams {
     const float* forced;
     int* progress;
     int* abort_flag;
+    long long* trace;            // optional [16 steps][32 slots] SM-clock timeline of CTA 0 (WRNN_TC_TRACE=1)
 };
 size_t loop_tc_weight_image_bytes();
 cudaError_t set_tc_deadline(long long cycles);

@@ -27,42 +27,52 @@ using namespace tc;
 
 constexpr int NEPI = 16;                    // epilogue warps
 constexpr int NT = (NEPI + 2) * 32;         // + TMA producer warp + MMA warp
-constexpr int kSlots = 4, kKB = 64, kNKB = kRnn / kKB;
+constexpr int kSlots = 4, kMaxSlots = 8, kKB = 64, kNKB = kRnn / kKB;   // ring: kSlots x 16 KB, re-cut into up to 8 smaller slots
 constexpr int kTileBytes = 128 * 128;       // one [128 rows x 64 fp16] activation tile
 constexpr int NB_ = 64, NC_ = 32, ND_ = 16; // MMA N per stage (E: 16 RAW / 32 MOL)
 constexpr int kWB = 0, kWC = kWB + NB_ * 128 * kNKB, kWD = kWC + NC_ * 128 * kNKB, kWE = kWD + ND_ * 128 * kNKB;
 constexpr int kWBytes = kWE + 32 * 128 * kNKB;          // 147456
 constexpr int kRing = kWBytes;                          // 4 x 16 KB
 constexpr int kBars = kRing + kSlots * kTileBytes;      // mbarriers + misc
-constexpr int kSmemBytes = kBars + 256;
+constexpr int kMolScratch = kBars + 256;                // [128 rows][4] {score, index} for the cooperative MOL draw
+constexpr int kBias = kMolScratch + 128 * 4 * 8;        // fc3 bias (MOL)
+// tcgen05.mma always reads 128 rows (16 KB) from a slot base; with slots shorter than that the last slot reads up to
+// 8 KB past the ring (into the control words: harmless garbage rows), so the allocation must cover ring + 72 KB
+constexpr int kSmemBytes = (kBias + 128 > kRing + 73728) ? (kBias + 128) : (kRing + 73728);
 // TMEM columns
 constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kTmemCols = 256;
 
 struct Ctl {
-    uint64_t full[kSlots];
-    uint64_t empty[kSlots];
+    uint64_t full[kMaxSlots];
+    uint64_t empty[kMaxSlots];
     uint64_t accfull[4];
     uint32_t tmem;
     int abort_local;
 };
 
-__device__ __forceinline__ bool aborted(const TcParams& p, Ctl* c) {
-    return *reinterpret_cast<volatile int*>(&c->abort_local) != 0 || ld_volatile_i32(p.abort_flag) != 0;
-}
+// Abort state: a CTA-local flag in shared memory (cheap to poll) mirrors the global flag (polled rarely: a
+// global load costs ~0.7 us and must stay off the wait paths).
+__device__ __forceinline__ bool aborted_local(Ctl* c) { return *reinterpret_cast<volatile int*>(&c->abort_local) != 0; }
+__device__ __forceinline__ bool aborted(const TcParams& p, Ctl* c) { return aborted_local(c); }
 __device__ __forceinline__ void raise_abort(const TcParams& p, Ctl* c) {
     *reinterpret_cast<volatile int*>(&c->abort_local) = 1;
     atomicExch(p.abort_flag, 1);
+}
+// slow path of every spin loop: returns true when the wait must be abandoned
+__device__ __noinline__ bool spin_check(const TcParams& p, Ctl* c, long long& t0) {
+    if (aborted_local(c)) return true;
+    if (ld_volatile_i32(p.abort_flag) != 0) { *reinterpret_cast<volatile int*>(&c->abort_local) = 1; return true; }
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); return true; }
+    return false;
 }
 // All waits go through these: they return false (and everything keeps moving) once the abort flag is up.
 __device__ __forceinline__ bool wait_mbar(const TcParams& p, Ctl* c, uint64_t* bar, uint32_t parity) {
     long long t0 = 0;
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (((++spins) & 31) == 0) {
-            if (aborted(p, c)) return false;
-            if (t0 == 0) t0 = clock64();
-            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); return false; }
-        }
+        if (((++spins) & 63) == 0 && aborted_local(c)) return false;
+        if ((spins & 4095) == 0 && spin_check(p, c, t0)) return false;
     }
     return true;
 }
@@ -73,11 +83,7 @@ __device__ __forceinline__ bool wait_counter(const TcParams& p, Ctl* c, const un
         unsigned int v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= want) return true;
-        if (((++spins) & 31) == 0) {
-            if (aborted(p, c)) return false;
-            if (t0 == 0) t0 = clock64();
-            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); return false; }
-        }
+        if (((++spins) & 255) == 0 && spin_check(p, c, t0)) return false;
     }
 }
 __device__ __forceinline__ bool wait_x(const TcParams& p, Ctl* c, const unsigned long long* w, uint32_t tag, float& v) {
@@ -86,12 +92,15 @@ __device__ __forceinline__ bool wait_x(const TcParams& p, Ctl* c, const unsigned
     while (true) {
         const unsigned long long q = ll_load(w);
         if (ll_tag(q) == tag) { v = ll_val(q); return true; }
-        if (((++spins) & 31) == 0) {
-            if (aborted(p, c)) { v = 0.f; return false; }
-            if (t0 == 0) t0 = clock64();
-            if (clock64() - t0 > g_tc_deadline) { raise_abort(p, c); v = 0.f; return false; }
-        }
+        if (((++spins) & 255) == 0 && spin_check(p, c, t0)) { v = 0.f; return false; }
     }
+}
+
+// optional timeline of one CTA (group 0, CTA 0), steps [kTraceStep0, kTraceStep0+kTraceSteps): SM clocks
+constexpr int kTraceStep0 = 64, kTraceSteps = 16, kTraceSlots = 32;
+__device__ __forceinline__ void trace(const TcParams& p, int t, int slot) {
+    if (p.trace && blockIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
+        p.trace[(t - kTraceStep0) * kTraceSlots + slot] = clock64();
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -100,10 +109,8 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2
 // epilogue threads only: named barrier, then one thread releases the group counter
 __device__ __forceinline__ void publish_arrive(unsigned int* ctr) {
     asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-    if (threadIdx.x == 0) {
-        __threadfence();
+    if (threadIdx.x == 0)   // release at gpu scope: cumulative over the stores the barrier above ordered before it
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    }
 }
 
 }  // namespace
@@ -129,17 +136,23 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         fence_proxy_async_smem();
     }
     if (tid == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
         for (int i = 0; i < 4; ++i) mbar_init(&ctl->accfull[i], 1);
         ctl->abort_local = 0;
         mbar_fence_init();
     }
+    if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (p.mode == 1 && tid < 30) ? p.bfc3[tid] : 0.f;
     if (warp == 0) tmem_alloc(&ctl->tmem, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = ctl->tmem;
     unsigned int* ctrs = p.counters + g * 4;     // H1, H2, F1, F2 of my group
+    // activation ring: as many slots as fit the 64 KB ring (a slot holds box_rows x 128 B, 1024-aligned); with
+    // <= 64 live folds per group all eight k-blocks of a stage are in flight at once
+    // (measured: packing shorter slots so that the 16 KB MMA read of one slot overlaps the TMA target of the next is
+    //  ~20 % slower per step than keeping the slots 16 KB apart, so the stride stays at the full tile)
+    constexpr uint32_t slot_bytes = kTileBytes, nslots = kSlots;
 
     if (warp == NEPI) {
         // =================================== TMA producer ===================================================
@@ -152,15 +165,17 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 for (int ph = 0; ph < nph; ++ph) {
                     const bool ok = wait_counter(p, ctl, ctrs + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
                     fence_proxy_async();
+                    trace(p, t, 12 + ph);
                     for (int kb = 0; kb < kNKB; ++kb, ++q) {
-                        const uint32_t slot = q % kSlots, round = q / kSlots;
+                        const uint32_t slot = q % nslots, round = q / nslots;
                         bool go = ok;
                         if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
                         if (go && !aborted(p, ctl)) {
-                            mbar_arrive_expect_tx(&ctl->full[slot], kTileBytes);
-                            tma_load_2d(smem + kRing + slot * kTileBytes, maps[ph], &ctl->full[slot], kb * kKB, g * 128);
+                            mbar_arrive_expect_tx(&ctl->full[slot], (uint32_t)p.tile_bytes);
+                            tma_load_2d(smem + kRing + slot * slot_bytes, maps[ph], &ctl->full[slot], kb * kKB, g * 128);
                         }
                     }
+                    trace(p, t, 16 + ph);
                 }
             }
         }
@@ -176,11 +191,13 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 for (int ph = 0; ph < nph; ++ph) {
                     const uint32_t idesc = umma_idesc_f16(128, (int)ncol[ph]);
                     for (int kb = 0; kb < kNKB; ++kb, ++q) {
-                        const uint32_t slot = q % kSlots, round = q / kSlots;
+                        const uint32_t slot = q % nslots, round = q / nslots;
+                        if (ph == 0 && kb < 4) trace(p, t, 24 + kb);
                         const bool ok = wait_mbar(p, ctl, &ctl->full[slot], round & 1);
                         tcgen05_fence_after();
+                        if (ph == 0 && kb < 4) trace(p, t, 20 + kb);
                         if (ok) {
-                            const uint32_t a0 = smem_u32(smem + kRing + slot * kTileBytes);
+                            const uint32_t a0 = smem_u32(smem + kRing + slot * slot_bytes);
                             const uint32_t b0 = smem_u32(smem + wofs[ph] + kb * ncol[ph] * 128);
 #pragma unroll
                             for (int j = 0; j < kKB / 16; ++j)
@@ -228,8 +245,10 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 ca = __ldcs(cs); cb = __ldcs(cs + 1); cc = __ldcs(cs + 2); cd = __ldcs(cs + 3);
             }
             // ---- A: x_{t-1}, GRU1 for my 2 units, publish h1 -----------------------------------------------
+            if (tid == 0) trace(p, t, 0);
             float x = 0.f;
             if (t > 0 && live) wait_x(p, ctl, pX, (uint32_t)t, x);
+            if (tid == 0) trace(p, t, 1);
             float gh[8];
             if (t > 0) { tmem_ld8(tlane + kAccB + 16 * up + 8, gh); tmem_ld_wait(); }
             else {
@@ -249,13 +268,16 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             }
             tcgen05_fence_before();
             publish_arrive(ctrs + 0);
+            if (tid == 0) trace(p, t, 2);
             // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 ----------------------------------------
             float pb[8], p3[2];
             wait_mbar(p, ctl, &ctl->accfull[0], par);
             tcgen05_fence_after();
+            if (tid == 0) trace(p, t, 3);
             tmem_ld8(tlane + kAccB + 16 * up, pb);
             if (t > 0) tmem_ld8(tlane + kAccC + 8 * up, gh);
             tmem_ld_wait();
+            if (tid == 0) trace(p, t, 28);
             {
                 const float c2r[2] = {cb.z, cb.w}, c2z[2] = {cc.x, cc.y}, c2n[2] = {cc.z, cc.w};
 #pragma unroll
@@ -268,11 +290,18 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 }
                 if (live) *reinterpret_cast<__half2*>(pH2) = __floats2half2_rn(h2[0], h2[1]);
             }
+            if (tid == 0) trace(p, t, 29);
             tcgen05_fence_before();
-            publish_arrive(ctrs + 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (tid == 0) {
+                trace(p, t, 30);
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctrs + 1) : "memory");
+            }
+            if (tid == 0) trace(p, t, 4);
             // ---- C: [gh2' | W_fc1a h2] ; f1 ; publish ---------------------------------------------------------
             wait_mbar(p, ctl, &ctl->accfull[1], par);
             tcgen05_fence_after();
+            if (tid == 0) trace(p, t, 5);
             tmem_ld8(tlane + kAccC + 8 * up, pb);
             tmem_ld_wait();
             {
@@ -282,9 +311,11 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             }
             tcgen05_fence_before();
             publish_arrive(ctrs + 2);
+            if (tid == 0) trace(p, t, 6);
             // ---- D: fc2 ; publish -------------------------------------------------------------------------------
             wait_mbar(p, ctl, &ctl->accfull[2], par);
             tcgen05_fence_after();
+            if (tid == 0) trace(p, t, 7);
             {
                 float d[4];
                 tmem_ld4(tlane + kAccD + 2 * up, d);
@@ -293,51 +324,62 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             }
             tcgen05_fence_before();
             publish_arrive(ctrs + 3);
+            if (tid == 0) trace(p, t, 8);
             // ---- E: fc3 + sampling -------------------------------------------------------------------------------
             if (p.mode == 1) {
-                // MOL: CTA 0 of the group has all 30 outputs of a fold in one TMEM lane: sample in-thread
-                if (cta == 0 && up == 0) {
+                // MOL (vocoder/distribution.py:104-140): CTA 0 of the group has all 30 outputs of a fold in one TMEM
+                // lane.  The four threads of a fold split the Gumbel draws (thread `up` owns Philox block `up`, i.e.
+                // mixtures 4up..4up+3), meet through shared memory, and thread up==2 (which also holds the logistic
+                // uniform, block 2 word 2) finishes the draw.
+                if (cta == 0) {
                     wait_mbar(p, ctl, &ctl->accfull[3], par);
                     tcgen05_fence_after();
+                    if (tid == 0) trace(p, t, 9);
                     float lg[32];
                     tmem_ld8(tlane + kAccE + 0, lg); tmem_ld8(tlane + kAccE + 8, lg + 8);
                     tmem_ld8(tlane + kAccE + 16, lg + 16); tmem_ld8(tlane + kAccE + 24, lg + 24);
                     tmem_ld_wait();
-                    if (live) {
+                    const float* sbias = reinterpret_cast<const float*>(smem + kBias);
+                    float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, (uint32_t)(up < 3 ? up : 2)), key);
+                    float best = -INFINITY;
+                    int kbest = 0;
 #pragma unroll
-                        for (int i = 0; i < 30; ++i) {
-                            lg[i] += p.bfc3[i];
-                            if (p.logits_out) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i];
+                    for (int w = 0; w < 4; ++w) {
+                        const int i = up * 4 + w;
+                        if (i < 10) {
+                            const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
+                            float li = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 10; ++q) if (q == i) li = lg[q] + sbias[q];
+                            const float sc = li - __logf(-__logf(um));
+                            if (sc > best) { best = sc; kbest = i; }
                         }
-                        float best = -INFINITY;
-                        int kbest = 0;
+                    }
+                    scratch[row * 4 + up] = make_float2(best, __int_as_float(kbest));
+                    asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");
+                    if (up == 2 && live) {
 #pragma unroll
-                        for (int blk = 0; blk < 3; ++blk) {
-                            const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, (uint32_t)blk), key);
-#pragma unroll
-                            for (int w = 0; w < 4; ++w) {
-                                const int i = blk * 4 + w;
-                                if (i < 10) {
-                                    const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
-                                    const float sc = lg[i] - logf(-logf(um));
-                                    if (sc > best) { best = sc; kbest = i; }
-                                }
-                            }
+                        for (int q = 0; q < 2; ++q) {          // candidates of up = 0, 1 come first (lower indices win ties)
+                            const float2 c = scratch[row * 4 + q];
+                            if (c.x >= best && !(c.x == best && __float_as_int(c.y) > kbest)) { best = c.x; kbest = __float_as_int(c.y); }
                         }
                         float mean = 0.f, lsc = 0.f;
 #pragma unroll
                         for (int i = 0; i < 10; ++i)
-                            if (i == kbest) { mean = lg[10 + i]; lsc = lg[20 + i]; }
+                            if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
                         lsc = fmaxf(lsc, -32.23619130191664f);
-                        const uint4 r2 = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 2u), key);
-                        const float ul = 1e-5f + u01(r2.z) * (1.0f - 2e-5f);
-                        float xs = mean + expf(lsc) * (logf(ul) - logf(1.0f - ul));
+                        const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
+                        float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
                         xs = fminf(fmaxf(xs, -1.0f), 1.0f);
                         p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
                         const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
                         ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
+                        if (p.logits_out)
+                            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
                     }
                     tcgen05_fence_before();
+                    if (tid == 0) trace(p, t, 10);
                 }
             } else {
                 // RAW: my CTA's classes of every fold -> exchange words; then one warp per assigned fold samples
