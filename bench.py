@@ -34,7 +34,26 @@ WORKLOADS = {
     "cfg3": ("MOL", 9, 60, True, 3000, 1500),
     "cfg3a": ("MOL", 9, 60, True, 6000, 1000),
     "cfg1x60": ("RAW", 9, 60, True, 6000, 1000),  # RAW at the cfg3 shape
+    # cfg4: cfg1 with weights pruned to ~90 % zero 1x4 groups (vocoder/pruner.py); CPU comparator = libwavernn port
+    "cfg4": ("RAW", 9, 10, True, 8000, 800),
+    # cfg5: 256 utterances of 5..20 s (numpy default_rng(2)), all folds pooled, sharded by utterance over the ranks
+    "cfg5": ("RAW", 9, 0, True, 6000, 1000),
 }
+PRUNED = {"cfg4"}
+MULTI = {"cfg5"}
+
+
+def workload_mels(wl, rank, world):
+    """Synthetic mels (synthesizer range [-4,4]) of this rank and the global index of its first utterance."""
+    from oracle import weights
+    mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
+    if wl in MULTI:
+        lens = np.random.default_rng(2).integers(5, 21, size=256)
+        idx = [i for i in range(256) if i % world == rank]
+        return [weights.synthetic_mel(80 * int(lens[i]), seed=100 + i) for i in idx], idx
+    return [weights.synthetic_mel(80 * seconds, seed=1 + rank)], [rank]
+
+
 PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -90,37 +109,53 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def cpu_baseline(wl, sd, mode, mel_norm, batched, target, overlap, seconds):
+    """CPU comparator on the host cores, bounded sample.  cfg4: the libwavernn C++ port (block-sparse engine, one
+    engine per thread as vocoder/libwavernn/inference.py:43-54); otherwise the torch-CPU port of the reference loop."""
+    if wl in PRUNED:
+        import tempfile
+        from oracle import libwavernn_io
+        from oracle.libwavernn_runner import build, time_threads
+        build(force=True)                                   # -march=native: rebuild on the box it runs on
+        path = os.path.join(tempfile.mkdtemp(), "model.bin")
+        libwavernn_io.write_bin(path, sd)
+        threads = os.cpu_count()
+        n, dt = time_threads(path, mel_norm, threads, 4)                     # calibration
+        frames = int(max(4, min(mel_norm.shape[1] - 1, 4 * seconds / max(dt, 1e-3))))
+        n, dt = time_threads(path, mel_norm, threads, frames)
+        return {"value": n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+                "sample": "libwavernn C++ port (oracle/libwavernn_port.cpp, -O2 -ffast-math -march=native), %d threads x %d frames "
+                          "each of the pruned model; steady-state samples/s (fold overlap not counted)" % (threads, frames)}
+    from oracle.torch_port import time_generate
+    r = time_generate(sd, mode, mel_norm, batched, target, overlap, threads=os.cpu_count(), time_budget_s=seconds, seed=1)
+    return {"value": r["out_samples"] / r["est_total_seconds"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
+            "sample": "%d of %d loop steps x %d folds (torch CPU port of the reference loop), conditioning in full; "
+                      "extrapolated linearly" % (r["steps_done"], r["steps_total"], r["folds"])}
+
+
 def reference_arm(args, wl):
-    """CPU arm: the reference's loop restated with torch CPU ops, bounded sample, all host threads."""
+    """CPU arm (rank 0 only): the reference's own CPU implementation of the path on the box's host cores -- the
+    torch-CPU port of its loop (or, for the pruned workload, the libwavernn C++ port) -- on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import weights
-    from oracle.torch_port import time_generate
-    import torch
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
     sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
-    mel = weights.synthetic_mel(80 * seconds, seed=1) / np.float32(4.0)
-    threads = os.cpu_count()
+    if wl in PRUNED:
+        sd = weights.prune_state_dict(sd, z=0.9)
+    mel = workload_mels(wl, 0, 1)[0][0] / np.float32(4.0)
     budget = float(args.cpu_seconds) / max(1, args.steps + args.warmup)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = time_generate(sd, mode, mel, batched, target, overlap, threads=threads, time_budget_s=budget, seed=1)
-        if i >= args.warmup:
-            vals.append(r)
-    est = float(np.mean([r["est_total_seconds"] for r in vals]))
-    out_samples = vals[0]["out_samples"]
-    value = out_samples / est
-    sample = "%d of %d loop steps x %d folds per step-sample, conditioning in full; extrapolated linearly" % (
-        vals[0]["steps_done"], vals[0]["steps_total"], vals[0]["folds"])
+    vals = [cpu_baseline(wl, sd, mode, mel, batched, target, overlap, budget) for _ in range(args.warmup + args.steps)][args.warmup:]
+    value = float(np.mean([v["value"] for v in vals]))
+    out_samples = (mel.shape[1] - 1) * 200
     line = {
         "impl": "reference", "metric": "vocoder_output_samples_per_sec", "value": value, "unit": "samples/s",
         "x_realtime": value / 16000.0, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": out_samples / value * 1e3, "higher_is_better": True,
+        "scaling": "strong" if wl in MULTI else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": dict(vals[-1], value=value),
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -128,8 +163,9 @@ def reference_arm(args, wl):
 
 def workload_config(wl):
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
-    return {"workload": "%s: WaveRNN fatchord %s%s, %d s synthetic 80-mel @16 kHz, %s" % (
-        wl, mode, (" %d-bit" % bits) if mode == "RAW" else "", seconds,
+    return {"workload": "%s: WaveRNN fatchord %s%s, %s synthetic 80-mel @16 kHz, %s" % (
+        wl, mode, (" %d-bit" % bits) if mode == "RAW" else "",
+        "256 utterances of 5-20 s" if wl in MULTI else "%d s" % seconds,
         ("batched target=%d overlap=%d" % (target, overlap)) if batched else "unbatched (single fold)"),
         "weights": "random-init rnn_dims=512 fc_dims=512 hop=200", "cache": "L2 flushed (256 MiB write) between timed steps"}
 
@@ -175,16 +211,18 @@ def main():
     hp.bits, hp.mode = bits, mode
     hparams.wavernn_fatchord.bits, hparams.wavernn_fatchord.mode = bits, mode   # infer_waveform reads the globals
     sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
+    if wl in PRUNED:
+        sd = weights.prune_state_dict(sd, z=0.9)
     model = inference.load_state(sd, devices=[local_rank], override_hp_fatchord=hp)
     model.precision = {"f32": _native.PREC_F32, "f16": _native.PREC_F16}[args.precision]
-    T = 80 * seconds
-    mel_raw = weights.synthetic_mel(T, seed=1 + rank)                       # synthesizer range [-4, 4]
-    mel_host = torch.from_numpy(mel_raw).pin_memory()
-    mel_dev = (mel_host / 4.0).cuda()
-    out_samples = (T - 1) * 200
+    mels_raw, utt_idx = workload_mels(wl, rank, world)                      # synthesizer range [-4, 4]
+    mels_host = [torch.from_numpy(m).pin_memory() for m in mels_raw]
+    mels_dev = [(m / 4.0).cuda() for m in mels_host]
+    out_samples = sum((m.shape[1] - 1) * 200 for m in mels_raw)           # of this rank
     wav_dev = torch.empty(out_samples, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     C = model.n_classes
+    import ctypes as Ct
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,10 +233,9 @@ def main():
     def step_resident():
         flush.fill_(1)
         torch.cuda.synchronize()
-        rq, arrs, wav, offsets, keep = model._request([np.zeros((80, T), np.float32)], batched, target, overlap,
-                                                      hp.mu_law, True, None, want_wav=False, utt_index0=rank)
-        import ctypes as Ct
-        ptr = (Ct.c_void_p * 1)(mel_dev.data_ptr())
+        rq, arrs, wav, offsets, keep = model._request([np.zeros(m.shape, np.float32) for m in mels_raw], batched, target,
+                                                      overlap, hp.mu_law, True, None, want_wav=False, utt_index0=utt_idx[0])
+        ptr = (Ct.c_void_p * len(mels_dev))(*[m.data_ptr() for m in mels_dev])
         rq.mels = Ct.cast(ptr, Ct.POINTER(Ct.c_void_p))
         rq.mels_on_device = 1
         rq.wav = wav_dev.data_ptr()
@@ -212,9 +249,13 @@ def main():
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        wav = inference.infer_waveform(mel_host.numpy(), normalize=True, batched=batched, target=target, overlap=overlap)
+        if len(mels_host) == 1:
+            wavs = [inference.infer_waveform(mels_host[0].numpy(), normalize=True, batched=batched, target=target, overlap=overlap)]
+        else:
+            wavs = inference.infer_waveforms([m.numpy() for m in mels_host], normalize=True, batched=batched, target=target,
+                                             overlap=overlap, utt_index0=utt_idx[0])
         dt = time.perf_counter() - t0
-        assert wav.shape[0] == out_samples
+        assert sum(w.shape[0] for w in wavs) == out_samples
         return dt * 1e3
 
     sampler = ClockSampler(local_rank)
@@ -239,17 +280,21 @@ def main():
     barrier()
     clocks = sampler.finish()
     e2e_total = float(sum(e2e_ms))
+    all_samples = out_samples
     if world > 1:
         t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = float(t[0]), float(t[1])
+        n = torch.tensor([out_samples], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        all_samples = int(n[0])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * out_samples * args.steps / (total_ms / 1e3)
-    e2e_value = world * out_samples * args.steps / (e2e_total / 1e3)
+    value = all_samples * args.steps / (total_ms / 1e3)
+    e2e_value = all_samples * args.steps / (e2e_total / 1e3)
     pk, pk_kind = peaks()
     F, S = last_t["n_folds"], last_t["n_steps"]
     flops = 2.0 * macs_per_row_step(C) * F * S
@@ -261,15 +306,16 @@ def main():
     line = {
         "metric": "vocoder_output_samples_per_sec", "value": value, "unit": "samples/s", "x_realtime": value / 16000.0,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if wl in MULTI else "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "f32" else "f16", "data": "synthetic",
         "precision_note": ("fp32 weights/FMA/state (parity mode)" if args.precision == "f32" else
                            "fp16 weights+activations on tcgen05, fp32 accumulate, fp32 recurrent state and conditioning; "
                            "teacher-forced logits 4.2e-4 rel, 100% identical draws on the golden run (tests/test_gpu_tc.py)"),
-        "config": dict(workload_config(wl), folds=F, loop_steps=S, per_gpu="one utterance per GPU, independent"),
+        "config": dict(workload_config(wl), folds=F, loop_steps=S, per_gpu=("256 utterances sharded by utterance" if wl in MULTI else "one utterance per GPU, independent"),
+                       pruned=("~90% zero 1x4 groups (pruner.py rule), run through the dense kernels" if wl in PRUNED else None)),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "x_realtime": e2e_value / 16000.0,
-                "h2d_bytes_per_step": int(mel_raw.nbytes), "d2h_bytes_per_step": int(out_samples * 8),
+                "h2d_bytes_per_step": int(sum(m.nbytes for m in mels_raw)), "d2h_bytes_per_step": int(out_samples * 8),
                 "ms_per_step": e2e_total / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -283,13 +329,7 @@ def main():
         "phases_ms": {k: last_t[k] for k in ("ms_h2d", "ms_cond", "ms_loop", "ms_post", "ms_d2h")},
     }
     if not args.no_cpu_baseline:
-        from oracle.torch_port import time_generate
-        r = time_generate(sd, mode, mel_raw / np.float32(4.0), batched, target, overlap, threads=os.cpu_count(),
-                          time_budget_s=args.cpu_seconds, seed=1)
-        line["cpu_baseline"] = {"value": r["out_samples"] / r["est_total_seconds"], "unit": "samples/s",
-                                "cores": r["threads"], "kind": "port",
-                                "sample": "%d of %d loop steps x %d folds (torch CPU port of the reference loop), "
-                                          "conditioning in full; extrapolated linearly" % (r["steps_done"], r["steps_total"], r["folds"])}
+        line["cpu_baseline"] = cpu_baseline(wl, sd, mode, mels_raw[0] / np.float32(4.0), batched, target, overlap, args.cpu_seconds)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
