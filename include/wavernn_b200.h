@@ -115,6 +115,10 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* req);
  * (200*T, 80) reconstructed from the engine's interpolation tables (debug / parity).                */
 int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames, float* mels_up);
 
+/* Same front end through the tensor-core path (cond_tc.cu: tcgen05 + TMA, hi/lo fp16 operand pairs, fp32
+ * accumulation) that the fp16 loop uses; returns aux (T,128).                                          */
+int wrnn_condition_tc(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames);
+
 /* Post chain only (fatchord_version.py:242-255) on host (F,S) float32 samples: xfade_and_unfold,
  * decode_mu_law, de_emphasis, truncation and fade-out on the GPU.  wav must hold (T-1)*200.          */
 int wrnn_postprocess(wrnn_engine* e, const float* samples, int64_t num_folds, int64_t S, int32_t batched,

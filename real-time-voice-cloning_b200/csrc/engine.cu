@@ -68,7 +68,9 @@ struct wrnn_engine {
     // grow-only work buffers
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
-    DevBuf wTc, bTcExch, bCS;   // tensor-core loop: per-CTA fp16 weight images, exchange buffers, per-sample conditioning
+    DevBuf wTc, bTcExch, bCS;
+    DevBuf wCondTc, bCondH;     // tensor-core front end: hi/lo fp16 weights (scaled by 2^8) and activation pairs
+    size_t oCondTc[kCondLayers + 4] = {};   // element offsets of each layer's W_hi inside wCondTc (W_lo follows)   // tensor-core loop: per-CTA fp16 weight images, exchange buffers, per-sample conditioning
     int* dAbort = nullptr;
     int* hProgress = nullptr;   // mapped pinned
     int* dProgress = nullptr;
@@ -178,7 +180,7 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     int smem = 0;
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     e->smem_limit = (size_t)smem;
-    if (err == cudaSuccess) err = cudaMalloc(&e->dAbort, sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc(&e->dAbort, 2 * sizeof(int));   // [0] loop abort flag, [1] front-end status
     if (err == cudaSuccess) err = cudaHostAlloc(&e->hProgress, sizeof(int), cudaHostAllocMapped);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->dProgress, e->hProgress, 0);
     for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
@@ -197,7 +199,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -448,6 +450,38 @@ int wrnn_finalize(wrnn_engine* e) {
             }
         }
     }
+    // hi/lo fp16 pairs of every front-end weight matrix, scaled by 2^8, for cond_tc.cu
+    {
+        std::vector<__half> ht;
+        auto pack = [&](const float* W, int N, int K, int Kpad, int idx) {
+            e->oCondTc[idx] = ht.size();
+            const size_t n = (size_t)N * Kpad;
+            ht.resize(ht.size() + 2 * n, __float2half_rn(0.f));
+            __half* hi = ht.data() + e->oCondTc[idx];
+            __half* lo = hi + n;
+            for (int r = 0; r < N; ++r)
+                for (int k = 0; k < K; ++k) {
+                    const float v = W[(size_t)r * K + k] * 256.0f;
+                    const __half h = __float2half_rn(v);
+                    hi[(size_t)r * Kpad + k] = h;
+                    lo[(size_t)r * Kpad + k] = __float2half_rn(v - __half2float(h));
+                }
+        };
+        {   // conv_in: [128][80][5] -> tap-major [128][5*128]
+            std::vector<float> w((size_t)128 * 640, 0.f);
+            for (int o = 0; o < 128; ++o)
+                for (int c = 0; c < kFeat; ++c)
+                    for (int j = 0; j < 5; ++j) w[(size_t)o * 640 + j * 128 + c] = hc[oW[0] + ((size_t)o * kFeat + c) * 5 + j];
+            pack(w.data(), 128, 640, 640, 0);
+        }
+        for (int i = 1; i < kCondLayers; ++i) pack(hc.data() + oW[i], 128, 128, 128, i);
+        pack(hc.data() + oMA1, 4 * H, 128, 128, kCondLayers + 0);
+        pack(hc.data() + oMA2, 4 * H, 128, 128, kCondLayers + 1);
+        pack(hc.data() + oMQ1, 4 * H, kFeat, 128, kCondLayers + 2);
+        pack(hc.data() + oMQ2, 4 * H, kFeat, 128, kCondLayers + 3);
+        CU(e->wCondTc.ensure(ht.size() * sizeof(__half)));
+        CU(cudaMemcpy(e->wCondTc.p, ht.data(), ht.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
     CU(e->wCond.ensure(hc.size() * sizeof(float)));
     CU(cudaMemcpy(e->wCond.p, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice));
     float* cb = e->wCond.as<float>();
@@ -464,6 +498,56 @@ int wrnn_finalize(wrnn_engine* e) {
 namespace {
 
 // Runs the conditioning front end for the utterances described by `utts` (already on device in bUtt).
+// Tensor-core front end (cond_tc.cu): same contractions, operands as hi/lo fp16 pairs, fp32 accumulation in TMEM.
+int run_conditioning_tc(wrnn_engine* e, int n_utts, int rows) {
+    const size_t n = (size_t)rows * 128;
+    CU(e->bCondH.ensure(8 * n * sizeof(__half) + (size_t)rows * sizeof(float) + 256));
+    for (int i = 0; i < 2; ++i) CU(e->bH[i].ensure(n * sizeof(float)));
+    CU(e->bAux.ensure(n * sizeof(float)));
+    CU(e->bTA1.ensure((size_t)rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTA2.ensure((size_t)rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTQ1.ensure((size_t)rows * 4 * kRnn * sizeof(float)));
+    CU(e->bTQ2.ensure((size_t)rows * 4 * kRnn * sizeof(float)));
+    cudaStream_t st = e->stream;
+    __half* hb = e->bCondH.as<__half>();
+    __half *MPhi = hb, *MPlo = hb + n, *Xhi = hb + 2 * n, *Xlo = hb + 3 * n, *Yhi = hb + 4 * n, *Ylo = hb + 5 * n, *Ahi = hb + 6 * n, *Alo = hb + 7 * n;
+    float* rowmask = reinterpret_cast<float*>(hb + 8 * n);
+    float* xf[2] = {e->bH[0].as<float>(), e->bH[1].as<float>()};
+    const __half* W = e->wCondTc.as<__half>();
+    auto whi = [&](int idx) { return W + e->oCondTc[idx]; };
+    auto wlo = [&](int idx, size_t cnt) { return W + e->oCondTc[idx] + cnt; };
+    CU(launch_mel_split(e->bMel.as<float>(), e->bUtt.as<UttDesc>(), n_utts, rows, MPhi, MPlo, rowmask, st));
+    GemmTcArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.scale = 1.0f / 256.0f; g.status = e->dAbort + 1;
+    // conv_in (k=5 as five row-shifted K blocks pairs) + BN + ReLU
+    g.N = 128; g.nkb = 10; g.kb_per_tap = 2; g.row_shift = 1; g.relu = 1; g.bias = e->dCB[0]; g.C = xf[0]; g.Chi = Xhi; g.Clo = Xlo;
+    CU(launch_gemm_tc_split(MPhi, MPlo, rows, 128, whi(0), wlo(0, (size_t)128 * 640), g, st));
+    g.nkb = 2; g.kb_per_tap = 2; g.row_shift = 0;
+    int cur = 0;
+    for (int i = 0; i < kResBlocks; ++i) {
+        g.relu = 1; g.bias = e->dCB[1 + 2 * i]; g.R = nullptr; g.C = nullptr; g.Chi = Yhi; g.Clo = Ylo;
+        CU(launch_gemm_tc_split(Xhi, Xlo, rows, 128, whi(1 + 2 * i), wlo(1 + 2 * i, 128 * 128), g, st));
+        g.relu = 0; g.bias = e->dCB[2 + 2 * i]; g.R = xf[cur]; g.C = xf[cur ^ 1]; g.Chi = Xhi; g.Clo = Xlo;
+        CU(launch_gemm_tc_split(Yhi, Ylo, rows, 128, whi(2 + 2 * i), wlo(2 + 2 * i, 128 * 128), g, st));
+        cur ^= 1;
+    }
+    g.relu = 0; g.bias = e->dCB[kCondLayers - 1]; g.R = nullptr; g.C = e->bAux.as<float>(); g.Chi = Ahi; g.Clo = Alo; g.rowmask = rowmask;
+    CU(launch_gemm_tc_split(Xhi, Xlo, rows, 128, whi(kCondLayers - 1), wlo(kCondLayers - 1, 128 * 128), g, st));
+    g.rowmask = nullptr; g.Chi = nullptr; g.Clo = nullptr; g.N = 4 * kRnn;
+    const size_t pn = (size_t)4 * kRnn * 128;
+    g.bias = e->dbA1; g.C = e->bTA1.as<float>();
+    CU(launch_gemm_tc_split(Ahi, Alo, rows, 128, whi(kCondLayers + 0), wlo(kCondLayers + 0, pn), g, st));
+    g.bias = e->dbA2; g.C = e->bTA2.as<float>();
+    CU(launch_gemm_tc_split(Ahi, Alo, rows, 128, whi(kCondLayers + 1), wlo(kCondLayers + 1, pn), g, st));
+    g.bias = nullptr; g.C = e->bTQ1.as<float>();
+    CU(launch_gemm_tc_split(MPhi, MPlo, rows, 128, whi(kCondLayers + 2), wlo(kCondLayers + 2, pn), g, st));
+    g.C = e->bTQ2.as<float>();
+    CU(launch_gemm_tc_split(MPhi, MPlo, rows, 128, whi(kCondLayers + 3), wlo(kCondLayers + 3, pn), g, st));
+    e->launches += 1 + 2 + 2 * kResBlocks + 4;
+    return WRNN_OK;
+}
+
 int run_conditioning(wrnn_engine* e, int n_utts, int ta_rows, int tq_rows) {
     CU(e->bX0.ensure((size_t)ta_rows * 400 * sizeof(float)));
     CU(e->bMP.ensure((size_t)tq_rows * kFeat * sizeof(float)));
@@ -508,7 +592,7 @@ int upload_utts(wrnn_engine* e, const float* const* mels, const int32_t* T, int 
         utts[i].tq_row0 = tq_rows;
         utts[i].pad_ = 0;
         mel_off += (long long)kFeat * T[i];
-        ta_rows += T[i] + 1;
+        ta_rows += T[i] + 2 * kPad;   // one row space for frames and padded frames: T frames, then the bias-only row T
         tq_rows += T[i] + 2 * kPad;
     }
     CU(e->bMel.ensure((size_t)mel_off * sizeof(float)));
@@ -585,7 +669,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     int rc = upload_utts(e, rq->mels, rq->T, n_utts, rq->mels_on_device, utts, ta_rows, tq_rows);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[1], st));
-    rc = run_conditioning(e, n_utts, ta_rows, tq_rows);
+    CU(cudaMemsetAsync(e->dAbort, 0, 2 * sizeof(int), st));
+    rc = use_tc ? run_conditioning_tc(e, n_utts, ta_rows) : run_conditioning(e, n_utts, ta_rows, tq_rows);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[2], st));
 
@@ -755,10 +840,11 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 std::this_thread::sleep_for(std::chrono::microseconds(100));
             }
         }
-        int aborted = 0;
-        CU(cudaMemcpyAsync(&aborted, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
+        int aborted[2] = {0, 0};
+        CU(cudaMemcpyAsync(aborted, e->dAbort, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (aborted) return fail(e, WRNN_ERR_TIMEOUT, "sample loop deadlock guard fired (an exchange word never arrived)");
+        if (aborted[1]) return fail(e, WRNN_ERR_TIMEOUT, "front-end tensor-core GEMM pipeline timed out");
+        if (aborted[0]) return fail(e, WRNN_ERR_TIMEOUT, "sample loop deadlock guard fired (an exchange word never arrived)");
         if (rq->progress) {
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             rq->progress(S - 1, S, B, (double)S / std::max(dt, 1e-9) * B / 1000.0, rq->progress_user);
@@ -803,7 +889,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     return WRNN_OK;
 }
 
-int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames, float* mels_up) {
+static int condition_impl(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames, float* mels_up, bool tc) {
     if (!e || !mel || T < 1) return WRNN_ERR_INVALID;
     if (!e->finalized) return fail(e, WRNN_ERR_NOT_LOADED, "Please load Wave-RNN in memory before using it");
     CU(cudaSetDevice(e->device));
@@ -812,10 +898,14 @@ int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frame
     const float* mels[1] = {mel};
     int rc = upload_utts(e, mels, &T, 1, 0, utts, ta_rows, tq_rows);
     if (rc) return rc;
-    rc = run_conditioning(e, 1, ta_rows, tq_rows);
+    CU(cudaMemsetAsync(e->dAbort, 0, 2 * sizeof(int), e->stream));
+    rc = tc ? run_conditioning_tc(e, 1, ta_rows) : run_conditioning(e, 1, ta_rows, tq_rows);
     if (rc) return rc;
+    int st2[2] = {0, 0};
+    CU(cudaMemcpyAsync(st2, e->dAbort, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (aux_frames) CU(cudaMemcpyAsync(aux_frames, e->bAux.p, (size_t)T * 128 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if (st2[1]) return fail(e, WRNN_ERR_TIMEOUT, "front-end tensor-core GEMM pipeline timed out");
     if (mels_up) {
         // debug view of the interpolation table: mels_up[n][c] = sum_d coef[n%200][d] * melpad[c][n/200 + d]
         for (int n = 0; n < T * kHop; ++n) {
@@ -831,6 +921,13 @@ int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frame
         }
     }
     return WRNN_OK;
+}
+
+int wrnn_condition(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames, float* mels_up) {
+    return condition_impl(e, mel, T, aux_frames, mels_up, false);
+}
+int wrnn_condition_tc(wrnn_engine* e, const float* mel, int32_t T, float* aux_frames) {
+    return condition_impl(e, mel, T, aux_frames, nullptr, true);
 }
 
 int wrnn_postprocess(wrnn_engine* e, const float* samples, int64_t num_folds, int64_t S, int32_t batched, int32_t overlap,

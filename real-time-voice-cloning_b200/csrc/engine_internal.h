@@ -102,6 +102,27 @@ cudaError_t launch_gemm_f32(const float* A, const float* W, const float* bias, c
                             int M, int N, int K, int relu, cudaStream_t stream);
 cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream);
 
+// ---- conditioning contractions on tensor cores (cond_tc.cu) ------------------------------------------------
+struct GemmTcArgs {
+    int M, N;            // output rows (frames) and columns (multiple of 128)
+    int nkb;             // K blocks of 64 columns
+    int kb_per_tap;      // K blocks per convolution tap (== nkb for a plain GEMM)
+    int row_shift;       // A rows advance by row_shift per tap (k=5 convolution without im2col)
+    int relu;
+    float scale;         // applied to the accumulator before the bias (weights are pre-scaled by 1/scale)
+    const float* bias;   // [N] or null
+    const float* R;      // residual [M][N] fp32 or null
+    const float* rowmask;// [M] or null: output rows are multiplied by it (bias-only rows of an utterance -> 0)
+    float* C;            // fp32 output [M][N] or null
+    __half* Chi;         // hi/lo fp16 output [M][N] or null (operand of the next layer)
+    __half* Clo;
+    int* status;
+};
+cudaError_t launch_gemm_tc_split(const __half* Ahi, const __half* Alo, int Arows, int Acols, const __half* Whi, const __half* Wlo,
+                                 const GemmTcArgs& args, cudaStream_t stream);
+cudaError_t launch_mel_split(const float* mel, const UttDesc* utts, int n_utts, int rows, __half* hi, __half* lo, float* rowmask,
+                             cudaStream_t stream);
+
 // ---- post chain (post.cu) ----------------------------------------------------------------------------
 struct PostUtt {
     long long samp_off;   // float offset of this utterance's (F,S) block in the samples buffer

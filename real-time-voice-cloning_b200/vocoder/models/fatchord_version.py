@@ -260,6 +260,15 @@ class WaveRNN(object):
             _raise(self._lib, self._h, rc)
         return up, aux
 
+    def conditioning_tc(self, mel):
+        """MelResNet output (T,128) computed by the tensor-core front end (cond_tc.cu)."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        aux = np.zeros((mel.shape[1], 128), np.float32)
+        rc = self._lib.wrnn_condition_tc(self._h, mel.ctypes.data, mel.shape[1], aux.ctypes.data)
+        if rc != _native.OK:
+            _raise(self._lib, self._h, rc)
+        return aux
+
     def pad_tensor(self, x, pad, side='both'):
         """fatchord_version.py:275-288 on a (b, t, c) torch tensor (same device as x)."""
         import torch

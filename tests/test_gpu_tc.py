@@ -83,3 +83,17 @@ def test_tc_loop_matches_f32_loop_many_folds():
     assert a["samples"].shape[0] > 100
     assert _rel(b["logits"], c["logits"]) < 1e-3
     assert float((b["samples"] == c["samples"]).mean()) >= 0.998
+
+
+def test_tensor_core_front_end_matches_reference():
+    """cond_tc.cu (tcgen05, hi/lo fp16 operand pairs) against the reference's MelResNet output and the fp32 SIMT path."""
+    from tests.util import golden, norm_mel
+    model, _ = make_model(seed=11, bits=9, mode="RAW")
+    g = golden("cond_raw9.npz")
+    mel = norm_mel(int(g["mel_T"]), int(g["mel_seed"]))
+    aux_tc = model.conditioning_tc(mel)
+    _, aux_f32 = model.conditioning(mel)
+    np.testing.assert_allclose(aux_tc, g["aux_frames"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(aux_tc, aux_f32, rtol=0, atol=2e-5)
+    mel2 = norm_mel(300, 9)                      # more than two 128-row tiles
+    np.testing.assert_allclose(model.conditioning_tc(mel2), model.conditioning(mel2)[1], rtol=0, atol=2e-5)
