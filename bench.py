@@ -177,12 +177,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="f16", choices=["f32", "f16"],
+    ap.add_argument("--precision", default=None, choices=["f32", "f16", "sparse"],
                     help="f16: tensor-core loop (fp16 operands, fp32 accumulate/state); f32: parity-mode loop")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = args.workload
+    if args.precision is None:      # defaults: tensor-core loop; pruned model -> block-sparse cluster loop; single fold -> fp32 loop
+        args.precision = "sparse" if wl in PRUNED else ("f32" if not WORKLOADS[wl][3] else "f16")
     if args.impl == "reference":
         return reference_arm(args, wl)
 
@@ -214,7 +216,7 @@ def main():
     if wl in PRUNED:
         sd = weights.prune_state_dict(sd, z=0.9)
     model = inference.load_state(sd, devices=[local_rank], override_hp_fatchord=hp)
-    model.precision = {"f32": _native.PREC_F32, "f16": _native.PREC_F16}[args.precision]
+    model.precision = {"f32": _native.PREC_F32, "f16": _native.PREC_F16, "sparse": _native.PREC_SPARSE_F32}[args.precision]
     mels_raw, utt_idx = workload_mels(wl, rank, world)                      # synthesizer range [-4, 4]
     mels_host = [torch.from_numpy(m).pin_memory() for m in mels_raw]
     mels_dev = [(m / 4.0).cuda() for m in mels_host]
@@ -302,13 +304,16 @@ def main():
     achieved = flops / loop_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
     floor = model.barrier_floor(20000)
-    n_exch = 6 if mode == "RAW" else 5       # h1, h2, f1, f2, (logits,) x per step
+    floor["cluster_us"] = model.cluster_floor(16, 20000)
+    n_exch = 5 if (mode == "MOL" or args.precision == "sparse") else 6       # h1, h2, f1, f2, (logits,) x per step
+    floor_us = {"f32": floor["ll_us"], "f16": floor["counter_us"], "sparse": floor["cluster_us"]}[args.precision]
     line = {
         "metric": "vocoder_output_samples_per_sec", "value": value, "unit": "samples/s", "x_realtime": value / 16000.0,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if wl in MULTI else "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else "f16", "data": "synthetic",
+        "dtype": "f16" if args.precision == "f16" else "f32", "data": "synthetic",
         "precision_note": ("fp32 weights/FMA/state (parity mode)" if args.precision == "f32" else
+                           "fp32 block-sparse (1x4 groups) cluster-local loop" if args.precision == "sparse" else
                            "fp16 weights+activations on tcgen05, fp32 accumulate, fp32 recurrent state and conditioning; "
                            "teacher-forced logits 4.2e-4 rel, 100% identical draws on the golden run (tests/test_gpu_tc.py)"),
         "config": dict(workload_config(wl), folds=F, loop_steps=S, per_gpu=("256 utterances sharded by utterance" if wl in MULTI else "one utterance per GPU, independent"),
@@ -319,13 +324,14 @@ def main():
                 "ms_per_step": e2e_total / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "wrnn_loop_f32_kernel" if args.precision == "f32" else "wrnn_loop_tc_kernel",
+                     "traffic": None, "kernel": {"f32": "wrnn_loop_f32_kernel", "f16": "wrnn_loop_tc_kernel", "sparse": "wrnn_loop_sparse_kernel"}[args.precision],
                      "peak_source": pk_kind + " bf16_tflops_sustained", "kernel_ms": loop_s * 1e3,
                      "algorithmic_flops_per_launch": flops},
         "loop": {"us_per_step": loop_s * 1e6 / S, "exchanges_per_step": n_exch, "exchange_floor_us": floor["ll_us"],
-                 "counter_barrier_floor_us": floor["counter_us"],
-                 "step_over_floor": (loop_s * 1e6 / S) / (n_exch * (floor["ll_us"] if args.precision == "f32" else floor["counter_us"])),
-                 "floor_used": "flag-in-data exchange" if args.precision == "f32" else "fence+atomic counter barrier"},
+                 "counter_barrier_floor_us": floor["counter_us"], "cluster16_exchange_floor_us": floor["cluster_us"],
+                 "step_over_floor": (loop_s * 1e6 / S) / (n_exch * floor_us),
+                 "floor_used": {"f32": "flag-in-data exchange through L2", "f16": "fence+atomic counter barrier through L2",
+                                "sparse": "DSMEM stores + cluster barrier (16 CTAs)"}[args.precision]},
         "phases_ms": {k: last_t[k] for k in ("ms_h2d", "ms_cond", "ms_loop", "ms_post", "ms_d2h")},
     }
     if not args.no_cpu_baseline:

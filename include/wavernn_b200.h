@@ -135,6 +135,10 @@ int wrnn_xfade_unfold(wrnn_engine* e, const double* y, int64_t num_folds, int64_
  * measured grid-barrier floor".                                                                      */
 int wrnn_barrier_floor(wrnn_engine* e, int32_t rounds, float* ll_us, float* counter_us);
 
+/* Floor of one cluster-local exchange (DSMEM stores into every peer + hardware cluster barrier), microseconds per
+ * round, for a cluster of `cluster_size` CTAs: the exchange the block-sparse loop uses.                          */
+int wrnn_cluster_floor(wrnn_engine* e, int32_t cluster_size, int32_t rounds, float* us);
+
 /* Self-test of the tensor-core building blocks (TMA 128B-swizzle load, tcgen05.mma, TMEM load):
  * C[128][N] = A[128][512] * W[N][512]^T, fp16 bit patterns in, fp32 out, N in {16,32,48,64}.            */
 int wrnn_debug_tc_gemm(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int32_t N, float* C);

@@ -3,6 +3,8 @@
 // cooperative grid, no arithmetic:
 //   LL      : every CTA publishes 4 {value,tag} words, every CTA spins until all 512 words carry the tag
 //   counter : plain stores + __threadfence + atomicAdd on one counter + spin + plain loads
+#include <cooperative_groups.h>
+
 #include "engine_internal.h"
 
 namespace wrnn {
@@ -61,7 +63,40 @@ __global__ void __launch_bounds__(512, 1) floor_counter_kernel(unsigned int* cou
     }
     if (sink == -1.f) data[2 * kRnn] = 0.f;
 }
+// cluster-local exchange: every CTA stores 32 floats into each of its 16 peers' shared memory, then cluster barrier
+__global__ void __launch_bounds__(256, 1) floor_cluster_kernel(int rounds, float* sink_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float buf[2][kRnn];
+    const int tid = threadIdx.x, rank = (int)cluster.block_rank(), n = (int)cluster.num_blocks();
+    float sink = 0.f;
+    cluster.sync();
+    for (int r = 0; r < rounds; ++r) {
+        float* b = buf[r & 1];
+        if (tid < 32)
+            for (int q = 0; q < n; ++q) cluster.map_shared_rank(b, q)[rank * 32 + tid] = (float)r;
+        cluster.sync();
+        sink += b[tid] + b[tid + 256];
+    }
+    cluster.sync();
+    if (sink == -1.f) *sink_out = sink;
+}
 }  // namespace
+
+cudaError_t launch_floor_cluster(int cluster_size, int rounds, float* sink, cudaStream_t stream) {
+    cudaError_t e = cudaSuccess;
+    if (cluster_size > 8) e = cudaFuncSetAttribute(floor_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, floor_cluster_kernel, rounds, sink);
+}
 
 cudaError_t launch_floor_ll(unsigned long long* buf, int rounds, int* abort_flag, cudaStream_t stream) {
     void* args[] = {&buf, &rounds, &abort_flag};

@@ -69,6 +69,8 @@ struct wrnn_engine {
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
     DevBuf wTc, bTcExch, bCS;
+    DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
+    int spStride[2] = {0, 0};
     DevBuf wCondTc, bCondH;     // tensor-core front end: hi/lo fp16 weights (scaled by 2^8) and activation pairs
     size_t oCondTc[kCondLayers + 4] = {};   // element offsets of each layer's W_hi inside wCondTc (W_lo follows)   // tensor-core loop: per-CTA fp16 weight images, exchange buffers, per-sample conditioning
     int* dAbort = nullptr;
@@ -199,7 +201,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1]};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -380,6 +382,69 @@ int wrnn_finalize(wrnn_engine* e) {
         }
         CU(e->wTc.ensure(hw.size()));
         CU(cudaMemcpy(e->wTc.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+    }
+
+    // ---- block-sparse cluster loop: compressed per-CTA images (only for pruned checkpoints) -----------------------
+    e->spStride[0] = e->spStride[1] = 0;
+    if (e->sparsity >= 0.5) {
+        const float* Wih2a = hl.data() + oWih2a;
+        const float* Wfc1a = hl.data() + oWfc1a;
+        const float* Wfc2a = hl.data() + oWfc2a;
+        for (int v = 0; v < 2; ++v) {
+            const int CL = v == 0 ? 16 : 8, U = H / CL, CRs = (C + CL - 1) / CL;
+            std::vector<std::vector<unsigned char>> imgs(CL);
+            size_t stride = 0;
+            for (int cr = 0; cr < CL; ++cr) {
+                std::vector<const float*> rows[4];
+                const int j0 = cr * U;
+                for (int gt = 0; gt < 3; ++gt) for (int u = 0; u < U; ++u) rows[0].push_back(r1hh->data.data() + (size_t)(gt * H + j0 + u) * H);
+                for (int gt = 0; gt < 3; ++gt) for (int u = 0; u < U; ++u) rows[0].push_back(Wih2a + (size_t)(gt * H + j0 + u) * H);
+                for (int u = 0; u < U; ++u) rows[0].push_back(Wfc1a + (size_t)(j0 + u) * H);
+                for (int gt = 0; gt < 3; ++gt) for (int u = 0; u < U; ++u) rows[1].push_back(r2hh->data.data() + (size_t)(gt * H + j0 + u) * H);
+                for (int u = 0; u < U; ++u) rows[1].push_back(Wfc1a + (size_t)(j0 + u) * H);
+                for (int u = 0; u < U; ++u) rows[2].push_back(Wfc2a + (size_t)(j0 + u) * H);
+                for (int r = 0; r < CRs; ++r) rows[3].push_back(cr * CRs + r < C ? f3w->data.data() + (size_t)(cr * CRs + r) * H : nullptr);
+                std::vector<int> rowptr[4];
+                std::vector<unsigned char> col[4];
+                std::vector<float> w[4];
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    rowptr[s4].push_back(0);
+                    for (const float* r : rows[s4]) {
+                        if (r)
+                            for (int gcol = 0; gcol < H / 4; ++gcol) {
+                                const float* q = r + 4 * gcol;
+                                if (q[0] != 0.f || q[1] != 0.f || q[2] != 0.f || q[3] != 0.f) {
+                                    col[s4].push_back((unsigned char)gcol);
+                                    w[s4].insert(w[s4].end(), q, q + 4);
+                                }
+                            }
+                        rowptr[s4].push_back((int)col[s4].size());
+                    }
+                }
+                std::vector<unsigned char>& im = imgs[cr];
+                im.assign(64, 0);
+                int hdr[16] = {0};
+                auto align = [&](size_t a) { im.resize((im.size() + a - 1) / a * a, 0); };
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    align(4); hdr[4 + 3 * s4 + 0] = (int)im.size();
+                    im.insert(im.end(), (unsigned char*)rowptr[s4].data(), (unsigned char*)(rowptr[s4].data() + rowptr[s4].size()));
+                    hdr[4 + 3 * s4 + 1] = (int)im.size();
+                    im.insert(im.end(), col[s4].begin(), col[s4].end());
+                    align(16); hdr[4 + 3 * s4 + 2] = (int)im.size();
+                    im.insert(im.end(), (unsigned char*)w[s4].data(), (unsigned char*)(w[s4].data() + w[s4].size()));
+                    hdr[s4] = (int)col[s4].size();
+                }
+                align(16);
+                memcpy(im.data(), hdr, sizeof(hdr));
+                stride = std::max(stride, im.size());
+            }
+            if (stride + 16384 > e->smem_limit) continue;      // not sparse enough for this cluster size
+            std::vector<unsigned char> all((size_t)CL * stride, 0);
+            for (int cr = 0; cr < CL; ++cr) memcpy(all.data() + (size_t)cr * stride, imgs[cr].data(), imgs[cr].size());
+            CU(e->wSp[v].ensure(all.size()));
+            CU(cudaMemcpy(e->wSp[v].p, all.data(), all.size(), cudaMemcpyHostToDevice));
+            e->spStride[v] = (int)stride;
+        }
     }
 
     // ---- conditioning weights: BatchNorm folded (eval: (x-mean)*rsqrt(var+eps)*gamma+beta, eps=1e-5) ------
@@ -638,8 +703,11 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     if (!e || !rq) return WRNN_ERR_INVALID;
     if (!e->finalized) return fail(e, WRNN_ERR_NOT_LOADED, "Please load Wave-RNN in memory before using it");
     if (rq->n_utts < 1 || !rq->mels || !rq->T) return fail(e, WRNN_ERR_INVALID, "wrnn_generate: no utterances");
-    if (rq->precision != WRNN_PREC_F32 && rq->precision != WRNN_PREC_F16)
-        return fail(e, WRNN_ERR_INVALID, "wrnn_generate: precision not available in this build");
+    if (rq->precision != WRNN_PREC_F32 && rq->precision != WRNN_PREC_F16 && rq->precision != WRNN_PREC_SPARSE_F32)
+        return fail(e, WRNN_ERR_INVALID, "wrnn_generate: unknown precision");
+    const bool use_sparse = rq->precision == WRNN_PREC_SPARSE_F32;
+    if (use_sparse && !e->spStride[0] && !e->spStride[1])
+        return fail(e, WRNN_ERR_INVALID, "block-sparse loop needs a pruned checkpoint (>= 50 % zero 1x4 groups that fit one cluster)");
     const bool use_tc = rq->precision == WRNN_PREC_F16;
     if (use_tc && !e->wTc.p) return fail(e, WRNN_ERR_INVALID, "tensor-core loop supports RAW 9/10-bit and MOL only");
     CU(cudaSetDevice(e->device));
@@ -737,11 +805,38 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     const size_t words_per_fold = (size_t)4 * kRnn + e->Cpad + 2;
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
-    const int wave = use_tc ? kTcMaxFolds : kMaxFoldsPerLaunch;
+    const int wave = use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch);
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);
         CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
-        if (use_tc) {
+        if (use_sparse) {
+            // ---- block-sparse cluster loop: folds partitioned over independent 16-CTA (or 8-CTA) clusters ------------------
+            SparseParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.v1 = e->dv1; sp.v2 = e->dv2; sp.v3 = e->dv3; sp.bhn1 = e->dbhn1; sp.bhn2 = e->dbhn2; sp.bfc3 = e->dbfc3;
+            sp.TA1 = e->bTA1.as<float4>(); sp.TA2 = e->bTA2.as<float4>(); sp.TQ1 = e->bTQ1.as<float4>(); sp.TQ2 = e->bTQ2.as<float4>();
+            sp.coef = e->dcoef;
+            sp.folds = e->bFolds.as<FoldDesc>() + w0;
+            sp.B = B; sp.S = S; sp.C = e->C; sp.Cpad = (e->C + 3) & ~3; sp.mode = e->mode; sp.seed = rq->seed;
+            sp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+            sp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            sp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+            sp.progress = e->dProgress;
+            cudaError_t lerr = cudaErrorInvalidValue;
+            for (int v = 0; v < 2 && lerr != cudaSuccess; ++v) {
+                if (!e->spStride[v]) continue;
+                const int CL = v == 0 ? 16 : 8;
+                sp.wimg = e->wSp[v].as<unsigned char>(); sp.img_stride = e->spStride[v]; sp.CRs = (e->C + CL - 1) / CL;
+                int Bc = std::min(8, std::max(1, (B + 8) / 9));
+                while (Bc > 1 && loop_sparse_smem_bytes(CL, sp.img_stride, Bc, sp.Cpad, sp.CRs) > e->smem_limit) --Bc;
+                if (loop_sparse_smem_bytes(CL, sp.img_stride, Bc, sp.Cpad, sp.CRs) > e->smem_limit) continue;
+                sp.Bc = Bc;
+                lerr = launch_loop_sparse(sp, CL, (B + Bc - 1) / Bc, st);
+                if (lerr != cudaSuccess) cudaGetLastError();      // e.g. 16-CTA clusters not schedulable: try 8
+            }
+            if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
+            e->launches += 1;
+        } else if (use_tc) {
             // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
             const int rows0 = (B + 1) / 2, Mg = rows0;
             const size_t cs_bytes = (size_t)kTcGroups * S * Mg * 256 * 64;
@@ -998,6 +1093,24 @@ int wrnn_debug_tc_gemm(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int
     CU(cudaMemcpyAsync(&status, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (status) return fail(e, WRNN_ERR_TIMEOUT, "tc gemm self-test: pipeline stage " + std::to_string(status) + " timed out");
+    return WRNN_OK;
+}
+
+int wrnn_cluster_floor(wrnn_engine* e, int32_t cluster_size, int32_t rounds, float* us) {
+    if (!e || rounds < 1 || !us) return WRNN_ERR_INVALID;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    CU(e->bFloor.ensure(4 * kRnn * sizeof(unsigned long long) + 64));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(e->ev[0], st));
+        CU(launch_floor_cluster(cluster_size, rounds, e->bFloor.as<float>(), st));
+        CU(cudaEventRecord(e->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        e->launches += 1;
+        best = std::min(best, elapsed(e->ev[0], e->ev[1]) * 1000.f / rounds);
+    }
+    *us = best;
     return WRNN_OK;
 }
 

@@ -86,6 +86,24 @@ cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t st
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                const FoldDesc* folds, int B, int rows0, int S, int Mg, float4* CS, cudaStream_t stream);
 
+// ---- block-sparse cluster loop (loop_sparse.cu) -----------------------------------------------------------------
+struct SparseParams {
+    const unsigned char* wimg;   // [cluster size][img_stride] per-CTA images: int header[16] (byte offsets of rowptr/col/w per
+    int img_stride;              // stage at header[4+3s..]), then rowptr (int), group columns (u8), weights (float4)
+    const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
+    const float4 *TA1, *TA2, *TQ1, *TQ2;
+    const float* coef;
+    const FoldDesc* folds;
+    int B, Bc, S, C, Cpad, CRs, mode;
+    unsigned long long seed;
+    float* samples;
+    float* logits_out;
+    const float* forced;
+    int* progress;
+};
+size_t loop_sparse_smem_bytes(int cluster, int img_stride, int Bc, int Cpad, int CRs);
+cudaError_t launch_loop_sparse(const SparseParams& p, int cluster, int n_clusters, cudaStream_t stream);
+
 // ---- conditioning front end (cond.cu) ---------------------------------------------------------------
 struct UttDesc {
     long long mel_off;   // float offset of this utterance's (80,T) block in the device mel buffer
@@ -144,6 +162,7 @@ cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float*
 
 // ---- exchange-floor microbenchmark (bench_floor.cu) -----------------------------------------------------
 cudaError_t launch_floor_ll(unsigned long long* buf, int rounds, int* abort_flag, cudaStream_t stream);
+cudaError_t launch_floor_cluster(int cluster_size, int rounds, float* sink, cudaStream_t stream);
 cudaError_t launch_floor_counter(unsigned int* counter, float* data, int rounds, int* abort_flag, cudaStream_t stream);
 
 }  // namespace wrnn

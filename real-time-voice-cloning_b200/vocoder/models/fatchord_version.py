@@ -324,6 +324,13 @@ class WaveRNN(object):
             _raise(self._lib, self._h, rc)
         return dict(ll_us=ll.value, counter_us=cnt.value)
 
+    def cluster_floor(self, cluster_size=16, rounds=20000):
+        us = C.c_float()
+        rc = self._lib.wrnn_cluster_floor(self._h, cluster_size, rounds, C.byref(us))
+        if rc != _native.OK:
+            _raise(self._lib, self._h, rc)
+        return us.value
+
     def debug_tc_gemm(self, A, W):
         """Self-test of the tcgen05/TMA building blocks: A (128,512), W (N,512) float16 -> (128,N) float32."""
         A = np.ascontiguousarray(A, dtype=np.float16)
