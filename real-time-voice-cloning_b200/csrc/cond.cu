@@ -162,7 +162,57 @@ __global__ void __launch_bounds__(256) expand_cond_kernel(const float4* __restri
     }
 }
 
+// Same expansion for the cluster-local loop (loop_tc2.cu): CS[cluster][t][CTA 16][gate 4][unit 32][fold 32][2],
+// values {gi1_g, gi2_g} for gates g = r,z,n and {fc1, fc2} for g = 3.  Block = (cluster, CTA, 8 steps); thread = (unit, fold).
+__global__ void __launch_bounds__(1024) expand_cond2_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
+                                                            const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
+                                                            const float* __restrict__ coef, const FoldDesc* __restrict__ folds,
+                                                            int B, int Bc, int S, float* __restrict__ CS) {
+    const int cl = blockIdx.x >> 4, crank = blockIdx.x & 15;
+    const int fold = threadIdx.x & 31, u = threadIdx.x >> 5, j = crank * 32 + u;
+    const int b = cl * Bc + fold;
+    const bool live = fold < Bc && b < B;
+    FoldDesc fd;
+    if (live) fd = folds[b];
+    const int t1 = min(S, (int)(blockIdx.y + 1) * 8);
+    for (int t = blockIdx.y * 8; t < t1; ++t) {
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+        if (live) {
+            const int n = fd.n0 + t;
+            const bool valid = n < fd.N;
+            const int q0 = valid ? n / kHop : 0;
+            const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
+            a1 = __ldg(TA1 + ra); a2 = __ldg(TA2 + ra);
+            if (valid) {
+                const float* cf = coef + (n - q0 * kHop) * kTaps;
+#pragma unroll
+                for (int d = 0; d < kTaps; ++d) {
+                    const float c = __ldg(cf + d);
+                    if (c != 0.f) {
+                        const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
+                        const float4 q1 = __ldg(TQ1 + rq), q2 = __ldg(TQ2 + rq);
+                        a1.x = fmaf(c, q1.x, a1.x); a1.y = fmaf(c, q1.y, a1.y); a1.z = fmaf(c, q1.z, a1.z); a1.w = fmaf(c, q1.w, a1.w);
+                        a2.x = fmaf(c, q2.x, a2.x); a2.y = fmaf(c, q2.y, a2.y); a2.z = fmaf(c, q2.z, a2.z);
+                    }
+                }
+            }
+        }
+        float2* out = reinterpret_cast<float2*>(CS) + ((((size_t)cl * S + t) * 16 + crank) * 4 * 32 + u) * 32 + fold;
+        __stcs(out + 0 * 32 * 32, make_float2(a1.x, a2.x));
+        __stcs(out + 1 * 32 * 32, make_float2(a1.y, a2.y));
+        __stcs(out + 2 * 32 * 32, make_float2(a1.z, a2.z));
+        __stcs(out + 3 * 32 * 32, make_float2(a1.w, a2.w));
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_expand_cond2(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
+                                const FoldDesc* folds, int B, int Bc, int n_clusters, int S, float* CS, cudaStream_t stream) {
+    dim3 grid(n_clusters * 16, (S + 7) / 8);
+    expand_cond2_kernel<<<grid, 1024, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, B, Bc, S, CS);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                const FoldDesc* folds, int B, int rows0, int S, int Mg, float4* CS, cudaStream_t stream) {

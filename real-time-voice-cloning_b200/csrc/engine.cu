@@ -69,6 +69,7 @@ struct wrnn_engine {
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
     DevBuf wTc, bTcExch, bCS;
+    DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
     int spStride[2] = {0, 0};
     DevBuf wCondTc, bCondH;     // tensor-core front end: hi/lo fp16 weights (scaled by 2^8) and activation pairs
@@ -190,6 +191,8 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
         if (err == cudaSuccess) err = set_spin_deadline((long long)(atof(dl) * 1.9e6));
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
         if (err == cudaSuccess) err = set_tc_deadline((long long)(atof(dl) * 1.9e6));
+    if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
+        if (err == cudaSuccess) err = set_tc2_deadline((long long)(atof(dl) * 1.9e6));
     if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
     *out = e;
     return WRNN_OK;
@@ -201,7 +204,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1]};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -382,6 +385,43 @@ int wrnn_finalize(wrnn_engine* e) {
         }
         CU(e->wTc.ensure(hw.size()));
         CU(cudaMemcpy(e->wTc.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+    }
+
+    // ---- cluster-local tensor-core loop (MOL): per-CTA streams of weight tiles, gate-major rows (loop_tc2.cu) -------------
+    if (C == 30) {
+        const size_t img = loop_tc2_image_bytes();
+        std::vector<unsigned char> hw((size_t)16 * img, 0);
+        const float* Wih2a = hl.data() + oWih2a;
+        const float* Wfc1a = hl.data() + oWfc1a;
+        const float* Wfc2a = hl.data() + oWfc2a;
+        auto put_tile = [&](unsigned char* tile, int nrows, int r, const float* src) {
+            for (int kb = 0; kb < 8; ++kb)
+                for (int c = 0; c < 8; ++c) {
+                    __half* dst = reinterpret_cast<__half*>(tile + (size_t)kb * nrows * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+                    for (int i = 0; i < 8; ++i) dst[i] = __float2half_rn(src[kb * 64 + c * 8 + i]);
+                }
+        };
+        for (int cr = 0; cr < 16; ++cr) {
+            unsigned char* t0 = hw.data() + (size_t)cr * img;
+            unsigned char* t1 = t0 + (size_t)128 * 1024;
+            unsigned char* t2 = t1 + (size_t)96 * 1024;
+            unsigned char* t3 = t2 + (size_t)128 * 1024;
+            unsigned char* t4 = t3 + (size_t)32 * 1024;
+            for (int u = 0; u < 32; ++u) {
+                const int j = cr * 32 + u;
+                for (int gt = 0; gt < 3; ++gt) {
+                    put_tile(t0, 128, 32 * gt + u, Wih2a + (size_t)(gt * H + j) * H);
+                    put_tile(t1, 96, 32 * gt + u, r1hh->data.data() + (size_t)(gt * H + j) * H);
+                    put_tile(t2, 128, 32 * gt + u, r2hh->data.data() + (size_t)(gt * H + j) * H);
+                }
+                put_tile(t0, 128, 96 + u, Wfc1a + (size_t)j * H);
+                put_tile(t2, 128, 96 + u, Wfc1a + (size_t)j * H);
+                put_tile(t3, 32, u, Wfc2a + (size_t)j * H);
+            }
+            for (int c = 0; c < 30; ++c) put_tile(t4, 30, c, f3w->data.data() + (size_t)c * H);
+        }
+        CU(e->wTc2.ensure(hw.size()));
+        CU(cudaMemcpy(e->wTc2.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
     }
 
     // ---- block-sparse cluster loop: compressed per-CTA images (only for pruned checkpoints) -----------------------
@@ -836,6 +876,29 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             }
             if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
             e->launches += 1;
+        } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wTc2.p && !(getenv("WRNN_TC_V1") && atoi(getenv("WRNN_TC_V1")))) {
+            // ---- cluster-local tensor-core loop (MOL): folds partitioned over independent 16-CTA clusters -----------------
+            const int ncl = std::max(1, std::min(8, (B + 7) / 8));
+            const int Bc = (B + ncl - 1) / ncl;                    // <= 32 because B <= 256
+            const size_t cs_bytes = (size_t)ncl * S * 16 * 4 * 32 * 32 * 2 * sizeof(float);
+            if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
+            CU(e->bCS.ensure(cs_bytes));
+            CU(launch_expand_cond2(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
+                                   e->bFolds.as<FoldDesc>() + w0, B, Bc, ncl, S, e->bCS.as<float>(), st));
+            Tc2Params tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.wimg = e->wTc2.as<unsigned char>(); tp.img_bytes = (int)loop_tc2_image_bytes();
+            tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
+            tp.CS = e->bCS.as<float>();
+            tp.folds = e->bFolds.as<FoldDesc>() + w0;
+            tp.B = B; tp.Bc = Bc; tp.S = S; tp.seed = rq->seed;
+            tp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+            tp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            tp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+            tp.progress = e->dProgress;
+            tp.abort_flag = e->dAbort;
+            CU(launch_loop_tc2(tp, ncl, st));
+            e->launches += 2;
         } else if (use_tc) {
             // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
             const int rows0 = (B + 1) / 2, Mg = rows0;

@@ -86,6 +86,27 @@ cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t st
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                const FoldDesc* folds, int B, int rows0, int S, int Mg, float4* CS, cudaStream_t stream);
 
+// ---- cluster-local tensor-core loop, MOL (loop_tc2.cu) --------------------------------------------------------------
+struct Tc2Params {
+    const unsigned char* wimg;   // [16][loop_tc2_image_bytes()] per-CTA streams of pre-swizzled weight tiles
+    int img_bytes;
+    const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
+    const float* CS;             // per-sample conditioning [cluster][step][16 CTAs][4 gates][32 units][32 folds][2] (expand_cond2)
+    const FoldDesc* folds;
+    int B, Bc, S;
+    unsigned long long seed;
+    float* samples;
+    float* logits_out;
+    const float* forced;
+    int* progress;
+    int* abort_flag;
+};
+size_t loop_tc2_image_bytes();
+cudaError_t set_tc2_deadline(long long cycles);
+cudaError_t launch_loop_tc2(const Tc2Params& p, int n_clusters, cudaStream_t stream);
+cudaError_t launch_expand_cond2(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
+                                const FoldDesc* folds, int B, int Bc, int n_clusters, int S, float* CS, cudaStream_t stream);
+
 // ---- block-sparse cluster loop (loop_sparse.cu) -----------------------------------------------------------------
 struct SparseParams {
     const unsigned char* wimg;   // [cluster size][img_stride] per-CTA images: int header[16] (byte offsets of rowptr/col/w per
