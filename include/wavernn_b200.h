@@ -135,6 +135,10 @@ int wrnn_xfade_unfold(wrnn_engine* e, const double* y, int64_t num_folds, int64_
  * measured grid-barrier floor".                                                                      */
 int wrnn_barrier_floor(wrnn_engine* e, int32_t rounds, float* ll_us, float* counter_us);
 
+/* tcgen05.mma issue-rate microbenchmark (M=128, K=16, one thread, `iters` groups of 4 MMAs): SM clocks spent issuing
+ * and until completion.  mode 0: one commit at the end; 1: commit per group; 2: wait for every commit.            */
+int wrnn_debug_umma_rate(wrnn_engine* e, int32_t N, int32_t iters, int32_t mode, int64_t* cycles_issue, int64_t* cycles_total);
+
 /* Floor of one cluster-local exchange (DSMEM stores into every peer + hardware cluster barrier), microseconds per
  * round, for a cluster of `cluster_size` CTAs: the exchange the block-sparse loop uses.                          */
 int wrnn_cluster_floor(wrnn_engine* e, int32_t cluster_size, int32_t rounds, float* us);

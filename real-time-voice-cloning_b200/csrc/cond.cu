@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(1024) expand_cond2_kernel(const float4* __rest
                                                             const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                             const float* __restrict__ coef, const FoldDesc* __restrict__ folds,
                                                             int B, int Bc, int S, float* __restrict__ CS) {
+    __shared__ float2 tile[4][32][33];                    // [gate][unit][fold], padded
     const int cl = blockIdx.x >> 4, crank = blockIdx.x & 15;
-    const int fold = threadIdx.x & 31, u = threadIdx.x >> 5, j = crank * 32 + u;
+    const int u = threadIdx.x & 31, fold = threadIdx.x >> 5, j = crank * 32 + u;     // lanes along units: coalesced table reads
     const int b = cl * Bc + fold;
     const bool live = fold < Bc && b < B;
     FoldDesc fd;
@@ -197,11 +198,16 @@ __global__ void __launch_bounds__(1024) expand_cond2_kernel(const float4* __rest
                 }
             }
         }
-        float2* out = reinterpret_cast<float2*>(CS) + ((((size_t)cl * S + t) * 16 + crank) * 4 * 32 + u) * 32 + fold;
-        __stcs(out + 0 * 32 * 32, make_float2(a1.x, a2.x));
-        __stcs(out + 1 * 32 * 32, make_float2(a1.y, a2.y));
-        __stcs(out + 2 * 32 * 32, make_float2(a1.z, a2.z));
-        __stcs(out + 3 * 32 * 32, make_float2(a1.w, a2.w));
+        __syncthreads();                                   // previous step's tile fully written out
+        tile[0][u][fold] = make_float2(a1.x, a2.x);
+        tile[1][u][fold] = make_float2(a1.y, a2.y);
+        tile[2][u][fold] = make_float2(a1.z, a2.z);
+        tile[3][u][fold] = make_float2(a1.w, a2.w);
+        __syncthreads();
+        float2* out = reinterpret_cast<float2*>(CS) + (((size_t)cl * S + t) * 16 + crank) * 4 * 32 * 32;
+        const int of = threadIdx.x & 31, ou = threadIdx.x >> 5;                     // lanes along folds: coalesced stores
+#pragma unroll
+        for (int g = 0; g < 4; ++g) __stcs(out + (g * 32 + ou) * 32 + of, tile[g][ou][of]);
     }
 }
 

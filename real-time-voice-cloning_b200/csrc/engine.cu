@@ -79,6 +79,7 @@ struct wrnn_engine {
     int* dProgress = nullptr;
     int fade_overlap = -1;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evx[2] = {};     // brackets the per-sample conditioning expansion of a wave
 };
 
 namespace {
@@ -187,6 +188,7 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     if (err == cudaSuccess) err = cudaHostAlloc(&e->hProgress, sizeof(int), cudaHostAllocMapped);
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->dProgress, e->hProgress, 0);
     for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
+    for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->evx[i]);
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))   // profilers slow the loop down: let them widen the guard
         if (err == cudaSuccess) err = set_spin_deadline((long long)(atof(dl) * 1.9e6));
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
@@ -845,10 +847,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     const size_t words_per_fold = (size_t)4 * kRnn + e->Cpad + 2;
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
+    float ms_expand = 0.f;
     const int wave = use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch);
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);
         CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
+        bool expanded = false;
         if (use_sparse) {
             // ---- block-sparse cluster loop: folds partitioned over independent 16-CTA (or 8-CTA) clusters ------------------
             SparseParams sp;
@@ -876,15 +880,21 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             }
             if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
             e->launches += 1;
-        } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wTc2.p && !(getenv("WRNN_TC_V1") && atoi(getenv("WRNN_TC_V1")))) {
+        } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wTc2.p && getenv("WRNN_TC_V2") && atoi(getenv("WRNN_TC_V2"))) {
+            // (opt-in: measured equal to loop_tc.cu in round 1 -- 27.4 vs 26.6 us/step -- see DESIGN.md section 4.3)
             // ---- cluster-local tensor-core loop (MOL): folds partitioned over independent 16-CTA clusters -----------------
-            const int ncl = std::max(1, std::min(8, (B + 7) / 8));
+            const int max_cl = std::max(1, loop_tc2_max_clusters());       // 16-CTA clusters that can be co-resident
+            if (getenv("WRNN_VERBOSE")) fprintf(stderr, "[wrnn] tc2: max co-resident 16-CTA clusters = %d\n", max_cl);
+            const int ncl = std::max(std::min(max_cl, (B + 7) / 8), (B + 31) / 32);
             const int Bc = (B + ncl - 1) / ncl;                    // <= 32 because B <= 256
             const size_t cs_bytes = (size_t)ncl * S * 16 * 4 * 32 * 32 * 2 * sizeof(float);
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
+            CU(cudaEventRecord(e->evx[0], st));
             CU(launch_expand_cond2(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
                                    e->bFolds.as<FoldDesc>() + w0, B, Bc, ncl, S, e->bCS.as<float>(), st));
+            CU(cudaEventRecord(e->evx[1], st));
+            expanded = true;
             Tc2Params tp;
             memset(&tp, 0, sizeof(tp));
             tp.wimg = e->wTc2.as<unsigned char>(); tp.img_bytes = (int)loop_tc2_image_bytes();
@@ -897,7 +907,25 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
             tp.progress = e->dProgress;
             tp.abort_flag = e->dAbort;
+            const bool want_trace2 = getenv("WRNN_TC_TRACE") != nullptr;
+            if (want_trace2) {
+                CU(e->bFloor.ensure(16 * 32 * sizeof(long long)));
+                CU(cudaMemsetAsync(e->bFloor.p, 0, 16 * 32 * sizeof(long long), st));
+                tp.trace = e->bFloor.as<long long>();
+            }
             CU(launch_loop_tc2(tp, ncl, st));
+            if (want_trace2) {
+                std::vector<long long> tr(16 * 32);
+                CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (FILE* f = fopen(getenv("WRNN_TC_TRACE"), "w")) {
+                    for (int i = 0; i < 16; ++i) {
+                        for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", tr[i * 32 + j] ? tr[i * 32 + j] - tr[i * 32] : -1LL);
+                        fprintf(f, "\n");
+                    }
+                    fclose(f);
+                }
+            }
             e->launches += 2;
         } else if (use_tc) {
             // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
@@ -905,8 +933,11 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             const size_t cs_bytes = (size_t)kTcGroups * S * Mg * 256 * 64;
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
+            CU(cudaEventRecord(e->evx[0], st));
             CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
                                   e->bFolds.as<FoldDesc>() + w0, B, rows0, S, Mg, e->bCS.as<float4>(), st));
+            CU(cudaEventRecord(e->evx[1], st));
+            expanded = true;
             const size_t actb = (size_t)kTcGroups * 128 * kRnn * sizeof(__half);
             const size_t lgb = (size_t)kTcGroups * 128 * e->Cpad * sizeof(unsigned long long);
             const size_t xb = (size_t)kTcGroups * 128 * sizeof(unsigned long long);
@@ -1001,6 +1032,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         int aborted[2] = {0, 0};
         CU(cudaMemcpyAsync(aborted, e->dAbort, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (expanded) ms_expand += elapsed(e->evx[0], e->evx[1]);
         if (aborted[1]) return fail(e, WRNN_ERR_TIMEOUT, "front-end tensor-core GEMM pipeline timed out");
         if (aborted[0]) return fail(e, WRNN_ERR_TIMEOUT, "sample loop deadlock guard fired (an exchange word never arrived)");
         if (rq->progress) {
@@ -1038,8 +1070,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     CU(cudaEventRecord(e->ev[5], st));
     CU(cudaStreamSynchronize(st));
     rq->ms_h2d = elapsed(e->ev[0], e->ev[1]);
-    rq->ms_cond = elapsed(e->ev[1], e->ev[2]);
-    rq->ms_loop = elapsed(e->ev[2], e->ev[3]);
+    rq->ms_cond = elapsed(e->ev[1], e->ev[2]) + ms_expand;     // front end + per-sample expansion
+    rq->ms_loop = elapsed(e->ev[2], e->ev[3]) - ms_expand;     // the loop kernels only
     rq->ms_post = elapsed(e->ev[3], e->ev[4]);
     rq->ms_d2h = elapsed(e->ev[4], e->ev[5]);
     rq->n_folds = Btot;
@@ -1156,6 +1188,20 @@ int wrnn_debug_tc_gemm(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int
     CU(cudaMemcpyAsync(&status, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (status) return fail(e, WRNN_ERR_TIMEOUT, "tc gemm self-test: pipeline stage " + std::to_string(status) + " timed out");
+    return WRNN_OK;
+}
+
+int wrnn_debug_umma_rate(wrnn_engine* e, int32_t N, int32_t iters, int32_t mode, int64_t* cycles_issue, int64_t* cycles_total) {
+    if (!e || !cycles_issue || !cycles_total) return WRNN_ERR_INVALID;
+    CU(cudaSetDevice(e->device));
+    CU(e->bFloor.ensure(4 * kRnn * sizeof(unsigned long long) + 64));
+    CU(run_umma_rate(N, iters, mode, e->bFloor.as<long long>(), e->stream));
+    long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, e->bFloor.p, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->launches += 1;
+    *cycles_issue = h[0];
+    *cycles_total = h[1];
     return WRNN_OK;
 }
 

@@ -100,9 +100,11 @@ struct Tc2Params {
     const float* forced;
     int* progress;
     int* abort_flag;
+    long long* trace;
 };
 size_t loop_tc2_image_bytes();
 cudaError_t set_tc2_deadline(long long cycles);
+int loop_tc2_max_clusters();
 cudaError_t launch_loop_tc2(const Tc2Params& p, int n_clusters, cudaStream_t stream);
 cudaError_t launch_expand_cond2(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                 const FoldDesc* folds, int B, int Bc, int n_clusters, int S, float* CS, cudaStream_t stream);
@@ -179,6 +181,7 @@ cudaError_t launch_xfade_unfold_f64(const double* y, int F, int S, int overlap, 
 // ---- tensor-core building blocks (tma_host.cu, tc_gemm_test.cu) ----------------------------------------
 cudaError_t make_tmap_f16_2d(void* tmap_out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                              uint32_t box_cols);
+cudaError_t run_umma_rate(int N, int iters, int mode, long long* out_dev, cudaStream_t stream);
 cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream);
 
 // ---- exchange-floor microbenchmark (bench_floor.cu) -----------------------------------------------------

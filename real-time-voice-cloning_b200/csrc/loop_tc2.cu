@@ -33,7 +33,8 @@ constexpr int kActBytes = 8 * NF * 128;           // one activation matrix [8 k-
 constexpr int oRing = 0;
 constexpr int oActA = oRing + kSlots2 * kSlotBytes2;     //  98304
 constexpr int oActB = oActA + kActBytes;                 // 131072
-constexpr int oR = oActB + kActBytes;                    // r gate  [32 u][32 f] fp32
+constexpr int oActC = oActB + kActBytes;                 // 163840  (f1 gets its own buffer: T1 may still read h1 in actA)
+constexpr int oR = oActC + kActBytes;                    // r gate  [32 u][32 f] fp32
 constexpr int oZ = oR + U * NF * 4;                      // z gate
 constexpr int oStg = oZ + U * NF * 4;                    // fp16 staging [32 f][32 u]
 constexpr int oLg = oStg + NF * U * 2;                   // logits [32 f][32] fp32
@@ -104,6 +105,11 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 __device__ __forceinline__ float sigmoid_fast2(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast2(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+constexpr int kTr0 = 64, kTrN = 16;
+__device__ __forceinline__ void trace2(const Tc2Params& p, int t, int slot) {
+    if (p.trace && blockIdx.x == 0 && t >= kTr0 && t < kTr0 + kTrN) p.trace[(t - kTr0) * 32 + slot] = clock64();
+}
+
 // rows of the five weight tiles and the byte offset at which a k-block lands inside a ring slot
 __device__ __constant__ int kTileRows[5] = {128, 96, 128, 32, 30};
 __device__ __constant__ int kTileDst[5] = {0, 0, 0, 96 * 128, 0};
@@ -126,7 +132,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
     float2* sMol = reinterpret_cast<float2*>(smem + oMol);
     float* sXs = reinterpret_cast<float*>(smem + oXs);
 
-    for (int i = tid; i < (2 * kActBytes) / 16; i += NT) reinterpret_cast<uint4*>(smem + oActA)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (3 * kActBytes) / 16; i += NT) reinterpret_cast<uint4*>(smem + oActA)[i] = make_uint4(0, 0, 0, 0);
     if (tid < NF) sXs[tid] = 0.f;
     fence_proxy_async_smem();
     if (tid == 0) {
@@ -170,29 +176,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(128, NF);
             const uint32_t acc[5] = {kAcc0, kAcc1, kAcc2, kAcc3, kAcc4};
-            const int actsel[5] = {0, 0, 1, 0, 1};               // A/B activation buffer read by each tile
+            const int actofs[5] = {oActA, oActA, oActB, oActC, oActB};   // activation matrix read by each tile
             const int ready[5] = {0, -1, 1, 2, 3};               // exchange that must be complete first
             uint32_t q = 0;
             for (int t = 0; t < p.S; ++t) {
                 const uint32_t par = (uint32_t)t & 1u;
                 for (int tile = 0; tile < 5; ++tile) {
                     bool ok = true;
+                    trace2(p, t, 10 + tile);
                     if (ready[tile] >= 0) ok = wait2<true>(p, ctl, &ctl->actready[ready[tile]], par);
-                    fence_proxy_async_smem();                     // peers' generic-proxy stores -> my async-proxy reads
-                    const uint32_t bbase = smem_u32(smem + (actsel[tile] ? oActB : oActA));
+                    fence_proxy_async_smem();
+                    trace2(p, t, 15 + tile);                     // peers' generic-proxy stores -> my async-proxy reads
+                    const uint32_t bbase = smem_u32(smem + actofs[tile]);
                     for (int kb = 0; kb < 8; ++kb, ++q) {
                         const uint32_t slot = q % kSlots2, round = q / kSlots2;
                         ok = wait2<false>(p, ctl, &ctl->full[slot], round & 1) && ok;
                         tcgen05_fence_after();
                         if (ok) {
-                            const uint32_t a0 = smem_u32(smem + oRing + slot * kSlotBytes2), b0 = bbase + kb * (NF * 128);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                umma_f16(tmem + acc[tile], umma_desc_sw128(a0 + j * 32), umma_desc_sw128(b0 + j * 32), idesc, (kb | j) ? 1u : 0u);
+                            const uint64_t ad = umma_desc_sw128(smem_u32(smem + oRing + slot * kSlotBytes2));
+                            const uint64_t bd = umma_desc_sw128(bbase + kb * (NF * 128));
+                            const uint32_t dcol = tmem + acc[tile];
+                            if (kb == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
+                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
                         }
                         umma_commit(&ctl->empty[slot]);
                     }
                     umma_commit(&ctl->accfull[tile]);
+                    trace2(p, t, 20 + tile);
                 }
             }
         }
@@ -207,7 +219,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
 #pragma unroll
         for (int i = 0; i < 8; ++i) { h1[i] = 0.f; h2[i] = 0.f; p3[i] = 0.f; }
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        const uint32_t actA = smem_u32(smem + oActA), actB = smem_u32(smem + oActB);
+        const uint32_t actA = smem_u32(smem + oActA), actB = smem_u32(smem + oActB), actC = smem_u32(smem + oActC);
         // DSMEM copy role: 16-byte chunk (fold cf, 8 units cp*8..) to destinations 4*cd .. 4*cd+3
         const int cf = (tid & 127) >> 2, cp = tid & 3, cd = tid >> 7;
         const uint32_t chunk_off = (uint32_t)((crank >> 1) * (NF * 128) + cf * 128 + ((((crank & 1) * 4 + cp) ^ (cf & 7)) << 4));
@@ -222,19 +234,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
             if (tid < CL) remote_arrive(&ctl->actready[e], (uint32_t)tid);
         };
 
+        // conditioning {a, b}[8 folds] for my (gate, unit): gates (c1, c2); q == 3: (fc1, fc2).  Fetched one step ahead
+        // (HBM latency stays off the chain).
+        auto cs_ptr = [&](int t) {
+            return reinterpret_cast<const float4*>(p.CS + ((((((size_t)cl * p.S + t) * CL + crank) * 4 + q) * U + u) * NF + 8 * fg) * 2);
+        };
+        float4 nx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i] = __ldcs(cs_ptr(0) + i);
         for (int t = 0; t < p.S; ++t) {
             const uint32_t par = (uint32_t)t & 1u;
-            // conditioning of this step: {a, b}[8 folds] for my (gate, unit): gates (c1, c2); q == 3: (fc1, fc2)
             float ca[8], cb[8];
-            {
-                const float4* cs = reinterpret_cast<const float4*>(
-                    p.CS + ((((((size_t)cl * p.S + t) * CL + crank) * 4 + q) * U + u) * NF + 8 * fg) * 2);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = __ldcs(cs + i);
-                    ca[2 * i] = v.x; cb[2 * i] = v.y; ca[2 * i + 1] = v.z; cb[2 * i + 1] = v.w;
-                }
+            for (int i = 0; i < 4; ++i) { ca[2 * i] = nx[i].x; cb[2 * i] = nx[i].y; ca[2 * i + 1] = nx[i].z; cb[2 * i + 1] = nx[i].w; }
+            if (t + 1 < p.S) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nx[i] = __ldcs(cs_ptr(t + 1) + i);
             }
+            if (tid == 0) trace2(p, t, 0);
             float x[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = sXs[8 * fg + i];
@@ -264,10 +281,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
             }
             tcgen05_fence_before();
             exchange(actA, 0, nullptr, 0);
+            if (tid == 0) trace2(p, t, 1);
             // ---- B: T0 = [W_ih2a | W_fc1a] h1 ; GRU2 -> h2 -> actB -----------------------------------------------
             float d[8];
             wait2<false>(p, ctl, &ctl->accfull[0], par);
             tcgen05_fence_after();
+            if (tid == 0) trace2(p, t, 2);
             tmem_ld8(tl + kAcc0, d);
             if (t > 0 && q < 3) tmem_ld8(tl + kAcc2, g);
             tmem_ld_wait();
@@ -292,10 +311,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
                 }
             }
             tcgen05_fence_before();
-            exchange(actB, 1, &ctl->accfull[1], par);             // T1 (reads actA) must be done before f1 may land in actA
+            exchange(actB, 1, &ctl->accfull[1], par);
+            if (tid == 0) trace2(p, t, 3);             // T1 (reads actA) must be done before f1 may land in actA
             // ---- C: T2 = [W_hh2 | W_fc1a] h2 ; f1 -> actA ---------------------------------------------------------
             wait2<false>(p, ctl, &ctl->accfull[2], par);
             tcgen05_fence_after();
+            if (tid == 0) trace2(p, t, 4);
             if (q == 3) {
                 tmem_ld8(tl + kAcc2, d);
                 tmem_ld_wait();
@@ -304,10 +325,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
                     sStg[(8 * fg + i) * U + u] = __float2half_rn(fmaxf(p3[i] + d[i] + fmaf(v3u, x[i], ca[i]), 0.f));
             }
             tcgen05_fence_before();
-            exchange(actA, 2, nullptr, 0);
+            exchange(actC, 2, nullptr, 0);
+            if (tid == 0) trace2(p, t, 5);
             // ---- D: T3 = fc2 (lanes 96..127) ; f2 -> actB ---------------------------------------------------------
             wait2<false>(p, ctl, &ctl->accfull[3], par);
             tcgen05_fence_after();
+            if (tid == 0) trace2(p, t, 6);
             if (q == 3) {
                 tmem_ld8(tl + kAcc3, d);
                 tmem_ld_wait();
@@ -316,9 +339,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
             }
             tcgen05_fence_before();
             exchange(actB, 3, nullptr, 0);
+            if (tid == 0) trace2(p, t, 7);
             // ---- E: T4 = fc3 (every CTA has all 30 outputs) ; mixture-of-logistics draw -------------------------------
             wait2<false>(p, ctl, &ctl->accfull[4], par);
             tcgen05_fence_after();
+            if (tid == 0) trace2(p, t, 8);
             if (q == 0) {
                 tmem_ld8(tl + kAcc4, d);
                 tmem_ld_wait();
@@ -372,6 +397,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
                 }
             }
             epi_bar();
+            if (tid == 0) trace2(p, t, 9);
             if (blockIdx.x == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
                 *reinterpret_cast<volatile int*>(p.progress) = t;
                 __threadfence_system();
@@ -389,6 +415,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
 
 cudaError_t set_tc2_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc2_deadline, &cycles, sizeof(cycles)); }
 size_t loop_tc2_image_bytes() { return (size_t)(128 + 96 + 128 + 32 + 30) * 1024; }
+
+int loop_tc2_max_clusters() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    if (cudaFuncSetAttribute(wrnn_loop_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2 + 1024) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(wrnn_loop_tc2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 8);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = kSmem2 + 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wrnn_loop_tc2_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cached = n;
+    return n;
+}
 
 cudaError_t launch_loop_tc2(const Tc2Params& p, int n_clusters, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(wrnn_loop_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2 + 1024);

@@ -100,7 +100,65 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(const __grid_const
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
 }
+// Microbenchmark: issue rate of tcgen05.mma (M=128, K=16, SS operands, SWIZZLE_128B) from one thread.
+//   mode 0: back-to-back MMAs on one accumulator, one commit at the end
+//   mode 1: commit to an mbarrier after every 4 MMAs (the loop kernels' per-k-block pattern), no waiting
+//   mode 2: as 1, and wait for each commit before issuing the next 4 (fully serialised: MMA latency)
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int mode, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                    // 16 KB
+    uint8_t* sB = base + 16384;            // N x 128 B (<= 32 KB)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 16384 + 32768);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) tmem_alloc(tslot, 256);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tslot;
+    if (threadIdx.x == 0) {
+        // mode 0..2: descriptors precomputed, accumulate flag constant (the tight issue loop)
+        // mode 20: descriptors rebuilt and predicate set up for every MMA (what the first loop kernels did)
+        const uint32_t idesc = umma_idesc_f16(128, N), a0 = smem_u32(sA), b0 = smem_u32(sB);
+        uint32_t ph = 0;
+        const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(b0);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (mode == 20) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) umma_f16(tmem, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(b0 + j * 32), idesc, (i | j) ? 1u : 0u);
+            } else {
+                umma_f16_c<true>(tmem, ad, bd, idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+            }
+            if (mode >= 1) umma_commit(&bar[0]);
+            if (mode == 2) { while (!mbar_try_wait(&bar[0], ph)) {} ph ^= 1; }
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar[1]);
+        while (!mbar_try_wait(&bar[1], 0)) {}
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
 }  // namespace
+
+cudaError_t run_umma_rate(int N, int iters, int mode, long long* out_dev, cudaStream_t stream) {
+    const int smem = 1024 + 16384 + 32768 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    umma_rate_kernel<<<1, 128, smem, stream>>>(N, iters, mode, out_dev);
+    return cudaGetLastError();
+}
 
 cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream) {
     if (N % 16 != 0 || N < 16 || N > 64) return cudaErrorInvalidValue;

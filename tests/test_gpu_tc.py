@@ -97,3 +97,28 @@ def test_tensor_core_front_end_matches_reference():
     np.testing.assert_allclose(aux_tc, aux_f32, rtol=0, atol=2e-5)
     mel2 = norm_mel(300, 9)                      # more than two 128-row tiles
     np.testing.assert_allclose(model.conditioning_tc(mel2), model.conditioning(mel2)[1], rtol=0, atol=2e-5)
+
+
+def test_cluster_local_tc_loop_mol(monkeypatch):
+    """loop_tc2.cu (opt-in with WRNN_TC_V2=1): same parity gates as the default tensor-core loop."""
+    from tests.util import golden, norm_mel
+    monkeypatch.setenv("WRNN_TC_V2", "1")
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    g = golden("gen_mol_batched.npz")
+    mel = norm_mel(int(g["mel_T"]), int(g["mel_seed"]))
+    ref = g["samples"]
+    B, Sm1 = ref.shape
+    forced = np.zeros((B, Sm1 + 1), np.float32)
+    forced[:, :-1] = ref
+    out = model.generate_debug(mel, True, int(g["target"]), int(g["overlap"]), forced=forced, want_logits=True,
+                               seed=int(g["seed"]), precision=F16)
+    assert _rel(out["logits"][:, ::8], g["logits_sub"]) < 1e-3
+    assert float((np.abs(out["samples"][:, :-1] - ref) < 1e-3).mean()) >= 0.998
+    # many folds: several clusters, partially filled last cluster
+    mel2 = norm_mel(400, 4)
+    a = model.generate_debug(mel2, True, 300, 50, want_logits=True, seed=5, max_steps=40, precision=F16)
+    monkeypatch.setenv("WRNN_TC_V2", "0")
+    forced2 = np.pad(a["samples"], ((0, 0), (0, 400 - 40)))
+    b = model.generate_debug(mel2, True, 300, 50, forced=forced2, want_logits=True, seed=5, max_steps=40)
+    assert a["samples"].shape[0] > 200
+    assert _rel(a["logits"], b["logits"]) < 1e-3
