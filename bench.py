@@ -327,9 +327,9 @@ def main():
                      "traffic": None, "kernel": {"f32": "wrnn_loop_f32_kernel", "f16": "wrnn_loop_tc_kernel", "sparse": "wrnn_loop_sparse_kernel"}[args.precision],
                      "peak_source": pk_kind + " bf16_tflops_sustained", "kernel_ms": loop_s * 1e3,
                      "algorithmic_flops_per_launch": flops},
-        "loop": {"us_per_step": loop_s * 1e6 / S, "exchanges_per_step": n_exch, "exchange_floor_us": floor["ll_us"],
+        "loop": {"us_per_step": loop_s * 1e6 / (S * max(1, last_t["n_launches"])), "exchanges_per_step": n_exch, "exchange_floor_us": floor["ll_us"],
                  "counter_barrier_floor_us": floor["counter_us"], "cluster16_exchange_floor_us": floor["cluster_us"],
-                 "step_over_floor": (loop_s * 1e6 / S) / (n_exch * floor_us),
+                 "step_over_floor": (loop_s * 1e6 / (S * max(1, last_t["n_launches"]))) / (n_exch * floor_us),
                  "floor_used": {"f32": "flag-in-data exchange through L2", "f16": "fence+atomic counter barrier through L2",
                                 "sparse": "DSMEM stores + cluster barrier (16 CTAs)"}[args.precision]},
         "phases_ms": {k: last_t[k] for k in ("ms_h2d", "ms_cond", "ms_loop", "ms_post", "ms_d2h")},
