@@ -197,3 +197,51 @@ def test_full_size_config1_properties(raw9):
     assert w1.shape == (159800,) and w1.dtype == np.float64
     assert np.array_equal(w1, w2)
     assert np.isfinite(w1).all() and w1[-1] == 0.0 and np.all(w1[:400] == 0.0)   # Q7: first overlap//2 muted
+
+
+def test_raw_10bit_and_8bit_vs_oracle():
+    """bits = 10 is the reference's default (config/hparams.py:223); 8 exercises the smallest class count."""
+    for bits, C in ((10, 1024), (8, 256)):
+        model, sd = make_model(seed=21, bits=bits, mode="RAW")
+        mel = norm_mel(23, 8)
+        out = model.generate_debug(mel, True, 600, 100, want_logits=True, seed=77, max_steps=150)
+        forced = np.pad(out["samples"], ((0, 0), (0, 800 - 150)))
+        _, tr = orc.generate(mel, sd, mode="RAW", batched=True, target=600, overlap=100, seed=77, forced_samples=forced,
+                             return_trace=True, max_steps=150)
+        assert rel_err(out["logits"], tr["logits"]) < REL_TOL
+        mine = np.rint((out["samples"] + 1.0) * (C - 1) / 2.0).astype(np.int64)
+        assert float((mine == tr["index"]).mean()) >= AGREE
+
+
+def test_mol_unbatched_vs_oracle(mol):
+    model, sd = mol
+    mel = norm_mel(22, 6)
+    out = model.generate_debug(mel, False, 0, 0, want_logits=True, seed=5, max_steps=300)
+    forced = np.pad(out["samples"], ((0, 0), (0, 22 * 200 - 300)))
+    _, tr = orc.generate(mel, sd, mode="MOL", batched=False, seed=5, forced_samples=forced, return_trace=True, max_steps=300)
+    assert rel_err(out["logits"], tr["logits"]) < REL_TOL
+    assert float((np.abs(out["samples"] - tr["samples"]) < 1e-4).mean()) >= AGREE
+
+
+def test_ragged_batch_all_precisions(raw9):
+    """Utterances of different lengths pooled in one call: every loop gives every utterance its own length and noise."""
+    model, _ = raw9
+    mels = [norm_mel(T, 40 + T) for T in (21, 57, 33, 90)]
+    model.seed = 9
+    ref = model.generate_batch(mels, True, 700, 150, True, True)
+    assert [len(w) for w in ref] == [(m.shape[1] - 1) * 200 for m in mels]
+    model.precision = 1
+    f16 = model.generate_batch(mels, True, 700, 150, True, True)
+    model.precision = 0
+    for a, b in zip(ref, f16):
+        assert a.shape == b.shape and np.isfinite(b).all()
+        assert np.mean(np.abs(a - b) < 1e-6) > 0.5       # same draws until the first fp16-induced flip in a fold
+
+
+def test_progress_callback_contract(raw9):
+    model, _ = raw9
+    calls = []
+    wav = model.generate(norm_mel(30, 2)[None], True, 1000, 200, True, True,
+                         progress_callback=lambda i, seq_len, b_size, rate: calls.append((i, seq_len, b_size, rate)))
+    assert wav.shape == (29 * 200,)
+    assert calls and calls[-1][0] == 1399 and calls[-1][1] == 1400 and calls[-1][2] == 5 and calls[-1][3] > 0
