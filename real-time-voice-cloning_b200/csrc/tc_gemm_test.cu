@@ -107,13 +107,13 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(const __grid_const
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int mode, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = base;                    // 16 KB
-    uint8_t* sB = base + 16384;            // N x 128 B (<= 32 KB)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 16384 + 32768);
+    uint8_t* sA = base;                    // 4 x 16 KB (modes 3/4 rotate over them)
+    uint8_t* sB = base + 65536;            // N x 128 B (<= 32 KB)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 65536 + 32768);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
-    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (65536 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
-    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); tslot[1] = 0; }
     if (threadIdx.x < 32) tmem_alloc(tslot, 256);
     tcgen05_fence_before();
     __syncthreads();
@@ -127,6 +127,16 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int
         const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(b0);
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
+            if (mode == 3 || mode == 4) {          // the loop kernels' per-k-block pattern: fence, 4 MMAs on a fresh tile, commit
+                tcgen05_fence_after();
+                const uint64_t a2 = umma_desc_sw128(a0 + (i & 3) * 16384);
+                umma_f16_c<true>(tmem, a2, bd, idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(a2, 32), umma_desc_advance(bd, 32), idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(a2, 64), umma_desc_advance(bd, 64), idesc);
+                umma_f16_c<true>(tmem, umma_desc_advance(a2, 96), umma_desc_advance(bd, 96), idesc);
+                umma_commit(&bar[0]);
+                continue;
+            }
             if (mode == 20) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) umma_f16(tmem, umma_desc_sw128(a0 + j * 32), umma_desc_sw128(b0 + j * 32), idesc, (i | j) ? 1u : 0u);
@@ -145,6 +155,18 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int
         const long long t2 = clock64();
         out[0] = t1 - t0;
         out[1] = t2 - t0;
+        *reinterpret_cast<volatile int*>(tslot + 1) = 1;
+    } else if (mode == 4 && threadIdx.x >= 32) {
+        // contention: three warps stream 16-byte loads/stores over the A tiles while the MMAs run
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        int it = 0;
+        while (*reinterpret_cast<volatile int*>(tslot + 1) == 0 && it < 2000000) {
+            const uint4 v = reinterpret_cast<uint4*>(sA)[(threadIdx.x * 7 + it * 96) & 4095];
+            acc.x ^= v.x;
+            reinterpret_cast<uint4*>(sB + 16384)[(threadIdx.x + it) & 1023] = acc;
+            ++it;
+        }
+        if (acc.x == 12345u) out[3] = it;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int
 }  // namespace
 
 cudaError_t run_umma_rate(int N, int iters, int mode, long long* out_dev, cudaStream_t stream) {
-    const int smem = 1024 + 16384 + 32768 + 64;
+    const int smem = 1024 + 65536 + 32768 + 64;
     cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     umma_rate_kernel<<<1, 128, smem, stream>>>(N, iters, mode, out_dev);
