@@ -45,7 +45,8 @@ MULTI = {"cfg5"}
 
 def workload_mels(wl, rank, world):
     """Synthetic mels (synthesizer range [-4,4]) of this rank and the global index of its first utterance."""
-    from oracle import weights
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import synth as weights
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
     if wl in MULTI:
         lens = np.random.default_rng(2).integers(5, 21, size=256)
@@ -139,7 +140,8 @@ def reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import weights
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import synth as weights
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
     sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
     if wl in PRUNED:
@@ -206,7 +208,7 @@ def main():
     from rtvc_b200 import _native
     from rtvc_b200.config import hparams
     from rtvc_b200.vocoder import inference
-    from oracle import weights      # deterministic synthetic weights / mels only
+    from rtvc_b200 import synth as weights      # deterministic synthetic weights / mels (input generation only)
 
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
     hp = copy.deepcopy(hparams.wavernn_fatchord)
