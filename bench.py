@@ -305,6 +305,11 @@ def main():
     loop_s = float(np.mean(loop_ms)) / 1e3
     achieved = flops / loop_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("%s:%s" % (wl, args.precision))
+    except Exception:
+        pass
     floor = model.barrier_floor(20000)
     floor["cluster_us"] = model.cluster_floor(16, 20000)
     n_exch = 5 if (mode == "MOL" or args.precision == "sparse") else 6       # h1, h2, f1, f2, (logits,) x per step
@@ -326,7 +331,7 @@ def main():
                 "ms_per_step": e2e_total / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": {"f32": "wrnn_loop_f32_kernel", "f16": "wrnn_loop_tc_kernel", "sparse": "wrnn_loop_sparse_kernel"}[args.precision],
+                     "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"), "kernel": {"f32": "wrnn_loop_f32_kernel", "f16": "wrnn_loop_tc_kernel", "sparse": "wrnn_loop_sparse_kernel"}[args.precision],
                      "peak_source": pk_kind + " bf16_tflops_sustained", "kernel_ms": loop_s * 1e3,
                      "algorithmic_flops_per_launch": flops},
         "loop": {"us_per_step": loop_s * 1e6 / (S * max(1, last_t["n_launches"])), "exchanges_per_step": n_exch, "exchange_floor_us": floor["ll_us"],
