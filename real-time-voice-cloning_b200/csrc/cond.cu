@@ -119,15 +119,15 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 }
 
 // Per-sample conditioning for the tensor-core loop: interpolates the per-frame tables once, ahead of the loop,
-// into CS[group][t][row][unit pair][16 floats] so a loop thread reads one contiguous 64-byte record per step:
+// into CS[virtual group][t][row][unit pair][16 floats] so a loop thread reads one contiguous 64-byte record per step:
 //   {c1_r[2], c1_z[2], c1_n[2], c2_r[2], c2_z[2], c2_n[2], c3[2], c4[2]}   (two hidden units per record)
 // Positions past the utterance (fold tail padding, Q9) take the bias-only row and no mel share.
 constexpr int kExpandSteps = 16;
 __global__ void __launch_bounds__(256) expand_cond_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                           const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                           const float* __restrict__ coef, const FoldDesc* __restrict__ folds,
-                                                          int rows0, int S, int Mg, float4* __restrict__ CS) {
-    const int b = blockIdx.x, g = (b >= rows0) ? 1 : 0, row = b - g * rows0;
+                                                          int S, int Mg, float4* __restrict__ CS) {
+    const int b = blockIdx.x, g = b / Mg, row = b - g * Mg;          // virtual group, row
     const FoldDesc fd = folds[b];
     const int j = threadIdx.x * 2;
     const int t1 = min(S, (int)(blockIdx.y + 1) * kExpandSteps);
@@ -221,9 +221,9 @@ cudaError_t launch_expand_cond2(const float4* TA1, const float4* TA2, const floa
 }
 
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
-                               const FoldDesc* folds, int B, int rows0, int S, int Mg, float4* CS, cudaStream_t stream) {
+                               const FoldDesc* folds, int B, int S, int Mg, float4* CS, cudaStream_t stream) {
     dim3 grid(B, (S + kExpandSteps - 1) / kExpandSteps);
-    expand_cond_kernel<<<grid, 256, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, rows0, S, Mg, CS);
+    expand_cond_kernel<<<grid, 256, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, S, Mg, CS);
     return cudaGetLastError();
 }
 

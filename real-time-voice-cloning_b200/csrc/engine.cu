@@ -420,7 +420,7 @@ int wrnn_finalize(wrnn_engine* e) {
                 put_tile(t2, 128, 96 + u, Wfc1a + (size_t)j * H);
                 put_tile(t3, 32, u, Wfc2a + (size_t)j * H);
             }
-            for (int c = 0; c < 30; ++c) put_tile(t4, 30, c, f3w->data.data() + (size_t)c * H);
+            for (int c = 0; c < 30; ++c) put_tile(t4, 32, c, f3w->data.data() + (size_t)c * H);   // padded to 32 rows (1024-aligned k-blocks)
         }
         CU(e->wTc2.ensure(hw.size()));
         CU(cudaMemcpy(e->wTc2.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
@@ -929,18 +929,20 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             e->launches += 2;
         } else if (use_tc) {
             // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
-            const int rows0 = (B + 1) / 2, Mg = rows0;
-            const size_t cs_bytes = (size_t)kTcGroups * S * Mg * 256 * 64;
+            // up to 256 folds: one set per group; more: two sets per group, pipelined through the same CTAs
+            const int nsets = (B > kTcGroups * 128) ? kTcSets : 1, nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
+            const size_t cs_bytes = (size_t)nvg * S * Mg * 256 * 64;
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
             CU(cudaEventRecord(e->evx[0], st));
             CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
-                                  e->bFolds.as<FoldDesc>() + w0, B, rows0, S, Mg, e->bCS.as<float4>(), st));
+                                  e->bFolds.as<FoldDesc>() + w0, B, S, Mg, e->bCS.as<float4>(), st));
             CU(cudaEventRecord(e->evx[1], st));
             expanded = true;
-            const size_t actb = (size_t)kTcGroups * 128 * kRnn * sizeof(__half);
-            const size_t lgb = (size_t)kTcGroups * 128 * e->Cpad * sizeof(unsigned long long);
-            const size_t xb = (size_t)kTcGroups * 128 * sizeof(unsigned long long);
+            const size_t xrows = (size_t)kTcGroups * kTcSets * 128;
+            const size_t actb = xrows * kRnn * sizeof(__half);
+            const size_t lgb = xrows * e->Cpad * sizeof(unsigned long long);
+            const size_t xb = xrows * sizeof(unsigned long long);
             const size_t exch = 4 * actb + lgb + xb + 256;
             CU(e->bTcExch.ensure(exch));
             CU(cudaMemsetAsync(e->bTcExch.p, 0, exch, st));
@@ -949,9 +951,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             memset(&tp, 0, sizeof(tp));
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
-            tp.CS = e->bCS.as<float4>(); tp.Mg = Mg;
+            tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets;
             tp.folds = e->bFolds.as<FoldDesc>() + w0;
-            tp.B = B; tp.rows0 = rows0; tp.S = S; tp.C = e->C; tp.Cpad = e->Cpad; tp.mode = e->mode;
+            tp.B = B; tp.S = S; tp.C = e->C; tp.Cpad = e->Cpad; tp.mode = e->mode;
             tp.seed = rq->seed;
             tp.H1 = reinterpret_cast<__half*>(xb0); tp.H2 = reinterpret_cast<__half*>(xb0 + actb);
             tp.F1 = reinterpret_cast<__half*>(xb0 + 2 * actb); tp.F2 = reinterpret_cast<__half*>(xb0 + 3 * actb);
@@ -965,9 +967,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.abort_flag = e->dAbort;
             alignas(64) unsigned char tmaps[4][128];
             __half* acts[4] = {tp.H1, tp.H2, tp.F1, tp.F2};
-            const int box_rows = std::min(128, (rows0 + 7) & ~7);     // only the live folds travel
+            const int box_rows = std::min(128, (Mg + 7) & ~7);     // only the live folds travel
             tp.tile_bytes = box_rows * 128;
-            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)kTcGroups * 128, kRnn, box_rows, 64));
+            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)xrows, kRnn, box_rows, 64));
             const bool want_trace = getenv("WRNN_TC_TRACE") != nullptr;
             if (want_trace) {
                 CU(e->bFloor.ensure(16 * 32 * sizeof(long long)));

@@ -58,21 +58,23 @@ cudaError_t set_spin_deadline(long long cycles);
 constexpr int kTcGroups = 2;      // independent groups of CTAs, each with a full fp16 copy of the loop weights
 constexpr int kTcCtas = 64;       // CTAs per group
 constexpr int kTcUnits = 8;       // hidden units per CTA
-constexpr int kTcMaxFolds = kTcGroups * 128;
+constexpr int kTcSets = 2;        // fold sets (<= 128 folds each) a group pipelines through its CTAs
+constexpr int kTcMaxFolds = kTcGroups * kTcSets * 128;
 
 struct TcParams {
     const unsigned char* wimg;   // [kTcCtas][loop_tc_weight_image_bytes()] per-CTA weight images in shared-memory layout
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
-    const float4* CS;            // per-sample conditioning [group][step][row < Mg][256 unit pairs][4 float4] (expand_cond)
-    int Mg;
+    const float4* CS;            // per-sample conditioning [virtual group][step][row < Mg][256 unit pairs][4 float4] (expand_cond)
+    int Mg;                      // folds per virtual group (= group x set); fold f is row f % Mg of virtual group f / Mg
+    int nsets;                   // fold sets per group in this launch (1 or 2)
     const FoldDesc* folds;
-    int B, rows0, S, C, Cpad, mode;
+    int B, S, C, Cpad, mode;
     int tile_bytes;              // bytes one TMA tile delivers: box_rows * 128
     unsigned long long seed;
-    __half *H1, *H2, *F1, *F2;   // activation exchange, [kTcGroups*128][512] fp16
-    unsigned int* counters;      // [kTcGroups][4] arrival counters (monotonic)
-    unsigned long long* bLG;     // [kTcGroups*128][Cpad] logits exchange words (RAW)
-    unsigned long long* bX;      // [kTcGroups*128] sample exchange words
+    __half *H1, *H2, *F1, *F2;   // activation exchange, [kTcGroups*kTcSets*128][512] fp16
+    unsigned int* counters;      // [kTcGroups*kTcSets][4] arrival counters (monotonic)
+    unsigned long long* bLG;     // [kTcGroups*kTcSets*128][Cpad] logits exchange words (RAW)
+    unsigned long long* bX;      // [kTcGroups*kTcSets*128] sample exchange words
     float* samples;
     float* logits_out;
     const float* forced;
@@ -84,7 +86,7 @@ size_t loop_tc_weight_image_bytes();
 cudaError_t set_tc_deadline(long long cycles);
 cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t stream);
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
-                               const FoldDesc* folds, int B, int rows0, int S, int Mg, float4* CS, cudaStream_t stream);
+                               const FoldDesc* folds, int B, int S, int Mg, float4* CS, cudaStream_t stream);
 
 // ---- cluster-local tensor-core loop, MOL (loop_tc2.cu) --------------------------------------------------------------
 struct Tc2Params {

@@ -27,14 +27,14 @@ using namespace tc;
 
 constexpr int CL = 16, U = 32, NF = 32;           // cluster size, units per CTA, folds per cluster (MMA N)
 constexpr int NEPI = 16, NT = (NEPI + 2) * 32;
-constexpr int kSlots2 = 6, kSlotBytes2 = 16384;
+constexpr int kSlots2 = 3, kSlotBytes2 = 32768;    // ring of 32 KB chunks: 14 bulk copies per step (a copy costs ~0.3 us, serialised)
 constexpr int kActBytes = 8 * NF * 128;           // one activation matrix [8 k-blocks][32 folds x 128 B] = 32 KB
 // shared memory map
-constexpr int oRing = 0;
-constexpr int oActA = oRing + kSlots2 * kSlotBytes2;     //  98304
-constexpr int oActB = oActA + kActBytes;                 // 131072
-constexpr int oActC = oActB + kActBytes;                 // 163840  (f1 gets its own buffer: T1 may still read h1 in actA)
-constexpr int oR = oActC + kActBytes;                    // r gate  [32 u][32 f] fp32
+constexpr int oActA = 0;
+constexpr int oActB = oActA + kActBytes;                 //  32768
+constexpr int oActC = oActB + kActBytes;                 //  65536  (f1 gets its own buffer: T1 may still read h1 in actA)
+constexpr int oRing = oActC + kActBytes;                 //  98304  (>= 12 KB into the allocation: T3's A tile starts 96 rows early)
+constexpr int oR = oRing + kSlots2 * kSlotBytes2;        // 196608  r gate  [32 u][32 f] fp32
 constexpr int oZ = oR + U * NF * 4;                      // z gate
 constexpr int oStg = oZ + U * NF * 4;                    // fp16 staging [32 f][32 u]
 constexpr int oLg = oStg + NF * U * 2;                   // logits [32 f][32] fp32
@@ -111,8 +111,13 @@ __device__ __forceinline__ void trace2(const Tc2Params& p, int t, int slot) {
 }
 
 // rows of the five weight tiles and the byte offset at which a k-block lands inside a ring slot
-__device__ __constant__ int kTileRows[5] = {128, 96, 128, 32, 30};
-__device__ __constant__ int kTileDst[5] = {0, 0, 0, 96 * 128, 0};
+// The five weight tiles stream as 14 chunks per step.  Per tile: chunks, k-blocks per chunk, bytes per k-block, and the
+// byte offset of the A tile's row 0 relative to a k-block's data (T3 = fc2 holds rows 96..127 only: its tile starts
+// 96 rows before the data; T4 = fc3 holds rows 0..31, the rows above read whatever follows: unused TMEM lanes).
+__device__ __constant__ int kChunks[5] = {4, 4, 4, 1, 1};
+__device__ __constant__ int kKbPerChunk[5] = {2, 2, 2, 8, 8};
+__device__ __constant__ int kKbBytes[5] = {128 * 128, 96 * 128, 128 * 128, 32 * 128, 32 * 128};
+__device__ __constant__ int kRow0[5] = {0, 0, 0, -96 * 128, 0};
 
 }  // namespace
 
@@ -158,14 +163,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
             for (int t = 0; t < p.S; ++t) {
                 const uint8_t* src = img;
                 for (int tile = 0; tile < 5; ++tile) {
-                    const uint32_t bytes = (uint32_t)kTileRows[tile] * 128u;
-                    for (int kb = 0; kb < 8; ++kb, ++q, src += bytes) {
+                    const uint32_t bytes = (uint32_t)(kKbPerChunk[tile] * kKbBytes[tile]);
+                    for (int c = 0; c < kChunks[tile]; ++c, ++q, src += bytes) {
                         const uint32_t slot = q % kSlots2, round = q / kSlots2;
                         bool go = true;
                         if (round > 0) go = wait2<false>(p, ctl, &ctl->empty[slot], (round - 1) & 1);
                         if (go && !aborted2(ctl)) {
                             mbar_arrive_expect_tx(&ctl->full[slot], bytes);
-                            bulk_g2s(smem + oRing + slot * kSlotBytes2 + kTileDst[tile], src, bytes, &ctl->full[slot]);
+                            bulk_g2s(smem + oRing + slot * kSlotBytes2, src, bytes, &ctl->full[slot]);
                         }
                     }
                 }
@@ -188,18 +193,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
                     fence_proxy_async_smem();
                     trace2(p, t, 15 + tile);                     // peers' generic-proxy stores -> my async-proxy reads
                     const uint32_t bbase = smem_u32(smem + actofs[tile]);
-                    for (int kb = 0; kb < 8; ++kb, ++q) {
+                    const uint32_t dcol = tmem + acc[tile];
+                    int kb = 0;
+                    for (int c = 0; c < kChunks[tile]; ++c, ++q) {
                         const uint32_t slot = q % kSlots2, round = q / kSlots2;
                         ok = wait2<false>(p, ctl, &ctl->full[slot], round & 1) && ok;
                         tcgen05_fence_after();
                         if (ok) {
-                            const uint64_t ad = umma_desc_sw128(smem_u32(smem + oRing + slot * kSlotBytes2));
-                            const uint64_t bd = umma_desc_sw128(bbase + kb * (NF * 128));
-                            const uint32_t dcol = tmem + acc[tile];
-                            if (kb == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
-                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
-                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
-                            umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                            const uint32_t a0 = smem_u32(smem + oRing + slot * kSlotBytes2) + (uint32_t)kRow0[tile];
+                            for (int kk = 0; kk < kKbPerChunk[tile]; ++kk, ++kb) {
+                                const uint64_t ad = umma_desc_sw128(a0 + kk * kKbBytes[tile]);
+                                const uint64_t bd = umma_desc_sw128(bbase + kb * (NF * 128));
+                                if (kb == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
+                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                            }
                         }
                         umma_commit(&ctl->empty[slot]);
                     }
@@ -414,7 +423,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) wrnn_loop_tc
 }
 
 cudaError_t set_tc2_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc2_deadline, &cycles, sizeof(cycles)); }
-size_t loop_tc2_image_bytes() { return (size_t)(128 + 96 + 128 + 32 + 30) * 1024; }
+size_t loop_tc2_image_bytes() { return (size_t)(128 + 96 + 128 + 32 + 32) * 1024; }
 
 int loop_tc2_max_clusters() {
     static int cached = -1;

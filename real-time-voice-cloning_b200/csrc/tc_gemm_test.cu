@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(const __grid_const
 //   mode 0: back-to-back MMAs on one accumulator, one commit at the end
 //   mode 1: commit to an mbarrier after every 4 MMAs (the loop kernels' per-k-block pattern), no waiting
 //   mode 2: as 1, and wait for each commit before issuing the next 4 (fully serialised: MMA latency)
+//   mode 5 / 7: rotate over 4 / 2 independent accumulators (N <= 64);  mode 6: M = 64
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int mode, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -135,6 +136,19 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int iters, int
                 umma_f16_c<true>(tmem, umma_desc_advance(a2, 64), umma_desc_advance(bd, 64), idesc);
                 umma_f16_c<true>(tmem, umma_desc_advance(a2, 96), umma_desc_advance(bd, 96), idesc);
                 umma_commit(&bar[0]);
+                continue;
+            }
+            if (mode == 5 || mode == 7) {          // independent accumulators: is the ~100 clk a dependent-accumulate latency?
+                const uint32_t na = mode == 5 ? 4u : 2u;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    umma_f16_c<true>(tmem + (j % na) * 64u, umma_desc_advance(ad, 32 * j), umma_desc_advance(bd, 32 * j), idesc);
+                continue;
+            }
+            if (mode == 6) {                       // M = 64
+                const uint32_t id64 = umma_idesc_f16(64, N);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) umma_f16_c<true>(tmem, umma_desc_advance(ad, 32 * j), umma_desc_advance(bd, 32 * j), id64);
                 continue;
             }
             if (mode == 20) {

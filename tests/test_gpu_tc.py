@@ -85,6 +85,25 @@ def test_tc_loop_matches_f32_loop_many_folds():
     assert float((b["samples"] == c["samples"]).mean()) >= 0.998
 
 
+@pytest.mark.parametrize("mode,seed", [("RAW", 11), ("MOL", 12)])
+def test_tc_loop_two_fold_sets_per_group(mode, seed):
+    """More than 256 folds: each group pipelines two sets of folds through its CTAs (TcParams.nsets = 2)."""
+    from tests.util import norm_mel
+    model, _ = make_model(seed=seed, bits=9, mode=mode)
+    mel = norm_mel(610, 4)                                    # 122000 samples -> 348 folds of 300 + 50
+    a = model.generate_debug(mel, True, 300, 50, want_logits=True, seed=5, max_steps=48, precision=F16)
+    forced = np.pad(a["samples"], ((0, 0), (0, 400 - 48)))
+    b = model.generate_debug(mel, True, 300, 50, forced=forced, want_logits=True, seed=5, max_steps=48)   # f32 loop
+    assert a["samples"].shape[0] > 256
+    assert _rel(a["logits"], b["logits"]) < 1e-3
+    if mode == "RAW":
+        assert float((a["samples"] == b["samples"]).mean()) >= 0.998
+    else:
+        assert float((np.abs(a["samples"] - b["samples"]) < 1e-3).mean()) >= 0.998
+    # rows of different sets must not be mixed up: every fold differs from its neighbours
+    assert len({a["samples"][i, :48].tobytes() for i in range(a["samples"].shape[0])}) == a["samples"].shape[0]
+
+
 def test_tensor_core_front_end_matches_reference():
     """cond_tc.cu (tcgen05, hi/lo fp16 operand pairs) against the reference's MelResNet output and the fp32 SIMT path."""
     from tests.util import golden, norm_mel

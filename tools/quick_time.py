@@ -37,5 +37,9 @@ for tag in which:
     run(raw, tag + " raw9 60s b137", 4800, True, 6000, 1000, prec, reps=1 if prec == 0 else 2)
     run(mol, tag + " cfg3 mol 60s b137", 4800, True, 6000, 1000, prec, reps=1 if prec == 0 else 2)
     run(mol, tag + " cfg3 mol 60s b213", 4800, True, 3000, 1500, prec, reps=1 if prec == 0 else 2)
+    if prec == 1:
+        run(mol, tag + " mol 60s b256 3410/341", 4800, True, 3410, 341, prec)
+        run(mol, tag + " mol 60s b512 1705/170", 4800, True, 1705, 170, prec)
+        run(raw, tag + " raw 60s b512 1705/170", 4800, True, 1705, 170, prec)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/quick_time.json", "w"), indent=1)
