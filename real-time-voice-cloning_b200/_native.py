@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwavernn_b200.so")
+LIB_PATH = os.environ.get("WRNN_B200_LIB") or os.path.join(HERE, "libwavernn_b200.so")   # override: A/B timing of kernel variants
 
 OK, ERR_INVALID, ERR_NOT_LOADED, ERR_CUDA, ERR_TIMEOUT, ERR_SHAPE, ERR_TOO_SHORT = 0, -1, -2, -3, -4, -5, -6
 MODE_RAW, MODE_MOL = 0, 1

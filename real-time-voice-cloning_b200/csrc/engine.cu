@@ -929,8 +929,10 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             e->launches += 2;
         } else if (use_tc) {
             // ---- tensor-core loop: expand the conditioning per sample, then one cooperative launch ----------------
-            // up to 256 folds: one set per group; more: two sets per group, pipelined through the same CTAs
-            const int nsets = (B > kTcGroups * 128) ? kTcSets : 1, nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
+            // up to 256 folds: one set per group; more: two or three sets per group, pipelined through the same CTAs
+            int nsets = std::min(kTcSets, (B + kTcGroups * 128 - 1) / (kTcGroups * 128));
+            if (const char* ev = getenv("WRNN_TC_SETS")) nsets = std::max(nsets, std::min(kTcSets, atoi(ev)));
+            const int nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
             const size_t cs_bytes = (size_t)nvg * S * Mg * 256 * 64;
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
@@ -952,6 +954,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
             tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets;
+            if (const char* ev = getenv("WRNN_TC_FLAGS")) tp.flags = atoi(ev);
             tp.folds = e->bFolds.as<FoldDesc>() + w0;
             tp.B = B; tp.S = S; tp.C = e->C; tp.Cpad = e->Cpad; tp.mode = e->mode;
             tp.seed = rq->seed;
@@ -969,23 +972,27 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             __half* acts[4] = {tp.H1, tp.H2, tp.F1, tp.F2};
             const int box_rows = std::min(128, (Mg + 7) & ~7);     // only the live folds travel
             tp.tile_bytes = box_rows * 128;
-            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_2d(tmaps[i], acts[i], (uint64_t)xrows, kRnn, box_rows, 64));
+            for (int i = 0; i < 4; ++i) CU(make_tmap_f16_kblocks(tmaps[i], acts[i], (uint64_t)xrows, kRnn, box_rows, kTcKbPerOp));
             const bool want_trace = getenv("WRNN_TC_TRACE") != nullptr;
             if (want_trace) {
-                CU(e->bFloor.ensure(16 * 32 * sizeof(long long)));
-                CU(cudaMemsetAsync(e->bFloor.p, 0, 16 * 32 * sizeof(long long), st));
+                CU(e->bFloor.ensure(16 * 192 * sizeof(long long)));
+                CU(cudaMemsetAsync(e->bFloor.p, 0, 16 * 192 * sizeof(long long), st));
                 tp.trace = e->bFloor.as<long long>();
             }
             CU(launch_loop_tc(tp, tmaps, st));
             if (want_trace) {
-                std::vector<long long> tr(16 * 32);
+                std::vector<long long> tr(16 * 192);
                 CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 if (FILE* f = fopen(getenv("WRNN_TC_TRACE"), "w")) {
                     for (int i = 0; i < 16; ++i) {
-                        for (int j = 0; j < 32; ++j) fprintf(f, "%lld ", tr[i * 32 + j] ? tr[i * 32 + j] - tr[i * 32] : -1LL);
+                        for (int j = 0; j < 192; ++j) fprintf(f, "%lld ", tr[i * 192 + j] ? tr[i * 192 + j] - tr[i * 192] : -1LL);
                         fprintf(f, "\n");
                     }
+                    fclose(f);
+                }
+                if (FILE* f = fopen((std::string(getenv("WRNN_TC_TRACE")) + ".abs").c_str(), "w")) {   // step starts (absolute)
+                    for (int i = 0; i < 16; ++i) fprintf(f, "%lld\n", tr[i * 192]);
                     fclose(f);
                 }
             }

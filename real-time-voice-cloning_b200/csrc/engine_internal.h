@@ -58,18 +58,20 @@ cudaError_t set_spin_deadline(long long cycles);
 constexpr int kTcGroups = 2;      // independent groups of CTAs, each with a full fp16 copy of the loop weights
 constexpr int kTcCtas = 64;       // CTAs per group
 constexpr int kTcUnits = 8;       // hidden units per CTA
-constexpr int kTcSets = 2;        // fold sets (<= 128 folds each) a group pipelines through its CTAs
+constexpr int kTcSets = 4;        // fold sets (<= 128 folds each) a group pipelines through its CTAs
 constexpr int kTcMaxFolds = kTcGroups * kTcSets * 128;
+constexpr int kTcKbPerOp = 2;      // k-blocks (64 columns each) one TMA operation of the loop brings in
 
 struct TcParams {
     const unsigned char* wimg;   // [kTcCtas][loop_tc_weight_image_bytes()] per-CTA weight images in shared-memory layout
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
     const float4* CS;            // per-sample conditioning [virtual group][step][row < Mg][256 unit pairs][4 float4] (expand_cond)
     int Mg;                      // folds per virtual group (= group x set); fold f is row f % Mg of virtual group f / Mg
-    int nsets;                   // fold sets per group in this launch (1 or 2)
+    int nsets;                   // fold sets per group in this launch (1..kTcSets)
     const FoldDesc* folds;
     int B, S, C, Cpad, mode;
-    int tile_bytes;              // bytes one TMA tile delivers: box_rows * 128
+    int tile_bytes;              // bytes one k-block of a TMA operation occupies: box_rows * 128
+    int flags;                   // bit 0: epilogue warps release the counters themselves (no publisher warp); 1: 4-slot ring; 2: L2 prefetch of the next record
     unsigned long long seed;
     __half *H1, *H2, *F1, *F2;   // activation exchange, [kTcGroups*kTcSets*128][512] fp16
     unsigned int* counters;      // [kTcGroups*kTcSets][4] arrival counters (monotonic)
@@ -183,6 +185,7 @@ cudaError_t launch_xfade_unfold_f64(const double* y, int F, int S, int overlap, 
 // ---- tensor-core building blocks (tma_host.cu, tc_gemm_test.cu) ----------------------------------------
 cudaError_t make_tmap_f16_2d(void* tmap_out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                              uint32_t box_cols);
+cudaError_t make_tmap_f16_kblocks(void* tmap_out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb);
 cudaError_t run_umma_rate(int N, int iters, int mode, long long* out_dev, cudaStream_t stream);
 cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream);
 

@@ -13,9 +13,18 @@
 //    group's [128 x 512] activation matrix in eight [128 x 64] swizzled tiles through a 4-slot mbarrier ring;
 //    one thread issues 32 tcgen05.mma per stage into TMEM; 16 epilogue warps (thread = fold x 2 units) read the
 //    accumulator with tcgen05.ld and do the GRU / ReLU / sampling math in fp32.
+//  * a TMA operation costs ~0.3-0.4 us whatever its size (measured: tiles of 2 KB and of 16 KB land equally far apart,
+//    and with four sets in flight the tile rate, not the tensor pipe, bounds the step), so one operation brings TWO
+//    k-blocks (a 3-D tensor map [k-block][row][64]: 32 KB) -- four operations per K=512 stage instead of eight.
+//    (Tried and dropped: multicast inside 4-CTA clusters -- L2 already merges up to ~4 readers of a line, no gain;
+//    8-CTA clusters are not co-resident 17 times on B200; replicated exchange matrices -- the extra stores cost more.)
+//  * MOL: fc3 (30 outputs) and the mixture draw run on a dedicated sampler CTA per group (blocks 128..), so no unit-
+//    owning CTA carries an extra stage; the 32 KB this frees in the other CTAs deepens their ring to 6 slots.
 //  * conditioning arrives pre-interpolated per sample (cond.cu: expand_cond), 64 B per thread per step.
 //  * "soft abort": a wait that passes its deadline raises a flag; from then on every wait returns at once, so
 //    all warps still walk the same barriers and the kernel ends cleanly (never a hung GPU).
+#include <cstdio>
+#include <cstdlib>
 #include "engine_internal.h"
 #include "sampling.cuh"
 #include "tc_common.cuh"
@@ -28,8 +37,8 @@ namespace {
 using namespace tc;
 
 constexpr int NEPI = 16;                    // epilogue warps
-constexpr int NT = (NEPI + 2) * 32;         // + TMA producer warp + MMA warp
-constexpr int kSlots = 4, kMaxSlots = 8, kKB = 64, kNKB = kRnn / kKB;   // ring: kSlots x 16 KB, re-cut into up to 8 smaller slots
+constexpr int NT = (NEPI + 3) * 32;         // + TMA producer warp + MMA warp + publisher warp
+constexpr int kSlots = 4, kMaxSlots = 6, kKB = 64, kNKB = kRnn / kKB;   // ring: 4 x 16 KB (6 where the fc3 rows are not resident)
 constexpr int kTileBytes = 128 * 128;       // one [128 rows x 64 fp16] activation tile
 constexpr int NB_ = 64, NC_ = 32, ND_ = 16; // MMA N per stage (E: 16 RAW / 32 MOL)
 constexpr int kWB = 0, kWC = kWB + NB_ * 128 * kNKB, kWD = kWC + NC_ * 128 * kNKB, kWE = kWD + ND_ * 128 * kNKB;
@@ -37,13 +46,14 @@ constexpr int kWBytes = kWE + 32 * 128 * kNKB;          // 147456
 constexpr int kRing = kWBytes;                          // 4 x 16 KB
 constexpr int kBars = kRing + kSlots * kTileBytes;      // mbarriers + misc
 constexpr int kMolScratchBytes = 128 * 4 * 8;           // [128 rows][4] {score, index} for the cooperative MOL draw, per fold set
-constexpr int kMolScratch = kBars + 256;
-constexpr int kBias = kMolScratch + kTcSets * kMolScratchBytes;   // fc3 bias (MOL)
+constexpr int kMolScratch = 0;                           // sampler CTA only: the GRU weight area is unused there
+constexpr int kBias = kBars + 256;                       // fc3 bias (MOL)
+constexpr int kConst = kBias + 128;                      // per-unit constants of the CTA's 8 units (72 floats)
 // tcgen05.mma always reads 128 rows (16 KB) from a slot base; with slots shorter than that the last slot reads up to
 // 8 KB past the ring (into the control words: harmless garbage rows), so the allocation must cover ring + 72 KB
-constexpr int kSmemBytes = (kBias + 128 > kRing + 73728) ? (kBias + 128) : (kRing + 73728);
+constexpr int kSmemBytes = (kConst + 512 > kRing + 73728) ? (kConst + 512) : (kRing + 73728);
 // TMEM columns
-constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kSetCols = 256, kTmemCols = kTcSets * kSetCols;   // per fold set
+constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kSetCols = 128, kTmemCols = 512;   // (sampler CTA: fc3 accumulator at column 0 of the set's block)   // per fold set
 
 struct Ctl {
     uint64_t full[kMaxSlots];
@@ -53,6 +63,7 @@ struct Ctl {
     int abort_local;
 };
 static_assert(sizeof(Ctl) <= 256, "control block");
+static_assert(kTcSets * kSetCols <= kTmemCols, "TMEM columns");
 
 // Abort state: a CTA-local flag in shared memory (cheap to poll) mirrors the global flag (polled rarely: a
 // global load costs ~0.7 us and must stay off the wait paths).
@@ -96,60 +107,151 @@ __device__ __forceinline__ bool wait_x(const TcParams& p, Ctl* c, const unsigned
     while (true) {
         const unsigned long long q = ll_load(w);
         if (ll_tag(q) == tag) { v = ll_val(q); return true; }
+#ifdef WRNN_XSLEEP
+        __nanosleep(WRNN_XSLEEP);          // 64 K threads poll a handful of L2 lines: back off
+#endif
         if (((++spins) & 255) == 0 && spin_check(p, c, t0)) { v = 0.f; return false; }
     }
 }
 
 // optional timeline of one CTA (group 0, CTA 0), steps [kTraceStep0, kTraceStep0+kTraceSteps): SM clocks
-constexpr int kTraceStep0 = 64, kTraceSteps = 16, kTraceSlots = 32;
+constexpr int kTraceStep0 = 64, kTraceSteps = 16, kTraceSlots = 192;
 __device__ __forceinline__ void trace(const TcParams& p, int t, int slot) {
     if (p.trace && blockIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
         p.trace[(t - kTraceStep0) * kTraceSlots + slot] = clock64();
 }
 
+// epilogue timeline of fold sets 0 and 1: slot 32 + 16 s + {0 A enter, 1 x, 2 A done, 3 B enter, 4 B acc, 5 B done, 6 C enter, ...}
+__device__ __forceinline__ void etrace(const TcParams& p, int t, int s, int k) {
+    if (p.trace && threadIdx.x == 0 && s < 2) trace(p, t, 32 + 16 * s + k);
+}
+
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-// epilogue threads only: named barrier, then one thread releases the group counter
-__device__ __forceinline__ void publish_arrive(unsigned int* ctr) {
-    asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-    if (threadIdx.x == 0)   // release at gpu scope: cumulative over the stores the barrier above ordered before it
+// Publishing a stage: the epilogue threads store their activations and ARRIVE on the set's named barrier without
+// waiting; the publisher warp completes that barrier and releases the group counter.  The release fence (a round trip
+// to L2 for the stores, ~0.7 us) is paid by the publisher, so the epilogue warps are already working on the next set.
+// One barrier per fold set is enough: a set's next stage cannot start before its previous publish was consumed.
+constexpr int kPubBar0 = 3;
+__device__ __forceinline__ void publish_arrive(int s, bool inline_release, unsigned int* ctr) {
+    if (inline_release) {              // the epilogue pays for the release itself (shorter chain, busier epilogue)
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        return;
+    }
+    asm volatile("bar.arrive %0, %1;" ::"r"(kPubBar0 + s), "n"((NEPI + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void publisher_release(int s, unsigned int* ctr) {
+    asm volatile("bar.sync %0, %1;" ::"r"(kPubBar0 + s), "n"((NEPI + 1) * 32) : "memory");
+    if ((threadIdx.x & 31) == 0)   // release at gpu scope: cumulative over the stores the barrier above ordered before it
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+
+// Station E, RAW: my CTA's classes of every fold -> exchange words; then one warp per assigned fold samples.
+// Out of line on purpose: its registers (and spills) stay out of the stages that sit on every step's chain.
+__device__ __noinline__ void raw_stage_e(const TcParams& p, Ctl* ctl, uint32_t tacc, int cta, int fold0, int nrows, size_t grow, int t,
+                                         uint2 key) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = (warp & 3) * 32 + lane, up = warp >> 2;
+    const bool live = row < nrows;
+    float d[4];
+    const int cpu = p.C / (kTcCtas * 4);                      // classes per (CTA, up): 2 (C=512) or 4 (C=1024)
+    tmem_ld4(tacc + kAccE + cpu * up, d);
+    tmem_ld_wait();
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < cpu) {
+                const int cls = cta * (cpu * 4) + cpu * up + i;
+                const float v = d[i] + p.bfc3[cls];
+                ll_store(p.bLG + grow * p.Cpad + cls, v, (uint32_t)t + 1u);
+                if (p.logits_out) p.logits_out[((size_t)(fold0 + row) * p.S + t) * p.C + cls] = v;
+            }
+        }
+    }
+    const int srow = cta + kTcCtas * warp;                    // warps 0,1 sample rows cta, cta+64
+    if (warp < 2 && srow < nrows && !aborted(p, ctl)) {
+        const FoldDesc sfd = p.folds[fold0 + srow];
+        const size_t sgrow = grow - row + srow;
+        const unsigned long long* lrow = p.bLG + sgrow * p.Cpad;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)sfd.fold, (uint32_t)sfd.utt, 0u), key);
+        const float u = u01(r.x);
+        int k = (p.C == 512) ? sample_raw_warp<16>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline)
+                             : sample_raw_warp<32>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline);
+        if (k < 0) { raise_abort(p, ctl); k = 0; }
+        if (lane == 0) {
+            const float xs = 2.0f * (float)k / ((float)p.C - 1.0f) - 1.0f;
+            p.samples[(size_t)(fold0 + srow) * p.S + t] = xs;
+            const float fed = p.forced ? p.forced[(size_t)(fold0 + srow) * p.S + t] : xs;
+            ll_store(p.bX + sgrow, fed, (uint32_t)t + 1u);
+        }
+    }
 }
 
 }  // namespace
 
-// per-thread state of one fold set (a CTA serves up to kTcSets sets of <= 128 folds, software-pipelined: while one set's
-// activations travel and its MMAs run, the epilogue warps work on the other set)
+// The schedule.  Per step a fold set passes five stations: A (GRU1 on the new sample), B, C, D (an MMA stage and its
+// epilogue each) and E (fc3 + the draw), each about one exchange + one K=512 reduction long.  Time is cut into slots; in
+// slot k, set s is at station (k - off(s)) mod 5 of step (k - off(s)) / 5, with off(s) = s * skew: with skew > 0 the sets sit at
+// DIFFERENT stations at any moment, so every in-order resource (TMA/MMA queue, epilogue warps, publisher, sampler CTA)
+// sees at most one job per set per slot and never queues one set's stage behind the same stage of all the others.
+// Every role enumerates the same (slot, set) sequence and picks the stations it serves.
+__device__ __forceinline__ bool job_of(int k, int s, int skew, int S, int& t, int& stn) {
+    const int idx = k - s * skew;
+    if (idx < 0 || idx >= 5 * S) return false;
+    t = idx / 5;
+    stn = idx - 5 * t;
+    return true;
+}
+
+// per-thread recurrent state of one fold set (a CTA serves up to kTcSets sets of <= 128 folds, software-pipelined: while
+// one set's activations travel and its MMAs run, the epilogue warps work on the other sets).  Everything else about a
+// set is recomputed from its index, and the conditioning record is fetched stage by stage just before the wait of that
+// stage, so that only these registers stay live across the other sets' stages.
+#ifndef WRNN_JIT
+#define WRNN_JIT 0     // 1: fetch the conditioning record stage by stage (fewer live registers; measured 5-8 % slower)
+#endif
 struct SetState {
-    int nrows, fold0;            // live folds of this virtual group, its first fold (launch index)
-    bool live;                   // my TMEM lane (row) carries a fold
     uint32_t fold, utt;          // Philox counter words of my fold
-    size_t grow;                 // my row in the exchange buffers
-    uint32_t tacc;               // TMEM address: my lane quarter, this set's column block
-    unsigned int* ctrs;          // H1, H2, F1, F2 arrival counters of this virtual group
-    const float4* cs;            // conditioning records of (this virtual group, my row, my unit pair), step 0
     float x, h1[2], h2[2], p3[2];
-    float4 ca, cb, cc, cd;
+#if !WRNN_JIT
+    float2 cr; float4 cz; float4 c34;      // whole conditioning record fetched in stage A
+#endif
 };
 
+template <int NSETS>
 __global__ void __launch_bounds__(NT, 1)
 wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
-                    const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2, TcParams p) {
+                    const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + kBars);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x / kTcCtas, cta = blockIdx.x % kTcCtas;       // group, CTA inside the group
-    const int nsets = p.nsets;                                            // fold sets per group (1 or 2)
-    const bool has_e = (p.mode == 0) || (cta == 0);                        // MOL: only CTA 0 of a group runs fc3
-    const int NE = (p.mode == 0) ? 16 : 32;
+    const bool mol = p.mode == 1;
+    const int nmain = kTcGroups * kTcCtas;
+    const bool sampler = (int)blockIdx.x >= nmain;                        // MOL: blocks past the groups run fc3 + the draw
+    const int g = sampler ? (int)blockIdx.x - nmain : (int)blockIdx.x / kTcCtas;   // group
+    const int cta = sampler ? 0 : (int)blockIdx.x % kTcCtas;              // unit-owning CTA inside the group
+    const bool idle = false;
+    constexpr int nsets = NSETS;                                          // fold sets per group (1..kTcSets)
+    const int NE = mol ? 32 : 16;
+    const int ph0 = sampler ? 3 : 0, ph1 = (mol && !sampler) ? 3 : 4;     // stages whose MMAs this CTA runs
+    const int skew = (p.flags >> 4) & 7;                                  // stations set s runs behind set s-1 (0: all sets in phase)
+    const int nslot_total = 5 * p.S + skew * (nsets - 1);                  // slots of the schedule (job_of)
+    const bool deep = mol && !sampler && !(p.flags & 2);
+    const uint32_t ring0 = deep ? kWE : kRing, nslots = deep ? 3u : 2u;       // ring of 32 KB slots (two k-blocks each)
+    constexpr uint32_t slot_bytes = kTcKbPerOp * kTileBytes;
+    const uint32_t kb_bytes = (uint32_t)p.tile_bytes;                         // the second k-block of a slot starts here
+    // (measured: packing shorter slots so that the 16 KB MMA read of one slot overlaps the TMA target of the next is
+    //  ~20 % slower per step than keeping the slots 16 KB apart, so the stride stays at the full tile)
 
     // ---- one-time setup ---------------------------------------------------------------------------------------
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)cta * kWBytes);
-        uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < kWBytes / 16; i += NT) dst[i] = src[i];
+    if (!idle) {
+        const int w0 = sampler ? kWE : 0, w1 = (mol && !sampler) ? kWE : kWBytes;
+        const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)cta * kWBytes + w0);
+        uint4* dst = reinterpret_cast<uint4*>(smem + w0);
+        for (int i = tid; i < (w1 - w0) / 16; i += NT) dst[i] = src[i];
         fence_proxy_async_smem();
     }
     if (tid == 0) {
@@ -158,42 +260,55 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         ctl->abort_local = 0;
         mbar_fence_init();
     }
-    if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (p.mode == 1 && tid < 30) ? p.bfc3[tid] : 0.f;
-    if (warp == 0) tmem_alloc(&ctl->tmem, kTmemCols);
+    if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (mol && tid < 30) ? p.bfc3[tid] : 0.f;
+    if (tid < 72) {                     // [unit pair 4][v1 r,z,n x2 | v2 r,z,n x2 | v3 x2 | b_hn1 x2 | b_hn2 x2]
+        const int up_ = tid / 18, i = tid % 18, u = i & 1, j = cta * kTcUnits + 2 * up_ + u;
+        float v;
+        if (i < 6) v = p.v1[(i >> 1) * kRnn + j];
+        else if (i < 12) v = p.v2[((i - 6) >> 1) * kRnn + j];
+        else if (i < 14) v = p.v3[j];
+        else if (i < 16) v = p.bhn1[j];
+        else v = p.bhn2[j];
+        reinterpret_cast<float*>(smem + kConst)[tid] = v;
+    }
+    if (warp == 0 && !idle) tmem_alloc(&ctl->tmem, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = ctl->tmem;
-    // activation ring: kSlots x 16 KB
-    // (measured: packing shorter slots so that the 16 KB MMA read of one slot overlaps the TMA target of the next is
-    //  ~20 % slower per step than keeping the slots 16 KB apart, so the stride stays at the full tile)
-    constexpr uint32_t slot_bytes = kTileBytes, nslots = kSlots;
 
+    if (idle) {
+        // nothing: straight to the teardown barrier
+    } else
     if (warp == NEPI) {
         // =================================== TMA producer ===================================================
         if (lane == 0) {
             const CUtensorMap* maps[4] = {&tmH1, &tmH2, &tmF1, &tmF2};
             for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
             uint32_t q = 0;
-            const int nph = has_e ? 4 : 3;
-            for (int t = 0; t < p.S; ++t) {
-                for (int ph = 0; ph < nph; ++ph) {
-                    for (int s = 0; s < nsets; ++s) {
-                        const int vg = g * nsets + s;
-                        const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
-                        fence_proxy_async();
-                        if (s == 0) trace(p, t, 12 + ph);
-                        for (int kb = 0; kb < kNKB; ++kb, ++q) {
-                            const uint32_t slot = q % nslots, round = q / nslots;
-                            bool go = ok;
-                            if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
-                            if (go && !aborted(p, ctl)) {
-                                mbar_arrive_expect_tx(&ctl->full[slot], (uint32_t)p.tile_bytes);
-                                tma_load_2d(smem + kRing + slot * slot_bytes, maps[ph], &ctl->full[slot], kb * kKB, vg * 128);
-                            }
+            for (int k = 0; k < nslot_total; ++k) {
+                for (int s = 0; s < nsets; ++s) {
+                    int t, stn;
+                    if (!job_of(k, s, skew, p.S, t, stn)) continue;
+                    const int ph = stn - 1;                       // stations B..E consume the exchange H1, H2, F1, F2
+                    if (ph < ph0 || ph >= ph1) continue;
+                    const int vg = g * nsets + s;
+                    const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
+                    fence_proxy_async();
+                    if (s == 0) trace(p, t, 12 + ph);
+                    trace(p, t, 64 + (ph * 4 + s) * 4 + 0);          // queue timeline: counter seen
+                    for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
+                        const uint32_t slot = q % nslots, round = q / nslots;
+                        bool go = ok;
+                        if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
+                        if (ph == 0 && s == 1) trace(p, t, 128 + kb);              // tile timeline of one job: slot free
+                        if (go && !aborted(p, ctl)) {
+                            mbar_arrive_expect_tx(&ctl->full[slot], kTcKbPerOp * kb_bytes);
+                            tma_load_3d(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
                         }
-                        if (s == 0) trace(p, t, 16 + ph);
                     }
+                    if (s == 0) trace(p, t, 16 + ph);
+                    trace(p, t, 64 + (ph * 4 + s) * 4 + 1);          // last tile issued
                 }
             }
         }
@@ -202,84 +317,113 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         if (lane == 0) {
             const uint32_t wofs[4] = {kWB, kWC, kWD, kWE};
             const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
-            const uint32_t acc[4] = {kAccB, kAccC, kAccD, kAccE};
+            const uint32_t acc[4] = {kAccB, kAccC, kAccD, sampler ? 0u : (uint32_t)kAccE};
             uint32_t q = 0;
-            const int nph = has_e ? 4 : 3;
-            for (int t = 0; t < p.S; ++t) {
-                for (int ph = 0; ph < nph; ++ph) {
+            for (int k = 0; k < nslot_total; ++k) {
+                for (int s = 0; s < nsets; ++s) {
+                    int t, stn;
+                    if (!job_of(k, s, skew, p.S, t, stn)) continue;
+                    const int ph = stn - 1;
+                    if (ph < ph0 || ph >= ph1) continue;
                     const uint32_t idesc = umma_idesc_f16(128, (int)ncol[ph]);
-                    for (int s = 0; s < nsets; ++s) {
-                        const uint32_t dcol = tmem + (uint32_t)s * kSetCols + acc[ph];
-                        for (int kb = 0; kb < kNKB; ++kb, ++q) {
-                            const uint32_t slot = q % nslots, round = q / nslots;
-                            if (s == 0 && ph == 0 && kb < 4) trace(p, t, 24 + kb);
-                            const bool ok = wait_mbar(p, ctl, &ctl->full[slot], round & 1);
-                            tcgen05_fence_after();
-                            if (s == 0 && ph == 0 && kb < 4) trace(p, t, 20 + kb);
-                            if (ok) {
-                                const uint64_t ad = umma_desc_sw128(smem_u32(smem + kRing + slot * slot_bytes));
-                                const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs[ph] + kb * ncol[ph] * 128));
-                                if (kb == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
+                    const uint32_t dcol = tmem + (uint32_t)s * kSetCols + acc[ph];
+                    for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
+                        const uint32_t slot = q % nslots, round = q / nslots;
+                        if (s == 0 && ph == 0 && kb < 4) trace(p, t, 24 + kb);
+                        const bool ok = wait_mbar(p, ctl, &ctl->full[slot], round & 1);
+                        tcgen05_fence_after();
+                        if (s == 0 && ph == 0 && kb < 4) trace(p, t, 20 + kb);
+                        if (kb == 0) trace(p, t, 64 + (ph * 4 + s) * 4 + 2);     // first tile landed
+                        if (ph == 0 && s == 1) trace(p, t, 136 + kb);              // tile landed (MMA thread saw it)
+                        if (ok) {
+#pragma unroll
+                            for (int kk = 0; kk < kTcKbPerOp; ++kk) {
+                                const uint64_t ad = umma_desc_sw128(smem_u32(smem + ring0 + slot * slot_bytes) + kk * kb_bytes);
+                                const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs[ph] + (kb + kk) * ncol[ph] * 128));
+                                if (kb + kk == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
                                 umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
                                 umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
                                 umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
                             }
-                            umma_commit(&ctl->empty[slot]);
                         }
-                        umma_commit(&ctl->accfull[s * 4 + ph]);
+                        umma_commit(&ctl->empty[slot]);
+                        if (ph == 0 && s == 1) trace(p, t, 144 + kb);              // MMAs + commit issued
                     }
+                    umma_commit(&ctl->accfull[s * 4 + ph]);
+                    trace(p, t, 64 + (ph * 4 + s) * 4 + 3);          // all MMAs of the job issued
                 }
             }
+        }
+    } else if (warp == NEPI + 2) {
+        // =================================== publisher ======================================================
+        // walks the stages in the order the epilogue warps publish them
+        if (!sampler && !(p.flags & 1)) {
+            for (int k = 0; k < nslot_total; ++k)
+                for (int s = 0; s < nsets; ++s) {
+                    int t, stn;
+                    if (job_of(k, s, skew, p.S, t, stn) && stn < 4) publisher_release(s, p.counters + (g * nsets + s) * 4 + stn);
+                }
         }
     } else {
         // =================================== epilogue warps =================================================
         // thread = (fold row, unit pair up): TMEM lane = row, my units are 8*cta + 2*up + {0,1}
         const int row = (warp & 3) * 32 + lane, up = warp >> 2;
         const int j0 = cta * kTcUnits + 2 * up;                           // first of my two hidden units
-        float v1[6], v2[6], v3[2], bh1[2], bh2[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-#pragma unroll
-            for (int gt = 0; gt < 3; ++gt) { v1[gt * 2 + u] = p.v1[gt * kRnn + j0 + u]; v2[gt * 2 + u] = p.v2[gt * kRnn + j0 + u]; }
-            v3[u] = p.v3[j0 + u]; bh1[u] = p.bhn1[j0 + u]; bh2[u] = p.bhn2[j0 + u];
-        }
+        // per-unit constants of my two units: shared memory (every lane of a warp reads the same word: a broadcast), not registers
+        const float* kc = reinterpret_cast<const float*>(smem + kConst) + up * 18;
+#define v1 (kc + 0)
+#define v2 (kc + 6)
+#define v3 (kc + 12)
+#define bh1 (kc + 14)
+#define bh2 (kc + 16)
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const bool inl = (p.flags & 1) != 0;
         const size_t cs_rec = (size_t)kTcCtas * 4 * 4;                      // float4 per (t,row) record = 1024
-        SetState st[kTcSets];
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        SetState st[NSETS];
+        int nrows_[NSETS];
 #pragma unroll
-        for (int s = 0; s < kTcSets; ++s) {
-            SetState& S = st[s];
-            const int vg = g * nsets + s;
-            S.fold0 = vg * p.Mg;
-            S.nrows = (s < nsets) ? max(0, min(p.Mg, p.B - S.fold0)) : 0;
-            S.live = row < S.nrows;
-            const FoldDesc fd = p.folds[S.live ? S.fold0 + row : 0];
-            S.fold = (uint32_t)fd.fold; S.utt = (uint32_t)fd.utt;
-            S.grow = (size_t)vg * 128 + row;
-            S.tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)s * kSetCols;
-            S.ctrs = p.counters + vg * 4;
-            S.cs = p.CS + (((size_t)vg * p.S) * p.Mg + row) * cs_rec + ((size_t)cta * 4 + up) * 4;
-            S.x = 0.f; S.h1[0] = S.h1[1] = S.h2[0] = S.h2[1] = S.p3[0] = S.p3[1] = 0.f;
-            S.ca = S.cb = S.cc = S.cd = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < NSETS; ++s) {
+            const int fold0 = (g * nsets + s) * p.Mg;
+            nrows_[s] = max(0, min(p.Mg, p.B - fold0));
+            const FoldDesc fd = p.folds[row < nrows_[s] ? fold0 + row : 0];
+            st[s].fold = (uint32_t)fd.fold; st[s].utt = (uint32_t)fd.utt;
+            st[s].x = 0.f; st[s].h1[0] = st[s].h1[1] = st[s].h2[0] = st[s].h2[1] = st[s].p3[0] = st[s].p3[1] = 0.f;
         }
+        // per-set quantities derived from the set index
+#define SET_VIEW(s)                                                                                              \
+        const int vg = g * nsets + (s);                                                                          \
+        const int fold0 = vg * p.Mg;                                                                             \
+        const int nrows = nrows_[s];                                                                             \
+        const bool live = row < nrows;                                                                           \
+        const size_t grow = (size_t)vg * 128 + row;                                                              \
+        const uint32_t tacc = tlane + (uint32_t)(s) * kSetCols;                                                  \
+        unsigned int* const ctrs = p.counters + vg * 4;                                                          \
+        const float4* const cs = p.CS + (((size_t)vg * p.S + t) * p.Mg + row) * cs_rec + ((size_t)cta * 4 + up) * 4;   \
+        (void)fold0; (void)nrows; (void)live; (void)grow; (void)tacc; (void)ctrs; (void)cs;
 
         // ---- A: x_{t-1}, GRU1 for my 2 units, publish h1 ---------------------------------------------------
         auto stageA = [&](SetState& S, const int s, const int t) {
-            if (S.live) {                    // conditioning of this step (issued before the wait on x)
-                const float4* cs = S.cs + (size_t)t * p.Mg * cs_rec;
-                S.ca = __ldcs(cs); S.cb = __ldcs(cs + 1); S.cc = __ldcs(cs + 2); S.cd = __ldcs(cs + 3);
-            }
+            SET_VIEW(s)
+            float4 ca = make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 cn = make_float2(0.f, 0.f);
+            if (live) { ca = __ldcs(cs); cn = __ldcs(reinterpret_cast<const float2*>(cs + 1)); }   // issued before the wait on x
+#if !WRNN_JIT
+            if (live) { S.cr = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); S.cz = __ldcs(cs + 2); S.c34 = __ldcs(cs + 3); }
+#endif
             if (tid == 0) trace(p, t, s == 0 ? 0 : 31);
+            etrace(p, t, s, 0);
             S.x = 0.f;
-            if (t > 0 && S.live) wait_x(p, ctl, p.bX + S.grow, (uint32_t)t, S.x);
+            if (t > 0 && live) wait_x(p, ctl, p.bX + grow, (uint32_t)t, S.x);
             if (tid == 0 && s == 0) trace(p, t, 1);
+            etrace(p, t, s, 1);
             float gh[8];
-            if (t > 0) { tmem_ld8(S.tacc + kAccB + 16 * up + 8, gh); tmem_ld_wait(); }
+            if (t > 0) { tmem_ld8(tacc + kAccB + 16 * up + 8, gh); tmem_ld_wait(); }
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gh[i] = 0.f;
             }
-            const float c1r[2] = {S.ca.x, S.ca.y}, c1z[2] = {S.ca.z, S.ca.w}, c1n[2] = {S.cb.x, S.cb.y};
+            const float c1r[2] = {ca.x, ca.y}, c1z[2] = {ca.z, ca.w}, c1n[2] = {cn.x, cn.y};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float r = sigmoid_fast(fmaf(v1[0 + u], S.x, c1r[u]) + gh[0 + u]);
@@ -287,26 +431,37 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 const float n = tanh_fast(fmaf(v1[4 + u], S.x, c1n[u]) + r * (gh[4 + u] + bh1[u]));
                 S.h1[u] = (1.0f - z) * n + z * S.h1[u];
             }
-            if (S.live) *reinterpret_cast<__half2*>(p.H1 + S.grow * kRnn + j0) = __floats2half2_rn(S.h1[0], S.h1[1]);
+            if (live) *reinterpret_cast<__half2*>(p.H1 + grow * kRnn + j0) = __floats2half2_rn(S.h1[0], S.h1[1]);
             tcgen05_fence_before();
-            publish_arrive(S.ctrs + 0);
+            publish_arrive(s, inl, ctrs + 0);
             if (tid == 0 && s == 0) trace(p, t, 2);
+            etrace(p, t, s, 2);
         };
         // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 -------------------------------------------
         auto stageB = [&](SetState& S, const int s, const int t) {
+            SET_VIEW(s)
+            float2 cr = make_float2(0.f, 0.f);
+            float4 cz = make_float4(0.f, 0.f, 0.f, 0.f);
+#if WRNN_JIT
+            if (live) { cr = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); cz = __ldcs(cs + 2); }
+#else
+            if (live) { cr = S.cr; cz = S.cz; }
+#endif
             float pb[8], gh[8];
+            etrace(p, t, s, 3);
             wait_mbar(p, ctl, &ctl->accfull[s * 4 + 0], (uint32_t)t & 1u);
             tcgen05_fence_after();
             if (tid == 0 && s == 0) trace(p, t, 3);
-            tmem_ld8(S.tacc + kAccB + 16 * up, pb);
-            if (t > 0) tmem_ld8(S.tacc + kAccC + 8 * up, gh);
+            etrace(p, t, s, 4);
+            tmem_ld8(tacc + kAccB + 16 * up, pb);
+            if (t > 0) tmem_ld8(tacc + kAccC + 8 * up, gh);
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) gh[i] = 0.f;
             }
             tmem_ld_wait();
             if (tid == 0 && s == 0) trace(p, t, 28);
-            const float c2r[2] = {S.cb.z, S.cb.w}, c2z[2] = {S.cc.x, S.cc.y}, c2n[2] = {S.cc.z, S.cc.w};
+            const float c2r[2] = {cr.x, cr.y}, c2z[2] = {cz.x, cz.y}, c2n[2] = {cz.z, cz.w};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float r = sigmoid_fast(pb[0 + u] + fmaf(v2[0 + u], S.x, c2r[u]) + gh[0 + u]);
@@ -315,55 +470,84 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 S.h2[u] = (1.0f - z) * n + z * S.h2[u];
                 S.p3[u] = pb[6 + u];
             }
-            if (S.live) *reinterpret_cast<__half2*>(p.H2 + S.grow * kRnn + j0) = __floats2half2_rn(S.h2[0], S.h2[1]);
+            if (live) *reinterpret_cast<__half2*>(p.H2 + grow * kRnn + j0) = __floats2half2_rn(S.h2[0], S.h2[1]);
             if (tid == 0 && s == 0) trace(p, t, 29);
             tcgen05_fence_before();
-            publish_arrive(S.ctrs + 1);
+            publish_arrive(s, inl, ctrs + 1);
             if (tid == 0 && s == 0) trace(p, t, 4);
+            etrace(p, t, s, 5);
         };
         // ---- C: [gh2' | W_fc1a h2] ; f1 ; publish ------------------------------------------------------------
         auto stageC = [&](SetState& S, const int s, const int t) {
+            SET_VIEW(s)
+            float2 c3 = make_float2(0.f, 0.f);
+#if WRNN_JIT
+            if (live) c3 = __ldcs(reinterpret_cast<const float2*>(cs + 3));
+#else
+            if (live) c3 = make_float2(S.c34.x, S.c34.y);
+#endif
             float pb[8];
+            etrace(p, t, s, 6);
             wait_mbar(p, ctl, &ctl->accfull[s * 4 + 1], (uint32_t)t & 1u);
             tcgen05_fence_after();
             if (tid == 0 && s == 0) trace(p, t, 5);
-            tmem_ld8(S.tacc + kAccC + 8 * up, pb);
+            etrace(p, t, s, 7);
+            tmem_ld8(tacc + kAccC + 8 * up, pb);
             tmem_ld_wait();
-            const float f0 = fmaxf(S.p3[0] + pb[6] + fmaf(v3[0], S.x, S.cd.x), 0.f);
-            const float f1 = fmaxf(S.p3[1] + pb[7] + fmaf(v3[1], S.x, S.cd.y), 0.f);
-            if (S.live) *reinterpret_cast<__half2*>(p.F1 + S.grow * kRnn + j0) = __floats2half2_rn(f0, f1);
+            const float f0 = fmaxf(S.p3[0] + pb[6] + fmaf(v3[0], S.x, c3.x), 0.f);
+            const float f1 = fmaxf(S.p3[1] + pb[7] + fmaf(v3[1], S.x, c3.y), 0.f);
+            if (live) *reinterpret_cast<__half2*>(p.F1 + grow * kRnn + j0) = __floats2half2_rn(f0, f1);
             tcgen05_fence_before();
-            publish_arrive(S.ctrs + 2);
+            publish_arrive(s, inl, ctrs + 2);
             if (tid == 0 && s == 0) trace(p, t, 6);
+            etrace(p, t, s, 8);
         };
         // ---- D: fc2 ; publish ----------------------------------------------------------------------------------
         auto stageD = [&](SetState& S, const int s, const int t) {
+            SET_VIEW(s)
+            float2 c4 = make_float2(0.f, 0.f);
+#if WRNN_JIT
+            if (live) {
+                c4 = __ldcs(reinterpret_cast<const float2*>(cs + 3) + 1);
+                if (t + 1 < p.S && (p.flags & 4)) {           // next step's record: pull both sectors into L2 now (no registers held)
+                    const float4* nx = cs + (size_t)p.Mg * cs_rec;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 2));
+                }
+            }
+#else
+            if (live) c4 = make_float2(S.c34.z, S.c34.w);
+#endif
+            etrace(p, t, s, 9);
             wait_mbar(p, ctl, &ctl->accfull[s * 4 + 2], (uint32_t)t & 1u);
             tcgen05_fence_after();
             if (tid == 0 && s == 0) trace(p, t, 7);
+            etrace(p, t, s, 10);
             float d[4];
-            tmem_ld4(S.tacc + kAccD + 2 * up, d);
+            tmem_ld4(tacc + kAccD + 2 * up, d);
             tmem_ld_wait();
-            if (S.live) *reinterpret_cast<__half2*>(p.F2 + S.grow * kRnn + j0) = __floats2half2_rn(fmaxf(d[0] + S.cd.z, 0.f), fmaxf(d[1] + S.cd.w, 0.f));
+            if (live) *reinterpret_cast<__half2*>(p.F2 + grow * kRnn + j0) = __floats2half2_rn(fmaxf(d[0] + c4.x, 0.f), fmaxf(d[1] + c4.y, 0.f));
             tcgen05_fence_before();
-            publish_arrive(S.ctrs + 3);
+            publish_arrive(s, inl, ctrs + 3);
             if (tid == 0 && s == 0) trace(p, t, 8);
+            etrace(p, t, s, 11);
         };
         // ---- E: fc3 + sampling ---------------------------------------------------------------------------------
         auto stageE = [&](SetState& S, const int s, const int t) {
+            SET_VIEW(s)
             const uint32_t par = (uint32_t)t & 1u;
             if (p.mode == 1) {
                 // MOL (vocoder/distribution.py:104-140): CTA 0 of the group has all 30 outputs of a fold in one TMEM
                 // lane.  The four threads of a fold split the Gumbel draws (thread `up` owns Philox block `up`, i.e.
                 // mixtures 4up..4up+3), meet through shared memory, and thread up==2 (which also holds the logistic
                 // uniform, block 2 word 2) finishes the draw.
-                if (cta == 0) {
+                if (sampler) {
                     wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
                     tcgen05_fence_after();
                     if (tid == 0 && s == 0) trace(p, t, 9);
                     float lg[32];
-                    tmem_ld8(S.tacc + kAccE + 0, lg); tmem_ld8(S.tacc + kAccE + 8, lg + 8);
-                    tmem_ld8(S.tacc + kAccE + 16, lg + 16); tmem_ld8(S.tacc + kAccE + 24, lg + 24);
+                    tmem_ld8(tacc + 0, lg); tmem_ld8(tacc + 8, lg + 8);
+                    tmem_ld8(tacc + 16, lg + 16); tmem_ld8(tacc + 24, lg + 24);
                     tmem_ld_wait();
                     const float* sbias = reinterpret_cast<const float*>(smem + kBias);
                     float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch + s * kMolScratchBytes);
@@ -384,7 +568,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     }
                     scratch[row * 4 + up] = make_float2(best, __int_as_float(kbest));
                     asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");
-                    if (up == 2 && S.live) {
+                    if (up == 2 && live) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {          // candidates of up = 0, 1 come first (lower indices win ties)
                             const float2 c = scratch[row * 4 + q];
@@ -398,83 +582,79 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                         const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
                         float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
                         xs = fminf(fmaxf(xs, -1.0f), 1.0f);
-                        p.samples[(size_t)(S.fold0 + row) * p.S + t] = xs;
-                        const float fed = p.forced ? p.forced[(size_t)(S.fold0 + row) * p.S + t] : xs;
-                        ll_store(p.bX + S.grow, fed, (uint32_t)t + 1u);
+                        p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
+                        const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
+                        ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
                         if (p.logits_out)
-                            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(S.fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
+                            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
                     }
                     tcgen05_fence_before();
                     if (tid == 0 && s == 0) trace(p, t, 10);
                 }
             } else {
-                // RAW: my CTA's classes of every fold -> exchange words; then one warp per assigned fold samples
                 wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
                 tcgen05_fence_after();
-                float d[4];
-                const int cpu = p.C / (kTcCtas * 4);                      // classes per (CTA, up): 2 (C=512) or 4 (C=1024)
-                tmem_ld4(S.tacc + kAccE + cpu * up, d);
-                tmem_ld_wait();
-                if (S.live) {
-                    for (int i = 0; i < cpu; ++i) {
-                        const int cls = cta * (cpu * 4) + cpu * up + i;
-                        const float v = d[i] + p.bfc3[cls];
-                        ll_store(p.bLG + S.grow * p.Cpad + cls, v, (uint32_t)t + 1u);
-                        if (p.logits_out) p.logits_out[((size_t)(S.fold0 + row) * p.S + t) * p.C + cls] = v;
-                    }
-                }
+                raw_stage_e(p, ctl, tacc, cta, fold0, nrows, grow, t, key);
                 tcgen05_fence_before();
-                const int srow = cta + kTcCtas * warp;                    // warps 0,1 sample rows cta, cta+64
-                if (warp < 2 && srow < S.nrows && !aborted(p, ctl)) {
-                    const FoldDesc sfd = p.folds[S.fold0 + srow];
-                    const size_t sgrow = S.grow - row + srow;
-                    const unsigned long long* lrow = p.bLG + sgrow * p.Cpad;
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)sfd.fold, (uint32_t)sfd.utt, 0u), key);
-                    const float u = u01(r.x);
-                    int k = (p.C == 512) ? sample_raw_warp<16>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline)
-                                         : sample_raw_warp<32>(lrow, (uint32_t)t + 1u, u, p.abort_flag, g_tc_deadline);
-                    if (k < 0) { raise_abort(p, ctl); k = 0; }
-                    if (lane == 0) {
-                        const float xs = 2.0f * (float)k / ((float)p.C - 1.0f) - 1.0f;
-                        p.samples[(size_t)(S.fold0 + srow) * p.S + t] = xs;
-                        const float fed = p.forced ? p.forced[(size_t)(S.fold0 + srow) * p.S + t] : xs;
-                        ll_store(p.bX + sgrow, fed, (uint32_t)t + 1u);
-                    }
-                }
             }
         };
 
-        const bool two = nsets > 1;
-        for (int t = 0; t < p.S; ++t) {
-            stageA(st[0], 0, t); if (two) stageA(st[1], 1, t);
-            stageB(st[0], 0, t); if (two) stageB(st[1], 1, t);
-            stageC(st[0], 0, t); if (two) stageC(st[1], 1, t);
-            stageD(st[0], 0, t); if (two) stageD(st[1], 1, t);
-            stageE(st[0], 0, t); if (two) stageE(st[1], 1, t);
-            if (blockIdx.x == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
-                *reinterpret_cast<volatile int*>(p.progress) = t;
+        for (int k = 0; k < nslot_total; ++k) {
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s) {
+                int t, stn;
+                if (!job_of(k, s, skew, p.S, t, stn)) continue;
+                if (sampler) {
+                    if (stn == 4) stageE(st[s], s, t);
+                } else if (stn == 0) stageA(st[s], s, t);
+                else if (stn == 1) stageB(st[s], s, t);
+                else if (stn == 2) stageC(st[s], s, t);
+                else if (stn == 3) stageD(st[s], s, t);
+                else if (!mol) stageE(st[s], s, t);
+            }
+            if (blockIdx.x == 0 && tid == 0 && (k % 500) == 0 && p.progress) {
+                *reinterpret_cast<volatile int*>(p.progress) = k / 5;
                 __threadfence_system();
             }
         }
+#undef SET_VIEW
+#undef v1
+#undef v2
+#undef v3
+#undef bh1
+#undef bh2
     }
     // ---- teardown ---------------------------------------------------------------------------------------------
     if (aborted(p, ctl)) __nanosleep(200000);      // let any TMA still in flight land before the CTA goes away
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    if (warp == 0 && !idle) tmem_dealloc(tmem, kTmemCols);
 }
 
 cudaError_t set_tc_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc_deadline, &cycles, sizeof(cycles)); }
 size_t loop_tc_weight_image_bytes() { return kWBytes; }
 
-cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps /* 4 x CUtensorMap */, cudaStream_t stream) {
-    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
+// grid: the unit-owning CTAs of both groups, plus (MOL) one sampler CTA per group; cooperative launch because all CTAs
+// spin on each other and must be co-resident
+template <int NSETS>
+static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_tc_kernel<NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
     if (err != cudaSuccess) return err;
-    const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmaps);
     TcParams pp = p;
     void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
-    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel, dim3(kTcGroups * kTcCtas), dim3(NT), args,
-                                       kSmemBytes + 1024, stream);
+    const int grid = kTcGroups * kTcCtas + (p.mode == 1 ? kTcGroups : 0);
+    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel<NSETS>, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
+}
+
+cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps /* 4 x CUtensorMap */, cudaStream_t stream) {
+    const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmaps);
+    switch (p.nsets) {
+        case 1: return launch_loop_tc_n<1>(p, m, stream);
+        case 2: return launch_loop_tc_n<2>(p, m, stream);
+        case 3: return launch_loop_tc_n<3>(p, m, stream);
+        case 4: return launch_loop_tc_n<4>(p, m, stream);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace wrnn

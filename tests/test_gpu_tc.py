@@ -86,11 +86,11 @@ def test_tc_loop_matches_f32_loop_many_folds():
 
 
 @pytest.mark.parametrize("mode,seed", [("RAW", 11), ("MOL", 12)])
-def test_tc_loop_two_fold_sets_per_group(mode, seed):
-    """More than 256 folds: each group pipelines two sets of folds through its CTAs (TcParams.nsets = 2)."""
+def test_tc_loop_several_fold_sets_per_group(mode, seed):
+    """More than 256 folds: each group pipelines two or three sets of folds through its CTAs (TcParams.nsets)."""
     from tests.util import norm_mel
     model, _ = make_model(seed=seed, bits=9, mode=mode)
-    mel = norm_mel(610, 4)                                    # 122000 samples -> 348 folds of 300 + 50
+    mel = norm_mel(1400 if mode == "MOL" else 1000, 4)       # RAW: 571 folds of 300 + 50 (three sets); MOL: 800 folds (four sets)
     a = model.generate_debug(mel, True, 300, 50, want_logits=True, seed=5, max_steps=48, precision=F16)
     forced = np.pad(a["samples"], ((0, 0), (0, 400 - 48)))
     b = model.generate_debug(mel, True, 300, 50, forced=forced, want_logits=True, seed=5, max_steps=48)   # f32 loop

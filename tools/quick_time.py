@@ -41,5 +41,7 @@ for tag in which:
         run(mol, tag + " mol 60s b256 3410/341", 4800, True, 3410, 341, prec)
         run(mol, tag + " mol 60s b512 1705/170", 4800, True, 1705, 170, prec)
         run(raw, tag + " raw 60s b512 1705/170", 4800, True, 1705, 170, prec)
+        run(mol, tag + " mol 60s b766 1140/114", 4800, True, 1140, 114, prec)
+        run(raw, tag + " raw 60s b766 1140/114", 4800, True, 1140, 114, prec)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/quick_time.json", "w"), indent=1)

@@ -11,6 +11,9 @@ model.precision = 1
 if shape == "cfg3":
     mel = norm_mel(4800, 1)
     model.generate_debug(mel, True, 3000, 1500, max_steps=200, precision=1)
+elif shape == "b512":
+    mel = norm_mel(4800, 1)
+    model.generate_debug(mel, True, 1705, 170, max_steps=200, precision=1)
 else:
     mel = norm_mel(800, 1)
     model.generate_debug(mel, True, 8000, 800, max_steps=200, precision=1)
@@ -21,7 +24,7 @@ names = {0: "step start", 1: "x arrived", 2: "A published", 3: "accB ready", 4: 
          16: "prod: tma B issued", 17: "prod: tma C issued", 18: "prod: tma D issued", 19: "prod: tma E issued",
          20: "mma: B tile0 full", 21: "mma: B tile1 full", 22: "mma: B tile2 full", 23: "mma: B tile3 full",
          24: "mma: B tile0 wait begins", 25: "mma: B tile1 wait begins", 26: "mma: B tile2 wait begins", 27: "mma: B tile3 wait begins",
-         28: "B: tmem loaded", 29: "B: math+store done", 30: "B: after bar.sync"}
+         31: "set 1: step start", 28: "B: tmem loaded", 29: "B: math+store done", 30: "B: after bar.sync"}
 med = np.median(tr[2:], axis=0)
 order = sorted([k for k in names if med[k] >= 0], key=lambda k: med[k])
 print("median SM clocks since step start (steps 66..79), %s %s" % (mode, shape))
