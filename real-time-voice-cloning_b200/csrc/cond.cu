@@ -10,6 +10,7 @@
 //     the loop never touches an 80- or 128-wide conditioning vector.
 // This file holds the fp32 SIMT form (exact parity mode).
 #include "engine_internal.h"
+#include "cond_expand.cuh"
 
 namespace wrnn {
 
@@ -118,48 +119,15 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
 }
 
-// Per-sample conditioning for the tensor-core loop: interpolates the per-frame tables once, ahead of the loop,
-// into CS[virtual group][t][row][unit pair][16 floats] so a loop thread reads one contiguous 64-byte record per step:
-//   {c1_r[2], c1_z[2], c1_n[2], c2_r[2], c2_z[2], c2_n[2], c3[2], c4[2]}   (two hidden units per record)
-// Positions past the utterance (fold tail padding, Q9) take the bias-only row and no mel share.
-constexpr int kExpandSteps = 16;
+// Per-sample conditioning for the tensor-core loop (record layout: cond_expand.cuh), expanded ahead of the loop.
 __global__ void __launch_bounds__(256) expand_cond_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                           const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                           const float* __restrict__ coef, const FoldDesc* __restrict__ folds,
                                                           int S, int Mg, float4* __restrict__ CS) {
-    const int b = blockIdx.x, g = b / Mg, row = b - g * Mg;          // virtual group, row
+    const int b = blockIdx.x;
     const FoldDesc fd = folds[b];
-    const int j = threadIdx.x * 2;
-    const int t1 = min(S, (int)(blockIdx.y + 1) * kExpandSteps);
-    for (int t = blockIdx.y * kExpandSteps; t < t1; ++t) {
-        const int n = fd.n0 + t;
-        const bool valid = n < fd.N;
-        const int q0 = valid ? n / kHop : 0;
-        const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
-        float4 a1[2] = {__ldg(TA1 + ra), __ldg(TA1 + ra + 1)}, a2[2] = {__ldg(TA2 + ra), __ldg(TA2 + ra + 1)};
-        if (valid) {
-            const float* cf = coef + (n - q0 * kHop) * kTaps;
-#pragma unroll
-            for (int d = 0; d < kTaps; ++d) {
-                const float c = __ldg(cf + d);
-                if (c != 0.f) {
-                    const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 q1 = __ldg(TQ1 + rq + u), q2 = __ldg(TQ2 + rq + u);
-                        a1[u].x = fmaf(c, q1.x, a1[u].x); a1[u].y = fmaf(c, q1.y, a1[u].y);
-                        a1[u].z = fmaf(c, q1.z, a1[u].z); a1[u].w = fmaf(c, q1.w, a1[u].w);
-                        a2[u].x = fmaf(c, q2.x, a2[u].x); a2[u].y = fmaf(c, q2.y, a2[u].y); a2[u].z = fmaf(c, q2.z, a2[u].z);
-                    }
-                }
-            }
-        }
-        float4* out = CS + ((((size_t)g * S + t) * Mg + row) * 256 + threadIdx.x) * 4;
-        __stcs(out + 0, make_float4(a1[0].x, a1[1].x, a1[0].y, a1[1].y));
-        __stcs(out + 1, make_float4(a1[0].z, a1[1].z, a2[0].x, a2[1].x));
-        __stcs(out + 2, make_float4(a2[0].y, a2[1].y, a2[0].z, a2[1].z));
-        __stcs(out + 3, make_float4(a1[0].w, a1[1].w, a2[0].w, a2[1].w));
-    }
+    expand_cond_item(TA1, TA2, TQ1, TQ2, coef, fd, b, blockIdx.y * kExpandSteps, min(S, (int)(blockIdx.y + 1) * kExpandSteps), S, Mg, CS,
+                     threadIdx.x);
 }
 
 // Same expansion for the cluster-local loop (loop_tc2.cu): CS[cluster][t][CTA 16][gate 4][unit 32][fold 32][2],

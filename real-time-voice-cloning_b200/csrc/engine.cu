@@ -55,6 +55,7 @@ struct wrnn_engine {
     double sparsity = 0.0;
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
+    int n_sms = 0;
     size_t smem_limit = 0;
     // weights on device
     DevBuf wLoop;    // all loop weights, one allocation
@@ -67,7 +68,7 @@ struct wrnn_engine {
     std::vector<float> hcoef;
     // grow-only work buffers
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
-    DevBuf bPostUtt, bFade, bScratch, bWav, bFloor;
+    DevBuf bPostUtt, bFade, bScratch, bWav, bFloor, bCsDone;
     DevBuf wTc, bTcExch, bCS;
     DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
@@ -181,6 +182,7 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     e->CR = (e->C + kCtasF32 - 1) / kCtasF32;
     cudaError_t err = cudaSetDevice(device);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
     int smem = 0;
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     e->smem_limit = (size_t)smem;
@@ -206,7 +208,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -936,9 +938,18 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             const size_t cs_bytes = (size_t)nvg * S * Mg * 256 * 64;
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
+            // The expansion is HBM-write-bound (~0.5 ms per GB; 17 GB for a 60 s utterance).  Kernels on different streams
+            // do not overlap on this platform (tools/probes/concurrent.cu), so it runs INSIDE the loop kernel: the loop
+            // leaves 18-20 SMs free, expander CTAs on them produce the records a few 16-step chunks ahead of the loop
+            // (which needs <= 0.35 TB/s of them); per-chunk completion counters order the two.  WRNN_TC_OVERLAP=0: expand first.
+            const bool overlap_cs = !(getenv("WRNN_TC_OVERLAP") && atoi(getenv("WRNN_TC_OVERLAP")) == 0);
+            const int nchunks = (S + kExpandSteps - 1) / kExpandSteps;
+            CU(e->bCsDone.ensure((size_t)nchunks * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(e->bCsDone.p, 0, (size_t)nchunks * sizeof(unsigned int), st));
             CU(cudaEventRecord(e->evx[0], st));
-            CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
-                                  e->bFolds.as<FoldDesc>() + w0, B, S, Mg, e->bCS.as<float4>(), st));
+            if (!overlap_cs)
+                CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
+                                      e->bFolds.as<FoldDesc>() + w0, B, S, Mg, e->bCS.as<float4>(), st));
             CU(cudaEventRecord(e->evx[1], st));
             expanded = true;
             const size_t xrows = (size_t)kTcGroups * kTcSets * 128;
@@ -954,6 +965,13 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
             tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets;
+            if (overlap_cs) {
+                tp.cs_done = e->bCsDone.as<unsigned int>(); tp.CSw = e->bCS.as<float4>();
+                tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
+                tp.coef = e->dcoef;
+                tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + (e->mode == WRNN_MODE_MOL ? kTcGroups : 0)));
+                if (tp.n_expanders == 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
+            }
             if (const char* ev = getenv("WRNN_TC_FLAGS")) tp.flags = atoi(ev);
             tp.folds = e->bFolds.as<FoldDesc>() + w0;
             tp.B = B; tp.S = S; tp.C = e->C; tp.Cpad = e->Cpad; tp.mode = e->mode;

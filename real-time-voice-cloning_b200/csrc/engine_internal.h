@@ -60,6 +60,7 @@ constexpr int kTcCtas = 64;       // CTAs per group
 constexpr int kTcUnits = 8;       // hidden units per CTA
 constexpr int kTcSets = 4;        // fold sets (<= 128 folds each) a group pipelines through its CTAs
 constexpr int kTcMaxFolds = kTcGroups * kTcSets * 128;
+constexpr int kExpandSteps = 16;   // steps per block of expand_cond = granularity at which the loop may follow the expansion
 constexpr int kTcKbPerOp = 2;      // k-blocks (64 columns each) one TMA operation of the loop brings in
 
 struct TcParams {
@@ -70,6 +71,13 @@ struct TcParams {
     int nsets;                   // fold sets per group in this launch (1..kTcSets)
     const FoldDesc* folds;
     int B, S, C, Cpad, mode;
+    // conditioning expansion inside the loop kernel (expander CTAs on the SMs the loop leaves free): per-frame tables in,
+    // CS out, one completion counter per 16-step chunk; cs_done == nullptr: CS was expanded before the launch
+    unsigned int* cs_done;
+    float4* CSw;
+    const float4 *TA1, *TA2, *TQ1, *TQ2;
+    const float* coef;
+    int n_expanders;
     int tile_bytes;              // bytes one k-block of a TMA operation occupies: box_rows * 128
     int flags;                   // bit 0: epilogue warps release the counters themselves (no publisher warp); 1: 4-slot ring; 2: L2 prefetch of the next record
     unsigned long long seed;

@@ -28,6 +28,7 @@
 #include "engine_internal.h"
 #include "sampling.cuh"
 #include "tc_common.cuh"
+#include "cond_expand.cuh"
 
 namespace wrnn {
 
@@ -233,7 +234,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const bool sampler = (int)blockIdx.x >= nmain;                        // MOL: blocks past the groups run fc3 + the draw
     const int g = sampler ? (int)blockIdx.x - nmain : (int)blockIdx.x / kTcCtas;   // group
     const int cta = sampler ? 0 : (int)blockIdx.x % kTcCtas;              // unit-owning CTA inside the group
-    const bool idle = false;
+    const bool expander = sampler && g >= (mol ? kTcGroups : 0);          // blocks past the loop's CTAs expand the conditioning
+    const bool idle = expander;
     constexpr int nsets = NSETS;                                          // fold sets per group (1..kTcSets)
     const int NE = mol ? 32 : 16;
     const int ph0 = sampler ? 3 : 0, ph1 = (mol && !sampler) ? 3 : 4;     // stages whose MMAs this CTA runs
@@ -277,8 +279,25 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     tcgen05_fence_after();
     const uint32_t tmem = ctl->tmem;
 
-    if (idle) {
-        // nothing: straight to the teardown barrier
+    if (expander) {
+        // =================================== conditioning expander =============================================
+        // work item = (16-step chunk, fold), chunk-major, so chunks complete in the order the loop consumes them; two
+        // 256-thread halves of the CTA take items alternately; the remaining warps idle
+        const int e_idx = g - (mol ? kTcGroups : 0), half = tid >> 8;
+        if (half < 2 && p.cs_done) {
+            const int nchunks = (p.S + kExpandSteps - 1) / kExpandSteps;
+            const long long nitems = (long long)nchunks * p.B;
+            for (long long it = (long long)e_idx * 2 + half; it < nitems; it += 2LL * p.n_expanders) {
+                const int c = (int)(it / p.B), b = (int)(it - (long long)c * p.B);
+                const FoldDesc fd = p.folds[b];
+                int key = -1;             // (a fold's rows differ from the previous item's: start cold)
+                expand_cond_item_cached(p.TA1, p.TA2, p.TQ1, p.TQ2, p.coef, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.S, p.Mg,
+                                        p.CSw, tid & 255, reinterpret_cast<float*>(smem) + half * (kExpandCacheFloats * 256), key);
+                __threadfence();
+                asm volatile("bar.sync %0, 256;" ::"r"(8 + half) : "memory");
+                if ((tid & 255) == 0) atomicAdd(p.cs_done + c, 1u);
+            }
+        }
     } else
     if (warp == NEPI) {
         // =================================== TMA producer ===================================================
@@ -407,6 +426,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             SET_VIEW(s)
             float4 ca = make_float4(0.f, 0.f, 0.f, 0.f);
             float2 cn = make_float2(0.f, 0.f);
+            if (p.cs_done && (t % kExpandSteps) == 0 && live)     // the expansion runs on the spare SMs, a few chunks ahead of us
+                wait_counter(p, ctl, p.cs_done + t / kExpandSteps, (unsigned int)p.B);
             if (live) { ca = __ldcs(cs); cn = __ldcs(reinterpret_cast<const float2*>(cs + 1)); }   // issued before the wait on x
 #if !WRNN_JIT
             if (live) { S.cr = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); S.cz = __ldcs(cs + 2); S.c34 = __ldcs(cs + 3); }
@@ -642,7 +663,11 @@ static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cud
     if (err != cudaSuccess) return err;
     TcParams pp = p;
     void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
-    const int grid = kTcGroups * kTcCtas + (p.mode == 1 ? kTcGroups : 0);
+    const int grid = kTcGroups * kTcCtas + (p.mode == 1 ? kTcGroups : 0) + (p.cs_done ? p.n_expanders : 0);
+    if (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) {
+        wrnn_loop_tc_kernel<NSETS><<<grid, NT, kSmemBytes + 1024, stream>>>(m[0], m[1], m[2], m[3], pp);
+        return cudaGetLastError();
+    }
     return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel<NSETS>, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
 }
 
