@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) expand_cond_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                           const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                           const float* __restrict__ coef, const FoldDesc* __restrict__ folds,
-                                                          int S, int Mg, float4* __restrict__ CS) {
+                                                          int S, int cs_steps, int Mg, float4* __restrict__ CS) {
     const int b = blockIdx.x;
     const FoldDesc fd = folds[b];
-    expand_cond_item(TA1, TA2, TQ1, TQ2, coef, fd, b, blockIdx.y * kExpandSteps, min(S, (int)(blockIdx.y + 1) * kExpandSteps), S, Mg, CS,
+    expand_cond_item(TA1, TA2, TQ1, TQ2, coef, fd, b, blockIdx.y * kExpandSteps, min(S, (int)(blockIdx.y + 1) * kExpandSteps), cs_steps, Mg, CS,
                      threadIdx.x);
 }
 
@@ -191,7 +191,7 @@ cudaError_t launch_expand_cond2(const float4* TA1, const float4* TA2, const floa
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                const FoldDesc* folds, int B, int S, int Mg, float4* CS, cudaStream_t stream) {
     dim3 grid(B, (S + kExpandSteps - 1) / kExpandSteps);
-    expand_cond_kernel<<<grid, 256, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, S, Mg, CS);
+    expand_cond_kernel<<<grid, 256, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, S, (int)grid.y * kExpandSteps, Mg, CS);
     return cudaGetLastError();
 }
 

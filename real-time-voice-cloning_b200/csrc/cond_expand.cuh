@@ -13,7 +13,7 @@ namespace wrnn {
 // one work item = (fold b, steps [t0, t1)); executed by 256 threads, `tx` = 0..255 = unit pair
 __device__ __forceinline__ void expand_cond_item(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                  const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
-                                                 const float* __restrict__ coef, const FoldDesc& fd, int b, int t0, int t1, int S, int Mg,
+                                                 const float* __restrict__ coef, const FoldDesc& fd, int b, int t0, int t1, int cs_steps, int Mg,
                                                  float4* __restrict__ CS, int tx) {
     const int g = b / Mg, row = b - g * Mg;          // virtual group, row
     const int j = tx * 2;
@@ -40,7 +40,7 @@ __device__ __forceinline__ void expand_cond_item(const float4* __restrict__ TA1,
                 }
             }
         }
-        float4* out = CS + ((((size_t)g * S + t) * Mg + row) * 256 + tx) * 4;
+        float4* out = CS + ((((size_t)g * cs_steps + t) * Mg + row) * 256 + tx) * 4;
         __stcs(out + 0, make_float4(a1[0].x, a1[1].x, a1[0].y, a1[1].y));
         __stcs(out + 1, make_float4(a1[0].z, a1[1].z, a2[0].x, a2[1].x));
         __stcs(out + 2, make_float4(a2[0].y, a2[1].y, a2[0].z, a2[1].z));
@@ -56,7 +56,7 @@ __device__ __forceinline__ void expand_cond_item(const float4* __restrict__ TA1,
 constexpr int kExpandCacheFloats = 16 + kTaps * 14;
 __device__ __forceinline__ void expand_cond_item_cached(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                         const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
-                                                        const float* __restrict__ coef, const FoldDesc& fd, int b, int t0, int t1, int S, int Mg,
+                                                        const float* __restrict__ coef, const FoldDesc& fd, int b, int t0, int t1, int cs_steps, int Mg,
                                                         float4* __restrict__ CS, int tx, float* __restrict__ cache, int& key) {
     const int g = b / Mg, row = b - g * Mg;
     const int j = tx * 2;
@@ -108,7 +108,7 @@ __device__ __forceinline__ void expand_cond_item_cached(const float4* __restrict
                 }
             }
         }
-        float4* out = CS + ((((size_t)g * S + t) * Mg + row) * 256 + tx) * 4;
+        float4* out = CS + ((((size_t)g * cs_steps + (t % cs_steps)) * Mg + row) * 256 + tx) * 4;   // CS is a ring of cs_steps steps
         __stcs(out + 0, make_float4(a[0][0], a[1][0], a[0][1], a[1][1]));
         __stcs(out + 1, make_float4(a[0][2], a[1][2], a[0][4], a[1][4]));
         __stcs(out + 2, make_float4(a[0][5], a[1][5], a[0][6], a[1][6]));

@@ -935,17 +935,26 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             int nsets = std::min(kTcSets, (B + kTcGroups * 128 - 1) / (kTcGroups * 128));
             if (const char* ev = getenv("WRNN_TC_SETS")) nsets = std::max(nsets, std::min(kTcSets, atoi(ev)));
             const int nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
-            const size_t cs_bytes = (size_t)nvg * S * Mg * 256 * 64;
-            if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
-            CU(e->bCS.ensure(cs_bytes));
             // The expansion is HBM-write-bound (~0.5 ms per GB; 17 GB for a 60 s utterance).  Kernels on different streams
             // do not overlap on this platform (tools/probes/concurrent.cu), so it runs INSIDE the loop kernel: the loop
             // leaves 18-20 SMs free, expander CTAs on them produce the records a few 16-step chunks ahead of the loop
-            // (which needs <= 0.35 TB/s of them); per-chunk completion counters order the two.  WRNN_TC_OVERLAP=0: expand first.
+            // (which needs <= 0.35 TB/s of them); per-chunk counters order the two, and CS is a ring of cs_steps steps per
+            // fold (<= 24 GiB whatever the fold length).  WRNN_TC_OVERLAP=0: expand the whole table first.
             const bool overlap_cs = !(getenv("WRNN_TC_OVERLAP") && atoi(getenv("WRNN_TC_OVERLAP")) == 0);
             const int nchunks = (S + kExpandSteps - 1) / kExpandSteps;
-            CU(e->bCsDone.ensure((size_t)nchunks * sizeof(unsigned int)));
-            CU(cudaMemsetAsync(e->bCsDone.p, 0, (size_t)nchunks * sizeof(unsigned int), st));
+            int cs_steps = nchunks * kExpandSteps;
+            if (overlap_cs) {
+                const size_t per_step = (size_t)nvg * Mg * 256 * 64;
+                size_t budget = (size_t)24 << 30;
+                if (const char* ev = getenv("WRNN_TC_CS_BUDGET_MB")) budget = (size_t)atoll(ev) << 20;     // (tests: force the ring)
+                const size_t fit = (budget / per_step) / kExpandSteps * kExpandSteps;
+                cs_steps = (int)std::min<size_t>((size_t)cs_steps, std::max<size_t>(fit, 8 * kExpandSteps));
+            }
+            const size_t cs_bytes = (size_t)nvg * cs_steps * Mg * 256 * 64;
+            if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
+            CU(e->bCS.ensure(cs_bytes));
+            CU(e->bCsDone.ensure((size_t)2 * nchunks * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(e->bCsDone.p, 0, (size_t)2 * nchunks * sizeof(unsigned int), st));
             CU(cudaEventRecord(e->evx[0], st));
             if (!overlap_cs)
                 CU(launch_expand_cond(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
@@ -964,9 +973,10 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             memset(&tp, 0, sizeof(tp));
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
-            tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets;
+            tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets; tp.cs_steps = cs_steps;
             if (overlap_cs) {
                 tp.cs_done = e->bCsDone.as<unsigned int>(); tp.CSw = e->bCS.as<float4>();
+                if (cs_steps < nchunks * kExpandSteps) tp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
                 tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
                 tp.coef = e->dcoef;
                 tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + (e->mode == WRNN_MODE_MOL ? kTcGroups : 0)));

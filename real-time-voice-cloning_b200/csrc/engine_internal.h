@@ -74,6 +74,8 @@ struct TcParams {
     // conditioning expansion inside the loop kernel (expander CTAs on the SMs the loop leaves free): per-frame tables in,
     // CS out, one completion counter per 16-step chunk; cs_done == nullptr: CS was expanded before the launch
     unsigned int* cs_done;
+    unsigned int* cs_consumed;   // per chunk: unit-owning CTAs that have read it (the expanders reuse CS as a ring of cs_steps steps)
+    int cs_steps;                // steps CS holds per fold (== S rounded up to a chunk when it is not a ring)
     float4* CSw;
     const float4 *TA1, *TA2, *TQ1, *TQ2;
     const float* coef;

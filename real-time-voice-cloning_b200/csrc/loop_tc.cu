@@ -287,11 +287,18 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         if (half < 2 && p.cs_done) {
             const int nchunks = (p.S + kExpandSteps - 1) / kExpandSteps;
             const long long nitems = (long long)nchunks * p.B;
+            int waited = -1;
             for (long long it = (long long)e_idx * 2 + half; it < nitems; it += 2LL * p.n_expanders) {
                 const int c = (int)(it / p.B), b = (int)(it - (long long)c * p.B);
+                const int ring_chunks = p.cs_steps / kExpandSteps;
+                if (c >= ring_chunks && c != waited) {      // CS is a ring: chunk c overwrites chunk c - ring_chunks, which every
+                    waited = c;                             // unit-owning CTA must have finished reading
+                    if ((tid & 255) == 0) wait_counter(p, ctl, p.cs_consumed + (c - ring_chunks), (unsigned int)nmain);
+                    asm volatile("bar.sync %0, 256;" ::"r"(8 + half) : "memory");
+                }
                 const FoldDesc fd = p.folds[b];
                 int key = -1;             // (a fold's rows differ from the previous item's: start cold)
-                expand_cond_item_cached(p.TA1, p.TA2, p.TQ1, p.TQ2, p.coef, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.S, p.Mg,
+                expand_cond_item_cached(p.TA1, p.TA2, p.TQ1, p.TQ2, p.coef, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.cs_steps, p.Mg,
                                         p.CSw, tid & 255, reinterpret_cast<float*>(smem) + half * (kExpandCacheFloats * 256), key);
                 __threadfence();
                 asm volatile("bar.sync %0, 256;" ::"r"(8 + half) : "memory");
@@ -380,7 +387,11 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             for (int k = 0; k < nslot_total; ++k)
                 for (int s = 0; s < nsets; ++s) {
                     int t, stn;
-                    if (job_of(k, s, skew, p.S, t, stn) && stn < 4) publisher_release(s, p.counters + (g * nsets + s) * 4 + stn);
+                    if (!job_of(k, s, skew, p.S, t, stn) || stn >= 4) continue;
+                    publisher_release(s, p.counters + (g * nsets + s) * 4 + stn);
+                    // stage A is the only reader of the conditioning records: after the last set's, the chunk may be recycled
+                    if (p.cs_consumed && stn == 0 && s == nsets - 1 && ((t + 1) % kExpandSteps == 0) && lane == 0)
+                        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_consumed + t / kExpandSteps) : "memory");
                 }
         }
     } else {
@@ -418,7 +429,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         const size_t grow = (size_t)vg * 128 + row;                                                              \
         const uint32_t tacc = tlane + (uint32_t)(s) * kSetCols;                                                  \
         unsigned int* const ctrs = p.counters + vg * 4;                                                          \
-        const float4* const cs = p.CS + (((size_t)vg * p.S + t) * p.Mg + row) * cs_rec + ((size_t)cta * 4 + up) * 4;   \
+        const float4* const cs = p.CS + (((size_t)vg * p.cs_steps + (t % p.cs_steps)) * p.Mg + row) * cs_rec + ((size_t)cta * 4 + up) * 4;   \
         (void)fold0; (void)nrows; (void)live; (void)grow; (void)tacc; (void)ctrs; (void)cs;
 
         // ---- A: x_{t-1}, GRU1 for my 2 units, publish h1 ---------------------------------------------------

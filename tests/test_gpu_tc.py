@@ -141,3 +141,17 @@ def test_cluster_local_tc_loop_mol(monkeypatch):
     b = model.generate_debug(mel2, True, 300, 50, forced=forced2, want_logits=True, seed=5, max_steps=40)
     assert a["samples"].shape[0] > 200
     assert _rel(a["logits"], b["logits"]) < 1e-3
+
+
+def test_tc_loop_conditioning_ring(monkeypatch):
+    """Long folds: the per-sample conditioning table becomes a ring that the in-kernel expanders refill behind the loop
+    (engine.cu: cs_steps < S).  Same samples as with the whole table expanded up front."""
+    from tests.util import norm_mel
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    mel = norm_mel(120, 7)
+    monkeypatch.setenv("WRNN_TC_CS_BUDGET_MB", "64")          # 24000 samples -> 6 folds x 4400 steps: ring of a few hundred steps
+    a = model.generate_debug(mel, True, 4000, 200, want_logits=False, seed=3, precision=F16)
+    monkeypatch.setenv("WRNN_TC_OVERLAP", "0")
+    b = model.generate_debug(mel, True, 4000, 200, want_logits=False, seed=3, precision=F16)
+    assert a["samples"].shape[1] >= 4000
+    np.testing.assert_array_equal(a["samples"], b["samples"])

@@ -43,5 +43,8 @@ for tag in which:
         run(raw, tag + " raw 60s b512 1705/170", 4800, True, 1705, 170, prec)
         run(mol, tag + " mol 60s b766 1140/114", 4800, True, 1140, 114, prec)
         run(raw, tag + " raw 60s b766 1140/114", 4800, True, 1140, 114, prec)
+        run(mol, tag + " mol 60s b1024 853/85", 4800, True, 853, 85, prec)
+        run(mol, tag + " mol 60s b896 975/97", 4800, True, 975, 97, prec)
+        run(raw, tag + " raw 60s b1024 853/85", 4800, True, 853, 85, prec)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/quick_time.json", "w"), indent=1)
