@@ -69,7 +69,7 @@ struct wrnn_engine {
     // grow-only work buffers
     DevBuf bMel, bUtt, bX0, bMP, bH[3], bAux, bTA1, bTA2, bTQ1, bTQ2, bFolds, bExch, bSamples, bLogits, bForced;
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor, bCsDone;
-    DevBuf wTc, bTcExch, bCS;
+    DevBuf wTc, wTcS, bTcExch, bCS;
     DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
     int spStride[2] = {0, 0};
@@ -208,7 +208,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -389,6 +389,15 @@ int wrnn_finalize(wrnn_engine* e) {
         }
         CU(e->wTc.ensure(hw.size()));
         CU(cudaMemcpy(e->wTc.p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+        if (C == 512) {     // RAW sampler CTAs: quarter q of fc3 (rows 128 q ..) as eight [128 x 64] tiles
+            const size_t simg = loop_tc_raw_sampler_image_bytes();
+            const int nq = loop_tc_raw_sampler_ctas();
+            std::vector<unsigned char> hs((size_t)nq * simg, 0);
+            for (int q = 0; q < nq; ++q)
+                for (int r = 0; r < C / nq; ++r) put(hs.data() + (size_t)q * simg, C / nq, r, f3w->data.data() + (size_t)(q * (C / nq) + r) * H);
+            CU(e->wTcS.ensure(hs.size()));
+            CU(cudaMemcpy(e->wTcS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
+        }
     }
 
     // ---- cluster-local tensor-core loop (MOL): per-CTA streams of weight tiles, gate-major rows (loop_tc2.cu) -------------
@@ -974,12 +983,17 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
             tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets; tp.cs_steps = cs_steps;
+            // RAW with 512 classes: fc3 + the draw on 4 sampler CTAs per group (WRNN_TC_RAWSAMP=0: classes spread over the unit-owning CTAs)
+            if (e->mode != WRNN_MODE_MOL && e->C == 512 && !(getenv("WRNN_TC_RAWSAMP") && atoi(getenv("WRNN_TC_RAWSAMP")) == 0)) {
+                tp.raw_samplers = 1;
+                tp.wimg_s = e->wTcS.as<unsigned char>();
+            }
             if (overlap_cs) {
                 tp.cs_done = e->bCsDone.as<unsigned int>(); tp.CSw = e->bCS.as<float4>();
                 if (cs_steps < nchunks * kExpandSteps) tp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
                 tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
                 tp.coef = e->dcoef;
-                tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + (e->mode == WRNN_MODE_MOL ? kTcGroups : 0)));
+                tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers)));
                 if (tp.n_expanders == 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
             }
             if (const char* ev = getenv("WRNN_TC_FLAGS")) tp.flags = atoi(ev);

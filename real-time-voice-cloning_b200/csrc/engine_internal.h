@@ -65,6 +65,8 @@ constexpr int kTcKbPerOp = 2;      // k-blocks (64 columns each) one TMA operati
 
 struct TcParams {
     const unsigned char* wimg;   // [kTcCtas][loop_tc_weight_image_bytes()] per-CTA weight images in shared-memory layout
+    const unsigned char* wimg_s; // RAW sampler CTAs: [4][loop_tc_raw_sampler_image_bytes()] quarters of fc3 as N=128 tiles
+    int raw_samplers;            // != 0: RAW, 512 classes: fc3 + the draw run on 4 dedicated sampler CTAs per group
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
     const float4* CS;            // per-sample conditioning [virtual group][step][row < Mg][256 unit pairs][4 float4] (expand_cond)
     int Mg;                      // folds per virtual group (= group x set); fold f is row f % Mg of virtual group f / Mg
@@ -85,7 +87,7 @@ struct TcParams {
     unsigned long long seed;
     __half *H1, *H2, *F1, *F2;   // activation exchange, [kTcGroups*kTcSets*128][512] fp16
     unsigned int* counters;      // [kTcGroups*kTcSets][4] arrival counters (monotonic)
-    unsigned long long* bLG;     // [kTcGroups*kTcSets*128][Cpad] logits exchange words (RAW)
+    unsigned long long* bLG;     // [kTcGroups*kTcSets*128][Cpad] logits exchange words (RAW); RAW samplers: [2][rows][4] {max, sum} pairs
     unsigned long long* bX;      // [kTcGroups*kTcSets*128] sample exchange words
     float* samples;
     float* logits_out;
@@ -95,6 +97,9 @@ struct TcParams {
     long long* trace;            // optional [16 steps][32 slots] SM-clock timeline of CTA 0 (WRNN_TC_TRACE=1)
 };
 size_t loop_tc_weight_image_bytes();
+size_t loop_tc_raw_sampler_image_bytes();
+int loop_tc_raw_sampler_ctas();
+int loop_tc_sampler_ctas(int mode, int raw_samplers);   // CTAs past the unit-owning groups that run fc3 + the draw
 cudaError_t set_tc_deadline(long long cycles);
 cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t stream);
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,

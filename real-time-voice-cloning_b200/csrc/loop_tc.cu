@@ -53,6 +53,11 @@ constexpr int kConst = kBias + 128;                      // per-unit constants o
 // tcgen05.mma always reads 128 rows (16 KB) from a slot base; with slots shorter than that the last slot reads up to
 // 8 KB past the ring (into the control words: harmless garbage rows), so the allocation must cover ring + 72 KB
 constexpr int kSmemBytes = (kConst + 512 > kRing + 73728) ? (kConst + 512) : (kRing + 73728);
+// RAW with 512 classes: fc3 + the draw run on kRawQ dedicated sampler CTAs per group, 128 classes (one N=128 MMA tile,
+// 128 KB of resident fc3 rows at offset 0) each; their fc3 bias slice sits in the gap below the ring
+constexpr int kRawQ = 4, kRawQCols = 128, kRawBias = kRawQCols * 128 * kNKB;
+static_assert(kRawBias + kRawQCols * 4 <= kRing, "RAW sampler bias overlaps the ring");
+static_assert(kTcSets <= NEPI / 4, "RAW sampler: one group of four epilogue warps per fold set");
 // TMEM columns
 constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kSetCols = 128, kTmemCols = 512;   // (sampler CTA: fc3 accumulator at column 0 of the set's block)   // per fold set
 
@@ -62,6 +67,7 @@ struct Ctl {
     uint64_t accfull[4 * kTcSets];
     uint32_t tmem;
     int abort_local;
+    int exp_released;      // expander CTAs: items whose completion barrier the releaser warp has left
 };
 static_assert(sizeof(Ctl) <= 256, "control block");
 static_assert(kTcSets * kSetCols <= kTmemCols, "TMEM columns");
@@ -190,6 +196,83 @@ __device__ __noinline__ void raw_stage_e(const TcParams& p, Ctl* ctl, uint32_t t
     }
 }
 
+// Station E on a RAW sampler CTA (512 classes): the CTA holds fc3 rows [128 qd, 128 qd + 128) and has their products for
+// every fold of the set in TMEM (lane = fold, 128 columns).  Thread = fold: softmax partials {max, sum} of my quarter go
+// to the other three sampler CTAs of the group as tagged words (double-buffered by step parity), every CTA forms the
+// same normaliser and threshold u * Z from the four pairs, and the CTA whose quarter contains the threshold scans its
+// 128 classes for the first k with cdf[k] >= u (rule: oracle sample_raw; fatchord_version.py:224-230).
+__device__ __noinline__ void raw_sampler_e(const TcParams& p, Ctl* ctl, const float* sbias, uint32_t tacc, int qd, int fold0, int nrows,
+                                           size_t grow, int row, int t, uint32_t fold, uint32_t utt, uint2 key) {
+    const bool live = row < nrows;
+    const uint32_t tag = (uint32_t)t + 1u;
+    float m = -INFINITY, ssum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kRawQCols; c += 32) {          // online softmax partials, 32 classes at a time
+        float l[32];
+        tmem_ld8(tacc + c, l); tmem_ld8(tacc + c + 8, l + 8); tmem_ld8(tacc + c + 16, l + 16); tmem_ld8(tacc + c + 24, l + 24);
+        tmem_ld_wait();
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { l[i] += sbias[c + i]; cm = fmaxf(cm, l[i]); }
+        if (cm > m) { ssum *= __expf(m - cm); m = cm; }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ssum += __expf(l[i] - m);
+        if (p.logits_out && live) {
+            float* lo = p.logits_out + ((size_t)(fold0 + row) * p.S + t) * p.C + qd * kRawQCols + c;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lo[i] = l[i];
+        }
+    }
+    unsigned long long* xw = p.bLG + ((size_t)(t & 1) * ((size_t)kTcGroups * kTcSets * 128) + grow) * (2 * kRawQ);
+    if (live) { ll_store(xw + 2 * qd, m, tag); ll_store(xw + 2 * qd + 1, ssum, tag); }
+    float mq[kRawQ], zq[kRawQ];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < kRawQ; ++q) {
+        mq[q] = m; zq[q] = ssum;
+        if (q != qd && live && ok) {
+            long long t0 = 0;
+            int spins = 0;
+            while (true) {
+                unsigned long long a, b;
+                ll_load2(xw + 2 * q, a, b);
+                if (ll_tag(a) == tag && ll_tag(b) == tag) { mq[q] = ll_val(a); zq[q] = ll_val(b); break; }
+                if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) { ok = false; break; }
+            }
+        }
+    }
+    const float M = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+#pragma unroll
+    for (int q = 0; q < kRawQ; ++q) zq[q] *= __expf(mq[q] - M);
+    const float c0 = zq[0], c1 = c0 + zq[1], c2 = c1 + zq[2], Z = c2 + zq[3];
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, fold, utt, 0u), key);
+    const float thr = u01(r.x) * Z;
+    const int qs = thr <= c0 ? 0 : (thr <= c1 ? 1 : (thr <= c2 ? 2 : 3));
+    const bool mine = live && ok && qs == qd;
+    if (!__any_sync(0xffffffffu, mine)) return;         // (tcgen05.ld is warp-wide: the whole warp scans or none of it)
+    float cum = qs == 0 ? 0.f : (qs == 1 ? c0 : (qs == 2 ? c1 : c2));
+    int k = -1;
+#pragma unroll 1
+    for (int c = 0; c < kRawQCols; c += 32) {
+        float l[32];
+        tmem_ld8(tacc + c, l); tmem_ld8(tacc + c + 8, l + 8); tmem_ld8(tacc + c + 16, l + 16); tmem_ld8(tacc + c + 24, l + 24);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            cum += __expf(l[i] + sbias[c + i] - M);
+            if (k < 0 && cum >= thr) k = c + i;
+        }
+        if (__all_sync(0xffffffffu, k >= 0 || !mine)) break;
+    }
+    if (mine) {
+        if (k < 0) k = kRawQCols - 1;                   // rounding left the quarter's own sum short of the threshold
+        const float xs = 2.0f * (float)(qd * kRawQCols + k) / ((float)p.C - 1.0f) - 1.0f;
+        p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
+        const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
+        ll_store(p.bX + grow, fed, tag);
+    }
+}
+
 }  // namespace
 
 // The schedule.  Per step a fold set passes five stations: A (GRU1 on the new sample), B, C, D (an MMA stage and its
@@ -231,17 +314,22 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool mol = p.mode == 1;
     const int nmain = kTcGroups * kTcCtas;
-    const bool sampler = (int)blockIdx.x >= nmain;                        // MOL: blocks past the groups run fc3 + the draw
-    const int g = sampler ? (int)blockIdx.x - nmain : (int)blockIdx.x / kTcCtas;   // group
+    const bool rawq = !mol && p.raw_samplers != 0;                        // RAW, 512 classes: kRawQ sampler CTAs per group
+    const int spg = mol ? 1 : (rawq ? kRawQ : 0);                         // sampler CTAs per group
+    const bool has_samplers = spg != 0;
+    const int sidx = (int)blockIdx.x - nmain;                             // blocks past the groups: samplers, then expanders
+    const bool sampler = sidx >= 0;                                       // (fc3 + the draw)
+    const int g = sampler ? (spg ? sidx / spg : sidx) : (int)blockIdx.x / kTcCtas;   // group
+    const int qd = (sampler && rawq) ? sidx % kRawQ : 0;                  // RAW sampler: my quarter of the classes
     const int cta = sampler ? 0 : (int)blockIdx.x % kTcCtas;              // unit-owning CTA inside the group
-    const bool expander = sampler && g >= (mol ? kTcGroups : 0);          // blocks past the loop's CTAs expand the conditioning
+    const bool expander = sampler && sidx >= kTcGroups * spg;             // blocks past the loop's CTAs expand the conditioning
     const bool idle = expander;
     constexpr int nsets = NSETS;                                          // fold sets per group (1..kTcSets)
-    const int NE = mol ? 32 : 16;
-    const int ph0 = sampler ? 3 : 0, ph1 = (mol && !sampler) ? 3 : 4;     // stages whose MMAs this CTA runs
+    const int NE = mol ? 32 : ((rawq && sampler) ? kRawQCols : 16);
+    const int ph0 = sampler ? 3 : 0, ph1 = (has_samplers && !sampler) ? 3 : 4;   // stages whose MMAs this CTA runs
     const int skew = (p.flags >> 4) & 7;                                  // stations set s runs behind set s-1 (0: all sets in phase)
     const int nslot_total = 5 * p.S + skew * (nsets - 1);                  // slots of the schedule (job_of)
-    const bool deep = mol && !sampler && !(p.flags & 2);
+    const bool deep = has_samplers && !sampler && !(p.flags & 2);
     const uint32_t ring0 = deep ? kWE : kRing, nslots = deep ? 3u : 2u;       // ring of 32 KB slots (two k-blocks each)
     constexpr uint32_t slot_bytes = kTcKbPerOp * kTileBytes;
     const uint32_t kb_bytes = (uint32_t)p.tile_bytes;                         // the second k-block of a slot starts here
@@ -250,16 +338,19 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
 
     // ---- one-time setup ---------------------------------------------------------------------------------------
     if (!idle) {
-        const int w0 = sampler ? kWE : 0, w1 = (mol && !sampler) ? kWE : kWBytes;
-        const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)cta * kWBytes + w0);
+        const bool rs = rawq && sampler;                // RAW sampler: its quarter of fc3 (N = 128 tiles) at offset 0
+        const int w0 = rs ? 0 : (sampler ? kWE : 0), w1 = rs ? kRawBias : ((has_samplers && !sampler) ? kWE : kWBytes);
+        const uint4* src = reinterpret_cast<const uint4*>(rs ? p.wimg_s + (size_t)qd * kRawBias : p.wimg + (size_t)cta * kWBytes + w0);
         uint4* dst = reinterpret_cast<uint4*>(smem + w0);
         for (int i = tid; i < (w1 - w0) / 16; i += NT) dst[i] = src[i];
+        if (rs && tid < kRawQCols) reinterpret_cast<float*>(smem + kRawBias)[tid] = p.bfc3[qd * kRawQCols + tid];
         fence_proxy_async_smem();
     }
     if (tid == 0) {
         for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
         for (int i = 0; i < 4 * kTcSets; ++i) mbar_init(&ctl->accfull[i], 1);
         ctl->abort_local = 0;
+        ctl->exp_released = 0;
         mbar_fence_init();
     }
     if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (mol && tid < 30) ? p.bfc3[tid] : 0.f;
@@ -273,6 +364,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         else v = p.bhn2[j];
         reinterpret_cast<float*>(smem + kConst)[tid] = v;
     }
+    if (expander && p.cs_done)                      // interpolation weights [200][kTaps]: broadcast reads from shared memory
+        for (int i = tid; i < kHop * kTaps; i += NT) reinterpret_cast<float*>(smem)[i] = p.coef[i];
     if (warp == 0 && !idle) tmem_alloc(&ctl->tmem, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
@@ -281,28 +374,48 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
 
     if (expander) {
         // =================================== conditioning expander =============================================
-        // work item = (16-step chunk, fold), chunk-major, so chunks complete in the order the loop consumes them; two
-        // 256-thread halves of the CTA take items alternately; the remaining warps idle
-        const int e_idx = g - (mol ? kTcGroups : 0), half = tid >> 8;
-        if (half < 2 && p.cs_done) {
+        // work item = (16-step chunk, fold), chunk-major, so chunks complete in the order the loop consumes them.  512 worker
+        // threads (thread = hidden unit) produce the item's records and ARRIVE on a named barrier; the releaser warp completes
+        // it and bumps the chunk's counter with a release (cumulative over the workers' stores through the barrier), so the
+        // workers never wait for their stores to drain.  Two barriers alternate by item; exp_released keeps a worker from
+        // arriving at a barrier whose previous phase the releaser has not left yet.
+        const int e_idx = sidx - kTcGroups * spg;
+        if (p.cs_done && warp <= NEPI) {
             const int nchunks = (p.S + kExpandSteps - 1) / kExpandSteps;
             const long long nitems = (long long)nchunks * p.B;
-            int waited = -1;
-            for (long long it = (long long)e_idx * 2 + half; it < nitems; it += 2LL * p.n_expanders) {
+            const int ring_chunks = p.cs_steps / kExpandSteps;
+            const float* coef_s = reinterpret_cast<const float*>(smem);
+            volatile int* released = reinterpret_cast<volatile int*>(&ctl->exp_released);
+            int waited = -1, seq = 0;
+            for (long long it = e_idx; it < nitems; it += p.n_expanders, ++seq) {
                 const int c = (int)(it / p.B), b = (int)(it - (long long)c * p.B);
-                const int ring_chunks = p.cs_steps / kExpandSteps;
-                if (c >= ring_chunks && c != waited) {      // CS is a ring: chunk c overwrites chunk c - ring_chunks, which every
-                    waited = c;                             // unit-owning CTA must have finished reading
-                    if ((tid & 255) == 0) wait_counter(p, ctl, p.cs_consumed + (c - ring_chunks), (unsigned int)nmain);
-                    asm volatile("bar.sync %0, 256;" ::"r"(8 + half) : "memory");
+                const int bar_id = 9 + (seq & 1);
+                if (warp == NEPI) {                             // ---- releaser
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"((NEPI + 1) * 32) : "memory");
+                    if (lane == 0) {
+                        *released = seq + 1;
+                        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_done + c) : "memory");
+                    }
+                    continue;
+                }
+                if (c >= ring_chunks && c != waited) {          // CS is a ring: chunk c overwrites chunk c - ring_chunks, which every
+                    waited = c;                                 // unit-owning CTA must have finished reading
+                    if (tid == 0) wait_counter(p, ctl, p.cs_consumed + (c - ring_chunks), (unsigned int)nmain);
+                    asm volatile("bar.sync 8, %0;" ::"n"(NEPI * 32) : "memory");
                 }
                 const FoldDesc fd = p.folds[b];
-                int key = -1;             // (a fold's rows differ from the previous item's: start cold)
-                expand_cond_item_cached(p.TA1, p.TA2, p.TQ1, p.TQ2, p.coef, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.cs_steps, p.Mg,
-                                        p.CSw, tid & 255, reinterpret_cast<float*>(smem) + half * (kExpandCacheFloats * 256), key);
-                __threadfence();
-                asm volatile("bar.sync %0, 256;" ::"r"(8 + half) : "memory");
-                if ((tid & 255) == 0) atomicAdd(p.cs_done + c, 1u);
+                expand_cond_item_regs(p.TA1, p.TA2, p.TQ1, p.TQ2, coef_s, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.cs_steps, p.Mg,
+                                      p.CSw, tid);
+                if (seq >= 2) {
+                    if (lane == 0) {
+                        long long t0 = 0;
+                        int spins = 0;
+                        while (*released < seq - 1)
+                            if (((++spins) & 1023) == 0 && spin_check(p, ctl, t0)) break;
+                    }
+                    __syncwarp();
+                }
+                asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "n"((NEPI + 1) * 32) : "memory");
             }
         }
     } else
@@ -341,7 +454,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     } else if (warp == NEPI + 1) {
         // =================================== MMA issuer =====================================================
         if (lane == 0) {
-            const uint32_t wofs[4] = {kWB, kWC, kWD, kWE};
+            const uint32_t wofs[4] = {kWB, kWC, kWD, (rawq && sampler) ? 0u : (uint32_t)kWE};
             const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
             const uint32_t acc[4] = {kAccB, kAccC, kAccD, sampler ? 0u : (uint32_t)kAccE};
             uint32_t q = 0;
@@ -637,12 +750,22 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 int t, stn;
                 if (!job_of(k, s, skew, p.S, t, stn)) continue;
                 if (sampler) {
-                    if (stn == 4) stageE(st[s], s, t);
+                    if (stn == 4) {
+                        if (mol) stageE(st[s], s, t);
+                        else if (s == (warp >> 2)) {          // RAW sampler: warps 4s..4s+3 own fold set s (thread = fold)
+                            SET_VIEW(s)
+                            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], (uint32_t)t & 1u);
+                            tcgen05_fence_after();
+                            raw_sampler_e(p, ctl, reinterpret_cast<const float*>(smem + kRawBias), tacc, qd, fold0, nrows, grow, row, t,
+                                          st[s].fold, st[s].utt, key);
+                            tcgen05_fence_before();
+                        }
+                    }
                 } else if (stn == 0) stageA(st[s], s, t);
                 else if (stn == 1) stageB(st[s], s, t);
                 else if (stn == 2) stageC(st[s], s, t);
                 else if (stn == 3) stageD(st[s], s, t);
-                else if (!mol) stageE(st[s], s, t);
+                else if (!has_samplers) stageE(st[s], s, t);
             }
             if (blockIdx.x == 0 && tid == 0 && (k % 500) == 0 && p.progress) {
                 *reinterpret_cast<volatile int*>(p.progress) = k / 5;
@@ -665,6 +788,9 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
 
 cudaError_t set_tc_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc_deadline, &cycles, sizeof(cycles)); }
 size_t loop_tc_weight_image_bytes() { return kWBytes; }
+size_t loop_tc_raw_sampler_image_bytes() { return kRawBias; }
+int loop_tc_raw_sampler_ctas() { return kRawQ; }
+int loop_tc_sampler_ctas(int mode, int raw_samplers) { return mode == 1 ? kTcGroups : (raw_samplers ? kTcGroups * kRawQ : 0); }
 
 // grid: the unit-owning CTAs of both groups, plus (MOL) one sampler CTA per group; cooperative launch because all CTAs
 // spin on each other and must be co-resident
@@ -674,7 +800,7 @@ static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cud
     if (err != cudaSuccess) return err;
     TcParams pp = p;
     void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
-    const int grid = kTcGroups * kTcCtas + (p.mode == 1 ? kTcGroups : 0) + (p.cs_done ? p.n_expanders : 0);
+    const int grid = kTcGroups * kTcCtas + loop_tc_sampler_ctas(p.mode, p.raw_samplers) + (p.cs_done ? p.n_expanders : 0);
     if (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) {
         wrnn_loop_tc_kernel<NSETS><<<grid, NT, kSmemBytes + 1024, stream>>>(m[0], m[1], m[2], m[3], pp);
         return cudaGetLastError();
