@@ -38,7 +38,10 @@ namespace {
 using namespace tc;
 
 constexpr int NEPI = 16;                    // epilogue warps
-constexpr int NT = (NEPI + 3) * 32;         // + TMA producer warp + MMA warp + publisher warp
+#ifndef WRNN_POLLER
+#define WRNN_POLLER 0  // 1: a fourth service warp watches the exchange counters one job ahead of the TMA producer
+#endif
+constexpr int NT = (NEPI + 3 + WRNN_POLLER) * 32;   // + TMA producer warp + MMA warp + publisher warp (+ poller warp)
 constexpr int kSlots = 4, kMaxSlots = 6, kKB = 64, kNKB = kRnn / kKB;   // ring: 4 x 16 KB (6 where the fc3 rows are not resident)
 constexpr int kTileBytes = 128 * 128;       // one [128 rows x 64 fp16] activation tile
 constexpr int NB_ = 64, NC_ = 32, ND_ = 16; // MMA N per stage (E: 16 RAW / 32 MOL)
@@ -68,6 +71,7 @@ struct Ctl {
     uint32_t tmem;
     int abort_local;
     int exp_released;      // expander CTAs: items whose completion barrier the releaser warp has left
+    int polled;            // jobs (in the producer's order) whose exchange counter the poller warp has seen complete
 };
 static_assert(sizeof(Ctl) <= 256, "control block");
 static_assert(kTcSets * kSetCols <= kTmemCols, "TMEM columns");
@@ -351,6 +355,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         for (int i = 0; i < 4 * kTcSets; ++i) mbar_init(&ctl->accfull[i], 1);
         ctl->abort_local = 0;
         ctl->exp_released = 0;
+        ctl->polled = 0;
         mbar_fence_init();
     }
     if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (mol && tid < 30) ? p.bfc3[tid] : 0.f;
@@ -425,6 +430,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             const CUtensorMap* maps[4] = {&tmH1, &tmH2, &tmF1, &tmF2};
             for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
             uint32_t q = 0;
+            int jobno = 0;
             for (int k = 0; k < nslot_total; ++k) {
                 for (int s = 0; s < nsets; ++s) {
                     int t, stn;
@@ -432,7 +438,22 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     const int ph = stn - 1;                       // stations B..E consume the exchange H1, H2, F1, F2
                     if (ph < ph0 || ph >= ph1) continue;
                     const int vg = g * nsets + s;
+#if WRNN_POLLER
+                    {   // the poller warp has (usually long) seen this job's counter: one shared-memory read instead of an L2 round trip
+                        long long t0 = 0;
+                        int spins = 0, seen;
+                        while (true) {
+                            asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&ctl->polled)) : "memory");
+                            if (seen > jobno) break;
+                            if (((++spins) & 1023) == 0 && spin_check(p, ctl, t0)) break;
+                        }
+                        ++jobno;
+                    }
+                    const bool ok = !aborted_local(ctl);
+#else
+                    (void)jobno;
                     const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
+#endif
                     fence_proxy_async();
                     if (s == 0) trace(p, t, 12 + ph);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 0);          // queue timeline: counter seen
@@ -493,6 +514,24 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 }
             }
         }
+#if WRNN_POLLER
+    } else if (warp == NEPI + 3) {
+        // =================================== counter poller =================================================
+        // same job order as the producer; runs ahead of it as far as the counters allow
+        if (lane == 0) {
+            int jobno = 0;
+            for (int k = 0; k < nslot_total; ++k)
+                for (int s = 0; s < nsets; ++s) {
+                    int t, stn;
+                    if (!job_of(k, s, skew, p.S, t, stn)) continue;
+                    const int ph = stn - 1;
+                    if (ph < ph0 || ph >= ph1) continue;
+                    wait_counter(p, ctl, p.counters + (g * nsets + s) * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
+                    ++jobno;
+                    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&ctl->polled)), "r"(jobno) : "memory");
+                }
+        }
+#endif
     } else if (warp == NEPI + 2) {
         // =================================== publisher ======================================================
         // walks the stages in the order the epilogue warps publish them
