@@ -146,6 +146,8 @@ int wrnn_cluster_floor(wrnn_engine* e, int32_t cluster_size, int32_t rounds, flo
 /* Self-test of the tensor-core building blocks (TMA 128B-swizzle load, tcgen05.mma, TMEM load):
  * C[128][N] = A[128][512] * W[N][512]^T, fp16 bit patterns in, fp32 out, N in {16,32,48,64}.            */
 int wrnn_debug_tc_gemm(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int32_t N, float* C);
+/* same on a CTA pair (tcgen05 cta_group::2, M = 256): A (256,512), W (N,512), N in {32,64,96,128}, C (256,N) */
+int wrnn_debug_tc_gemm2(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int32_t N, float* C);
 
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches)          */
 int64_t wrnn_launch_count(const wrnn_engine* e);

@@ -46,7 +46,7 @@ class Request(C.Structure):
 
 EXPORTS = ["wrnn_create", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
            "wrnn_finalize", "wrnn_sparsity", "wrnn_fold_plan", "wrnn_generate", "wrnn_condition", "wrnn_condition_tc", "wrnn_postprocess",
-           "wrnn_xfade_unfold", "wrnn_barrier_floor", "wrnn_cluster_floor", "wrnn_debug_umma_rate", "wrnn_debug_tc_gemm", "wrnn_launch_count"]
+           "wrnn_xfade_unfold", "wrnn_barrier_floor", "wrnn_cluster_floor", "wrnn_debug_umma_rate", "wrnn_debug_tc_gemm", "wrnn_debug_tc_gemm2", "wrnn_launch_count"]
 
 _lib = None
 
@@ -81,6 +81,7 @@ def load():
     lib.wrnn_cluster_floor.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
     lib.wrnn_debug_umma_rate.argtypes = [vp, i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     lib.wrnn_debug_tc_gemm.argtypes = [vp, vp, vp, i32, vp]
+    lib.wrnn_debug_tc_gemm2.argtypes = [vp, vp, vp, i32, vp]
     lib.wrnn_barrier_floor.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.wrnn_launch_count.argtypes = [vp]
     lib.wrnn_launch_count.restype = i64

@@ -1242,6 +1242,27 @@ int wrnn_debug_tc_gemm(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int
     return WRNN_OK;
 }
 
+int wrnn_debug_tc_gemm2(wrnn_engine* e, const uint16_t* A, const uint16_t* W, int32_t N, float* C) {
+    if (!e || !A || !W || !C) return WRNN_ERR_INVALID;
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    CU(e->bScratch.ensure((size_t)256 * 512 * 2 + (size_t)N * 512 * 2 + (size_t)256 * N * 4 + 1024));
+    uint8_t* b = e->bScratch.as<uint8_t>();
+    uint8_t *dA = b, *dW = b + 256 * 512 * 2, *dC = dW + (size_t)N * 512 * 2;
+    CU(cudaMemcpyAsync(dA, A, 256 * 512 * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dW, W, (size_t)N * 512 * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dC, 0, (size_t)256 * N * 4, st));
+    CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
+    CU(run_tc_gemm2_test(dA, dW, N, reinterpret_cast<float*>(dC), e->dAbort, st));
+    e->launches += 1;
+    int status = 0;
+    CU(cudaMemcpyAsync(C, dC, (size_t)256 * N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&status, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (status) return fail(e, WRNN_ERR_TIMEOUT, "tc pair gemm self-test: pipeline stage " + std::to_string(status) + " timed out");
+    return WRNN_OK;
+}
+
 int wrnn_debug_umma_rate(wrnn_engine* e, int32_t N, int32_t iters, int32_t mode, int64_t* cycles_issue, int64_t* cycles_total) {
     if (!e || !cycles_issue || !cycles_total) return WRNN_ERR_INVALID;
     CU(cudaSetDevice(e->device));

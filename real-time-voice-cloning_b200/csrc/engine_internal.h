@@ -202,6 +202,7 @@ cudaError_t make_tmap_f16_2d(void* tmap_out, const void* base, uint64_t rows, ui
                              uint32_t box_cols);
 cudaError_t make_tmap_f16_kblocks(void* tmap_out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_kb);
 cudaError_t run_umma_rate(int N, int iters, int mode, long long* out_dev, cudaStream_t stream);
+cudaError_t run_tc_gemm2_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream);
 cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream);
 
 // ---- exchange-floor microbenchmark (bench_floor.cu) -----------------------------------------------------

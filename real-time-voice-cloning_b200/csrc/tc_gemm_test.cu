@@ -100,6 +100,96 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_test_kernel(const __grid_const
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
 }
+
+// Self-test of the CTA-pair path (cta_group::2): C[256][N] = A[256][512] * W[N][512]^T on one 2-CTA cluster.  CTA r loads A
+// rows [128 r, 128 r + 128) (two k-blocks per TMA operation, 3-slot ring, completion on the even CTA's barriers) and holds W
+// rows [N/2 r, N/2 r + N/2); the even CTA issues tcgen05.mma.cta_group::2 (M = 256) and multicasts the commits; each CTA
+// reads its 128 rows of the accumulator from its own TMEM.
+constexpr int kSlots2 = 3, kSlotBytes2 = 2 * kM * 128;
+__global__ void __launch_bounds__(192, 1) tc_gemm2_test_kernel(const __grid_constant__ CUtensorMap tmapA, const __half* __restrict__ W, int N,
+                                                               float* __restrict__ C, int* __restrict__ status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                                   // kSlots2 x 2 x [128 rows x 128 B]
+    uint8_t* sW = sA + kSlots2 * kSlotBytes2;             // kNKB x [N/2 rows x 128 B]
+    const int NH = N / 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kNKB * NH * 128);
+    uint64_t* full = bars;                                // [kSlots2]  (used in the even CTA)
+    uint64_t* empty = bars + kSlots2;                     // [kSlots2]
+    uint64_t* accfull = bars + 2 * kSlots2;               // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots2 + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    for (int i = tid; i < NH * kNKB * 8; i += blockDim.x) {
+        const int n = i / (kNKB * 8), rem = i % (kNKB * 8), kb = rem / 8, c = rem % 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(W + (size_t)(rank * NH + n) * kK + kb * kKB + c * 8);
+        *reinterpret_cast<uint4*>(sW + kb * NH * 128 + sw128_offset(n, c)) = v;
+    }
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < kSlots2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(accfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc_pair(tmem_slot, 128);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int kOps = kNKB / 2;
+
+    if (warp == 4) {                       // ---- TMA producer (both CTAs) ----
+        if (lane == 0) {
+            tma_prefetch_desc(&tmapA);
+            for (int op = 0; op < kOps; ++op) {
+                const int slot = op % kSlots2, round = op / kSlots2;
+                if (round > 0 && !wait_bar(&empty[slot], (round - 1) & 1)) { atomicExch(status, 2); break; }
+                if (leader) mbar_arrive_expect_tx(&full[slot], 2 * kSlotBytes2);
+                tma_load_3d_pair(sA + slot * kSlotBytes2, &tmapA, &full[slot], 0, (int)rank * kM, 2 * op);
+            }
+        }
+    } else if (warp == 5) {                // ---- MMA issuer (even CTA) ----
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_f16(2 * kM, N);
+            bool ok = true;
+            for (int op = 0; op < kOps && ok; ++op) {
+                const int slot = op % kSlots2, round = op / kSlots2;
+                if (!wait_bar(&full[slot], round & 1)) { atomicExch(status, 3); ok = false; break; }
+                tcgen05_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sA + slot * kSlotBytes2 + kk * kM * 128));
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sW + (2 * op + kk) * NH * 128));
+                    if (op == 0 && kk == 0) umma_f16_pair<false>(tmem, ad, bd, idesc); else umma_f16_pair<true>(tmem, ad, bd, idesc);
+                    umma_f16_pair<true>(tmem, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                    umma_f16_pair<true>(tmem, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                    umma_f16_pair<true>(tmem, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                }
+                umma_commit_pair(&empty[slot]);
+            }
+            umma_commit_pair(accfull);
+        }
+    } else {                               // ---- epilogue warps 0..3 of both CTAs ----
+        const bool ok = wait_bar(accfull, 0);
+        tcgen05_fence_after();
+        if (!ok) { if (lane == 0) atomicExch(status, 4); }
+        else {
+            const int row = warp * 32 + lane;
+            for (int c0 = 0; c0 < N; c0 += 8) {
+                float v[8];
+                tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) C[(size_t)(rank * kM + row) * N + c0 + i] = v[i];
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_pair(tmem, 128);
+}
 // Microbenchmark: issue rate of tcgen05.mma (M=128, K=16, SS operands, SWIZZLE_128B) from one thread.
 //   mode 0: back-to-back MMAs on one accumulator, one commit at the end
 //   mode 1: commit to an mbarrier after every 4 MMAs (the loop kernels' per-k-block pattern), no waiting
@@ -206,6 +296,23 @@ cudaError_t run_tc_gemm_test(const void* A_dev, const void* W_dev, int N, float*
     if (e != cudaSuccess) return e;
     tc_gemm_test_kernel<<<1, 192, smem, stream>>>(tmap, reinterpret_cast<const __half*>(W_dev), N, C_dev, status_dev);
     return cudaGetLastError();
+}
+
+cudaError_t run_tc_gemm2_test(const void* A_dev, const void* W_dev, int N, float* C_dev, int* status_dev, cudaStream_t stream) {
+    if (N % 32 != 0 || N < 32 || N > 128) return cudaErrorInvalidValue;
+    alignas(64) CUtensorMap tmap;
+    cudaError_t e = make_tmap_f16_kblocks(&tmap, A_dev, 2 * kM, kK, kM, 2);
+    if (e != cudaSuccess) return e;
+    const size_t smem = 1024 + (size_t)kSlots2 * kSlotBytes2 + (size_t)kNKB * (N / 2) * 128 + 256;
+    e = cudaFuncSetAttribute(tc_gemm2_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_gemm2_test_kernel, tmap, reinterpret_cast<const __half*>(W_dev), N, C_dev, status_dev);
 }
 
 }  // namespace wrnn

@@ -342,6 +342,17 @@ class WaveRNN(object):
             _raise(self._lib, self._h, rc)
         return out
 
+    def debug_tc_gemm2(self, A, W):
+        """Self-test of the CTA-pair path (tcgen05 cta_group::2): A (256,512), W (N,512) float16 -> (256,N) float32."""
+        A = np.ascontiguousarray(A, dtype=np.float16)
+        W = np.ascontiguousarray(W, dtype=np.float16)
+        assert A.shape == (256, 512) and W.shape[1] == 512
+        out = np.zeros((256, W.shape[0]), np.float32)
+        rc = self._lib.wrnn_debug_tc_gemm2(self._h, A.ctypes.data, W.ctypes.data, W.shape[0], out.ctypes.data)
+        if rc != _native.OK:
+            _raise(self._lib, self._h, rc)
+        return out
+
     def gen_display(self, i, seq_len, b_size, gen_rate):
         """Default progress line (fatchord_version.py:262-265)."""
         done = int(16 * i // max(1, seq_len))

@@ -22,6 +22,17 @@ def test_tc_gemm_self_test(model, N):
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-4)
 
 
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_tc_pair_gemm_self_test(model, N):
+    """CTA pair (cta_group::2, M = 256): each CTA brings 128 rows of A and N/2 rows of W."""
+    rng = np.random.default_rng(100 + N)
+    A = rng.uniform(-1, 1, size=(256, 512)).astype(np.float16)
+    W = rng.uniform(-0.05, 0.05, size=(N, 512)).astype(np.float16)
+    got = model.debug_tc_gemm2(A, W)
+    want = A.astype(np.float32) @ W.astype(np.float32).T
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-4)
+
+
 # ---- the fp16 tensor-core loop ("bf16/fp16 weights stated separately" in the north_star) ---------------------
 # Measured on CPU by emulating fp16 rounding of weights and activations in the oracle: logits within ~4e-4
 # relative, ~99.94 % identical draws on the random-init model.  Gates used here: 1e-3 relative, 99.8 % draws.
