@@ -943,6 +943,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             // up to 256 folds: one set per group; more: two or three sets per group, pipelined through the same CTAs
             int nsets = std::min(kTcSets, (B + kTcGroups * 128 - 1) / (kTcGroups * 128));
             if (const char* ev = getenv("WRNN_TC_SETS")) nsets = std::max(nsets, std::min(kTcSets, atoi(ev)));
+            // RAW with 512 classes: fc3 + the draw on 4 sampler CTAs per group (WRNN_TC_RAWSAMP=0: classes spread over the unit-owning CTAs)
+            const bool raw_samplers = e->mode != WRNN_MODE_MOL && e->C == 512 && !(getenv("WRNN_TC_RAWSAMP") && atoi(getenv("WRNN_TC_RAWSAMP")) == 0);
+            // CTA pairs (tcgen05 cta_group::2) whenever fc3 has its own CTAs: an even number of sets per group, set 2s+r on the
+            // rank-r CTA of every pair (WRNN_TC_PAIR=0: one CTA per MMA)
+            const bool pair = (e->mode == WRNN_MODE_MOL || raw_samplers) && !(getenv("WRNN_TC_PAIR") && atoi(getenv("WRNN_TC_PAIR")) == 0);
+            if (pair) nsets = nsets <= 2 ? 2 : 4;
             const int nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
             // The expansion is HBM-write-bound (~0.5 ms per GB; 17 GB for a 60 s utterance).  Kernels on different streams
             // do not overlap on this platform (tools/probes/concurrent.cu), so it runs INSIDE the loop kernel: the loop
@@ -983,8 +989,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             tp.wimg = e->wTc.as<unsigned char>();
             tp.v1 = e->dv1; tp.v2 = e->dv2; tp.v3 = e->dv3; tp.bhn1 = e->dbhn1; tp.bhn2 = e->dbhn2; tp.bfc3 = e->dbfc3;
             tp.CS = e->bCS.as<float4>(); tp.Mg = Mg; tp.nsets = nsets; tp.cs_steps = cs_steps;
-            // RAW with 512 classes: fc3 + the draw on 4 sampler CTAs per group (WRNN_TC_RAWSAMP=0: classes spread over the unit-owning CTAs)
-            if (e->mode != WRNN_MODE_MOL && e->C == 512 && !(getenv("WRNN_TC_RAWSAMP") && atoi(getenv("WRNN_TC_RAWSAMP")) == 0)) {
+            tp.pair = pair ? 1 : 0;
+            if (raw_samplers) {
                 tp.raw_samplers = 1;
                 tp.wimg_s = e->wTcS.as<unsigned char>();
             }
@@ -994,7 +1000,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
                 tp.coef = e->dcoef;
                 tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers)));
-                if (tp.n_expanders == 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
+                if (pair && ((kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers) + tp.n_expanders) & 1)) --tp.n_expanders;   // 2-CTA clusters
+                if (tp.n_expanders <= 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
             }
             if (const char* ev = getenv("WRNN_TC_FLAGS")) tp.flags = atoi(ev);
             tp.folds = e->bFolds.as<FoldDesc>() + w0;

@@ -71,6 +71,7 @@ struct TcParams {
     const float4* CS;            // per-sample conditioning [virtual group][step][row < Mg][256 unit pairs][4 float4] (expand_cond)
     int Mg;                      // folds per virtual group (= group x set); fold f is row f % Mg of virtual group f / Mg
     int nsets;                   // fold sets per group in this launch (1..kTcSets)
+    int pair;                    // != 0: unit-owning CTAs work as CTA pairs (cta_group::2); nsets is 2 or 4
     const FoldDesc* folds;
     int B, S, C, Cpad, mode;
     // conditioning expansion inside the loop kernel (expander CTAs on the SMs the loop leaves free): per-frame tables in,

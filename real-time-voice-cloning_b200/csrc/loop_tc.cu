@@ -38,10 +38,7 @@ namespace {
 using namespace tc;
 
 constexpr int NEPI = 16;                    // epilogue warps
-#ifndef WRNN_POLLER
-#define WRNN_POLLER 0  // 1: a fourth service warp watches the exchange counters one job ahead of the TMA producer
-#endif
-constexpr int NT = (NEPI + 3 + WRNN_POLLER) * 32;   // + TMA producer warp + MMA warp + publisher warp (+ poller warp)
+constexpr int NT = (NEPI + 3) * 32;         // + TMA producer warp + MMA warp + publisher warp
 constexpr int kSlots = 4, kMaxSlots = 6, kKB = 64, kNKB = kRnn / kKB;   // ring: 4 x 16 KB (6 where the fc3 rows are not resident)
 constexpr int kTileBytes = 128 * 128;       // one [128 rows x 64 fp16] activation tile
 constexpr int NB_ = 64, NC_ = 32, ND_ = 16; // MMA N per stage (E: 16 RAW / 32 MOL)
@@ -71,10 +68,8 @@ struct Ctl {
     uint32_t tmem;
     int abort_local;
     int exp_released;      // expander CTAs: items whose completion barrier the releaser warp has left
-    int polled;            // jobs (in the producer's order) whose exchange counter the poller warp has seen complete
 };
 static_assert(sizeof(Ctl) <= 256, "control block");
-static_assert(kTcSets * kSetCols <= kTmemCols, "TMEM columns");
 
 // Abort state: a CTA-local flag in shared memory (cheap to poll) mirrors the global flag (polled rarely: a
 // global load costs ~0.7 us and must stay off the wait paths).
@@ -293,22 +288,24 @@ __device__ __forceinline__ bool job_of(int k, int s, int skew, int S, int& t, in
     return true;
 }
 
-// per-thread recurrent state of one fold set (a CTA serves up to kTcSets sets of <= 128 folds, software-pipelined: while
-// one set's activations travel and its MMAs run, the epilogue warps work on the other sets).  Everything else about a
-// set is recomputed from its index, and the conditioning record is fetched stage by stage just before the wait of that
-// stage, so that only these registers stay live across the other sets' stages.
-#ifndef WRNN_JIT
-#define WRNN_JIT 0     // 1: fetch the conditioning record stage by stage (fewer live registers; measured 5-8 % slower)
-#endif
+// per-thread recurrent state of one fold set (a CTA serves several sets of <= 128 folds, software-pipelined: while one
+// set's activations travel and its MMAs run, the epilogue warps work on the other sets).  H = unit blocks of 8 hidden
+// units the CTA's accumulator rows cover: 1, or 2 for a CTA pair (its own and its partner's).  The whole conditioning
+// record is fetched in stage A (fetching it stage by stage needs fewer registers but measured 5-8 % slower).
+template <int H>
 struct SetState {
     uint32_t fold, utt;          // Philox counter words of my fold
-    float x, h1[2], h2[2], p3[2];
-#if !WRNN_JIT
-    float2 cr; float4 cz; float4 c34;      // whole conditioning record fetched in stage A
-#endif
+    float x, h1[2 * H], h2[2 * H], p3[2 * H];
+    float2 cr[H]; float4 cz[H]; float4 c34[H];
 };
 
-template <int NSETS>
+// NSETS = fold sets the epilogue warps of a unit-owning CTA serve.
+// PAIR  = the unit-owning CTAs work as CTA pairs (2-CTA clusters, tcgen05 cta_group::2): one MMA of M = 256 covers a set of
+//         the even CTA (A rows 0..127) and a set of the odd CTA (rows 128..255) against BOTH CTAs' weight rows (N doubles),
+//         so every activation tile a CTA pulls from L2 is used for 16 hidden units instead of 8: half the TMA operations,
+//         MMAs and L2->SM bytes per fold.  A group then has 2*NSETS sets; set 2s+r belongs to the rank-r CTAs (32 CTAs
+//         publish it and arrive on its counters).  Needs dedicated sampler CTAs (MOL, RAW-512).
+template <int NSETS, bool PAIR>
 __global__ void __launch_bounds__(NT, 1)
 wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmH2,
                     const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ TcParams p) {
@@ -328,7 +325,19 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const int cta = sampler ? 0 : (int)blockIdx.x % kTcCtas;              // unit-owning CTA inside the group
     const bool expander = sampler && sidx >= kTcGroups * spg;             // blocks past the loop's CTAs expand the conditioning
     const bool idle = expander;
-    constexpr int nsets = NSETS;                                          // fold sets per group (1..kTcSets)
+    constexpr int H = PAIR ? 2 : 1;                                       // unit blocks per epilogue thread
+    constexpr int GS = PAIR ? 2 * NSETS : NSETS;                          // fold sets per group
+    const bool pairu = PAIR && !sampler;                                  // this CTA is half of a CTA pair
+    const int rank = pairu ? (cta & 1) : 0;
+    const bool leader = rank == 0;                                        // issues the pair's MMAs, owns the `full` barriers
+    const int ctab = pairu ? (cta & ~1) : cta;                            // first unit block of my accumulator columns
+    const int nsets = sampler ? GS : NSETS;                               // sets this CTA works on
+    const unsigned int arrivals = PAIR ? kTcCtas / 2 : kTcCtas;           // CTAs that publish a set's activations
+    // TMEM columns of a unit-owning CTA, per set: [B | C | D | (E)]; a pair's accumulators are twice as wide
+    constexpr uint32_t accB = 0, accC = PAIR ? 128 : 64, accD = PAIR ? 192 : 96, setColsU = PAIR ? 256 : 128;
+    const uint32_t set_cols = sampler ? 128u : setColsU;
+    static_assert(NSETS * (PAIR ? 256 : 128) <= kTmemCols && GS <= kTcSets, "TMEM columns");
+#define VG_OF(s) (g * GS + (pairu ? 2 * (s) + rank : (s)))
     const int NE = mol ? 32 : ((rawq && sampler) ? kRawQCols : 16);
     const int ph0 = sampler ? 3 : 0, ph1 = (has_samplers && !sampler) ? 3 : 4;   // stages whose MMAs this CTA runs
     const int skew = (p.flags >> 4) & 7;                                  // stations set s runs behind set s-1 (0: all sets in phase)
@@ -355,12 +364,12 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         for (int i = 0; i < 4 * kTcSets; ++i) mbar_init(&ctl->accfull[i], 1);
         ctl->abort_local = 0;
         ctl->exp_released = 0;
-        ctl->polled = 0;
         mbar_fence_init();
     }
     if (tid < 32) reinterpret_cast<float*>(smem + kBias)[tid] = (mol && tid < 30) ? p.bfc3[tid] : 0.f;
-    if (tid < 72) {                     // [unit pair 4][v1 r,z,n x2 | v2 r,z,n x2 | v3 x2 | b_hn1 x2 | b_hn2 x2]
-        const int up_ = tid / 18, i = tid % 18, u = i & 1, j = cta * kTcUnits + 2 * up_ + u;
+    if (tid < 72 * H) {                 // per unit block: [unit pair 4][v1 r,z,n x2 | v2 r,z,n x2 | v3 x2 | b_hn1 x2 | b_hn2 x2]
+        const int hb = tid / 72, r72 = tid % 72;
+        const int up_ = r72 / 18, i = r72 % 18, u = i & 1, j = (ctab + hb) * kTcUnits + 2 * up_ + u;
         float v;
         if (i < 6) v = p.v1[(i >> 1) * kRnn + j];
         else if (i < 12) v = p.v2[((i - 6) >> 1) * kRnn + j];
@@ -371,9 +380,11 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     }
     if (expander && p.cs_done)                      // interpolation weights [200][kTaps]: broadcast reads from shared memory
         for (int i = tid; i < kHop * kTaps; i += NT) reinterpret_cast<float*>(smem)[i] = p.coef[i];
-    if (warp == 0 && !idle) tmem_alloc(&ctl->tmem, kTmemCols);
+    if (warp == 0 && !idle) {
+        if (pairu) tmem_alloc_pair(&ctl->tmem, kTmemCols); else tmem_alloc(&ctl->tmem, kTmemCols);
+    }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();        // (pair: the partner's barriers are initialised before any TMA completes on them)
     tcgen05_fence_after();
     const uint32_t tmem = ctl->tmem;
 
@@ -426,34 +437,19 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     } else
     if (warp == NEPI) {
         // =================================== TMA producer ===================================================
+        // (pair: both CTAs load their own set's rows; the bytes of both complete on the even CTA's `full` barrier)
         if (lane == 0) {
             const CUtensorMap* maps[4] = {&tmH1, &tmH2, &tmF1, &tmF2};
             for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
             uint32_t q = 0;
-            int jobno = 0;
             for (int k = 0; k < nslot_total; ++k) {
                 for (int s = 0; s < nsets; ++s) {
                     int t, stn;
                     if (!job_of(k, s, skew, p.S, t, stn)) continue;
                     const int ph = stn - 1;                       // stations B..E consume the exchange H1, H2, F1, F2
                     if (ph < ph0 || ph >= ph1) continue;
-                    const int vg = g * nsets + s;
-#if WRNN_POLLER
-                    {   // the poller warp has (usually long) seen this job's counter: one shared-memory read instead of an L2 round trip
-                        long long t0 = 0;
-                        int spins = 0, seen;
-                        while (true) {
-                            asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&ctl->polled)) : "memory");
-                            if (seen > jobno) break;
-                            if (((++spins) & 1023) == 0 && spin_check(p, ctl, t0)) break;
-                        }
-                        ++jobno;
-                    }
-                    const bool ok = !aborted_local(ctl);
-#else
-                    (void)jobno;
-                    const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
-#endif
+                    const int vg = VG_OF(s);
+                    const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, arrivals * (unsigned int)(t + 1));
                     fence_proxy_async();
                     if (s == 0) trace(p, t, 12 + ph);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 0);          // queue timeline: counter seen
@@ -463,8 +459,13 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                         if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
                         if (ph == 0 && s == 1) trace(p, t, 128 + kb);              // tile timeline of one job: slot free
                         if (go && !aborted(p, ctl)) {
-                            mbar_arrive_expect_tx(&ctl->full[slot], kTcKbPerOp * kb_bytes);
-                            tma_load_3d(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
+                            if (pairu) {
+                                if (leader) mbar_arrive_expect_tx(&ctl->full[slot], 2 * kTcKbPerOp * kb_bytes);
+                                tma_load_3d_pair(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
+                            } else {
+                                mbar_arrive_expect_tx(&ctl->full[slot], kTcKbPerOp * kb_bytes);
+                                tma_load_3d(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
+                            }
                         }
                     }
                     if (s == 0) trace(p, t, 16 + ph);
@@ -474,10 +475,10 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         }
     } else if (warp == NEPI + 1) {
         // =================================== MMA issuer =====================================================
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             const uint32_t wofs[4] = {kWB, kWC, kWD, (rawq && sampler) ? 0u : (uint32_t)kWE};
             const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
-            const uint32_t acc[4] = {kAccB, kAccC, kAccD, sampler ? 0u : (uint32_t)kAccE};
+            const uint32_t acc[4] = {accB, accC, accD, sampler ? 0u : (uint32_t)kAccE};
             uint32_t q = 0;
             for (int k = 0; k < nslot_total; ++k) {
                 for (int s = 0; s < nsets; ++s) {
@@ -485,8 +486,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     if (!job_of(k, s, skew, p.S, t, stn)) continue;
                     const int ph = stn - 1;
                     if (ph < ph0 || ph >= ph1) continue;
-                    const uint32_t idesc = umma_idesc_f16(128, (int)ncol[ph]);
-                    const uint32_t dcol = tmem + (uint32_t)s * kSetCols + acc[ph];
+                    const uint32_t idesc = pairu ? umma_idesc_f16(256, 2 * (int)ncol[ph]) : umma_idesc_f16(128, (int)ncol[ph]);
+                    const uint32_t dcol = tmem + (uint32_t)s * set_cols + acc[ph];
                     for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
                         const uint32_t slot = q % nslots, round = q / nslots;
                         if (s == 0 && ph == 0 && kb < 4) trace(p, t, 24 + kb);
@@ -500,38 +501,27 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                             for (int kk = 0; kk < kTcKbPerOp; ++kk) {
                                 const uint64_t ad = umma_desc_sw128(smem_u32(smem + ring0 + slot * slot_bytes) + kk * kb_bytes);
                                 const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs[ph] + (kb + kk) * ncol[ph] * 128));
-                                if (kb + kk == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
-                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
-                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
-                                umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                if (PAIR && pairu) {
+                                    if (kb + kk == 0) umma_f16_pair<false>(dcol, ad, bd, idesc); else umma_f16_pair<true>(dcol, ad, bd, idesc);
+                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                } else {
+                                    if (kb + kk == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
+                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                }
                             }
                         }
-                        umma_commit(&ctl->empty[slot]);
+                        if (PAIR && pairu) umma_commit_pair(&ctl->empty[slot]); else umma_commit(&ctl->empty[slot]);
                         if (ph == 0 && s == 1) trace(p, t, 144 + kb);              // MMAs + commit issued
                     }
-                    umma_commit(&ctl->accfull[s * 4 + ph]);
+                    if (PAIR && pairu) umma_commit_pair(&ctl->accfull[s * 4 + ph]); else umma_commit(&ctl->accfull[s * 4 + ph]);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 3);          // all MMAs of the job issued
                 }
             }
         }
-#if WRNN_POLLER
-    } else if (warp == NEPI + 3) {
-        // =================================== counter poller =================================================
-        // same job order as the producer; runs ahead of it as far as the counters allow
-        if (lane == 0) {
-            int jobno = 0;
-            for (int k = 0; k < nslot_total; ++k)
-                for (int s = 0; s < nsets; ++s) {
-                    int t, stn;
-                    if (!job_of(k, s, skew, p.S, t, stn)) continue;
-                    const int ph = stn - 1;
-                    if (ph < ph0 || ph >= ph1) continue;
-                    wait_counter(p, ctl, p.counters + (g * nsets + s) * 4 + ph, (unsigned int)kTcCtas * (unsigned int)(t + 1));
-                    ++jobno;
-                    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&ctl->polled)), "r"(jobno) : "memory");
-                }
-        }
-#endif
     } else if (warp == NEPI + 2) {
         // =================================== publisher ======================================================
         // walks the stages in the order the epilogue warps publish them
@@ -540,7 +530,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 for (int s = 0; s < nsets; ++s) {
                     int t, stn;
                     if (!job_of(k, s, skew, p.S, t, stn) || stn >= 4) continue;
-                    publisher_release(s, p.counters + (g * nsets + s) * 4 + stn);
+                    publisher_release(s, p.counters + VG_OF(s) * 4 + stn);
                     // stage A is the only reader of the conditioning records: after the last set's, the chunk may be recycled
                     if (p.cs_consumed && stn == 0 && s == nsets - 1 && ((t + 1) % kExpandSteps == 0) && lane == 0)
                         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_consumed + t / kExpandSteps) : "memory");
@@ -548,184 +538,52 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         }
     } else {
         // =================================== epilogue warps =================================================
-        // thread = (fold row, unit pair up): TMEM lane = row, my units are 8*cta + 2*up + {0,1}
+        // thread = (fold row, unit pair up): TMEM lane = row; my units are 8*(ctab+h) + 2*up + {0,1} for unit block h < H
         const int row = (warp & 3) * 32 + lane, up = warp >> 2;
-        const int j0 = cta * kTcUnits + 2 * up;                           // first of my two hidden units
-        // per-unit constants of my two units: shared memory (every lane of a warp reads the same word: a broadcast), not registers
-        const float* kc = reinterpret_cast<const float*>(smem + kConst) + up * 18;
-#define v1 (kc + 0)
-#define v2 (kc + 6)
-#define v3 (kc + 12)
-#define bh1 (kc + 14)
-#define bh2 (kc + 16)
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         const bool inl = (p.flags & 1) != 0;
         const size_t cs_rec = (size_t)kTcCtas * 4 * 4;                      // float4 per (t,row) record = 1024
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        SetState st[NSETS];
-        int nrows_[NSETS];
-#pragma unroll
-        for (int s = 0; s < NSETS; ++s) {
-            const int fold0 = (g * nsets + s) * p.Mg;
-            nrows_[s] = max(0, min(p.Mg, p.B - fold0));
-            const FoldDesc fd = p.folds[row < nrows_[s] ? fold0 + row : 0];
-            st[s].fold = (uint32_t)fd.fold; st[s].utt = (uint32_t)fd.utt;
-            st[s].x = 0.f; st[s].h1[0] = st[s].h1[1] = st[s].h2[0] = st[s].h2[1] = st[s].p3[0] = st[s].p3[1] = 0.f;
-        }
         // per-set quantities derived from the set index
 #define SET_VIEW(s)                                                                                              \
-        const int vg = g * nsets + (s);                                                                          \
+        const int vg = VG_OF(s);                                                                                 \
         const int fold0 = vg * p.Mg;                                                                             \
-        const int nrows = nrows_[s];                                                                             \
+        const int nrows = max(0, min(p.Mg, p.B - fold0));                                                        \
         const bool live = row < nrows;                                                                           \
         const size_t grow = (size_t)vg * 128 + row;                                                              \
-        const uint32_t tacc = tlane + (uint32_t)(s) * kSetCols;                                                  \
+        const uint32_t tacc = tlane + (uint32_t)(s) * set_cols;                                                  \
         unsigned int* const ctrs = p.counters + vg * 4;                                                          \
-        const float4* const cs = p.CS + (((size_t)vg * p.cs_steps + (t % p.cs_steps)) * p.Mg + row) * cs_rec + ((size_t)cta * 4 + up) * 4;   \
-        (void)fold0; (void)nrows; (void)live; (void)grow; (void)tacc; (void)ctrs; (void)cs;
+        (void)fold0; (void)nrows; (void)live; (void)grow; (void)tacc; (void)ctrs;
 
-        // ---- A: x_{t-1}, GRU1 for my 2 units, publish h1 ---------------------------------------------------
-        auto stageA = [&](SetState& S, const int s, const int t) {
-            SET_VIEW(s)
-            float4 ca = make_float4(0.f, 0.f, 0.f, 0.f);
-            float2 cn = make_float2(0.f, 0.f);
-            if (p.cs_done && (t % kExpandSteps) == 0 && live)     // the expansion runs on the spare SMs, a few chunks ahead of us
-                wait_counter(p, ctl, p.cs_done + t / kExpandSteps, (unsigned int)p.B);
-            if (live) { ca = __ldcs(cs); cn = __ldcs(reinterpret_cast<const float2*>(cs + 1)); }   // issued before the wait on x
-#if !WRNN_JIT
-            if (live) { S.cr = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); S.cz = __ldcs(cs + 2); S.c34 = __ldcs(cs + 3); }
-#endif
-            if (tid == 0) trace(p, t, s == 0 ? 0 : 31);
-            etrace(p, t, s, 0);
-            S.x = 0.f;
-            if (t > 0 && live) wait_x(p, ctl, p.bX + grow, (uint32_t)t, S.x);
-            if (tid == 0 && s == 0) trace(p, t, 1);
-            etrace(p, t, s, 1);
-            float gh[8];
-            if (t > 0) { tmem_ld8(tacc + kAccB + 16 * up + 8, gh); tmem_ld_wait(); }
-            else {
+        if (sampler) {
+            // ---- E on a sampler CTA: fc3 + the draw for every set of the group ---------------------------------
+            uint32_t sfold[GS], sutt[GS];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) gh[i] = 0.f;
+            for (int s = 0; s < GS; ++s) {
+                SET_VIEW(s)
+                const FoldDesc fd = p.folds[live ? fold0 + row : 0];
+                sfold[s] = (uint32_t)fd.fold; sutt[s] = (uint32_t)fd.utt;
             }
-            const float c1r[2] = {ca.x, ca.y}, c1z[2] = {ca.z, ca.w}, c1n[2] = {cn.x, cn.y};
+            for (int k = 0; k < nslot_total; ++k) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float r = sigmoid_fast(fmaf(v1[0 + u], S.x, c1r[u]) + gh[0 + u]);
-                const float z = sigmoid_fast(fmaf(v1[2 + u], S.x, c1z[u]) + gh[2 + u]);
-                const float n = tanh_fast(fmaf(v1[4 + u], S.x, c1n[u]) + r * (gh[4 + u] + bh1[u]));
-                S.h1[u] = (1.0f - z) * n + z * S.h1[u];
-            }
-            if (live) *reinterpret_cast<__half2*>(p.H1 + grow * kRnn + j0) = __floats2half2_rn(S.h1[0], S.h1[1]);
-            tcgen05_fence_before();
-            publish_arrive(s, inl, ctrs + 0);
-            if (tid == 0 && s == 0) trace(p, t, 2);
-            etrace(p, t, s, 2);
-        };
-        // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 -------------------------------------------
-        auto stageB = [&](SetState& S, const int s, const int t) {
-            SET_VIEW(s)
-            float2 cr = make_float2(0.f, 0.f);
-            float4 cz = make_float4(0.f, 0.f, 0.f, 0.f);
-#if WRNN_JIT
-            if (live) { cr = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); cz = __ldcs(cs + 2); }
-#else
-            if (live) { cr = S.cr; cz = S.cz; }
-#endif
-            float pb[8], gh[8];
-            etrace(p, t, s, 3);
-            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 0], (uint32_t)t & 1u);
-            tcgen05_fence_after();
-            if (tid == 0 && s == 0) trace(p, t, 3);
-            etrace(p, t, s, 4);
-            tmem_ld8(tacc + kAccB + 16 * up, pb);
-            if (t > 0) tmem_ld8(tacc + kAccC + 8 * up, gh);
-            else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) gh[i] = 0.f;
-            }
-            tmem_ld_wait();
-            if (tid == 0 && s == 0) trace(p, t, 28);
-            const float c2r[2] = {cr.x, cr.y}, c2z[2] = {cz.x, cz.y}, c2n[2] = {cz.z, cz.w};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float r = sigmoid_fast(pb[0 + u] + fmaf(v2[0 + u], S.x, c2r[u]) + gh[0 + u]);
-                const float z = sigmoid_fast(pb[2 + u] + fmaf(v2[2 + u], S.x, c2z[u]) + gh[2 + u]);
-                const float n = tanh_fast(pb[4 + u] + fmaf(v2[4 + u], S.x, c2n[u]) + r * (gh[4 + u] + bh2[u]));
-                S.h2[u] = (1.0f - z) * n + z * S.h2[u];
-                S.p3[u] = pb[6 + u];
-            }
-            if (live) *reinterpret_cast<__half2*>(p.H2 + grow * kRnn + j0) = __floats2half2_rn(S.h2[0], S.h2[1]);
-            if (tid == 0 && s == 0) trace(p, t, 29);
-            tcgen05_fence_before();
-            publish_arrive(s, inl, ctrs + 1);
-            if (tid == 0 && s == 0) trace(p, t, 4);
-            etrace(p, t, s, 5);
-        };
-        // ---- C: [gh2' | W_fc1a h2] ; f1 ; publish ------------------------------------------------------------
-        auto stageC = [&](SetState& S, const int s, const int t) {
-            SET_VIEW(s)
-            float2 c3 = make_float2(0.f, 0.f);
-#if WRNN_JIT
-            if (live) c3 = __ldcs(reinterpret_cast<const float2*>(cs + 3));
-#else
-            if (live) c3 = make_float2(S.c34.x, S.c34.y);
-#endif
-            float pb[8];
-            etrace(p, t, s, 6);
-            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 1], (uint32_t)t & 1u);
-            tcgen05_fence_after();
-            if (tid == 0 && s == 0) trace(p, t, 5);
-            etrace(p, t, s, 7);
-            tmem_ld8(tacc + kAccC + 8 * up, pb);
-            tmem_ld_wait();
-            const float f0 = fmaxf(S.p3[0] + pb[6] + fmaf(v3[0], S.x, c3.x), 0.f);
-            const float f1 = fmaxf(S.p3[1] + pb[7] + fmaf(v3[1], S.x, c3.y), 0.f);
-            if (live) *reinterpret_cast<__half2*>(p.F1 + grow * kRnn + j0) = __floats2half2_rn(f0, f1);
-            tcgen05_fence_before();
-            publish_arrive(s, inl, ctrs + 2);
-            if (tid == 0 && s == 0) trace(p, t, 6);
-            etrace(p, t, s, 8);
-        };
-        // ---- D: fc2 ; publish ----------------------------------------------------------------------------------
-        auto stageD = [&](SetState& S, const int s, const int t) {
-            SET_VIEW(s)
-            float2 c4 = make_float2(0.f, 0.f);
-#if WRNN_JIT
-            if (live) {
-                c4 = __ldcs(reinterpret_cast<const float2*>(cs + 3) + 1);
-                if (t + 1 < p.S && (p.flags & 4)) {           // next step's record: pull both sectors into L2 now (no registers held)
-                    const float4* nx = cs + (size_t)p.Mg * cs_rec;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 2));
-                }
-            }
-#else
-            if (live) c4 = make_float2(S.c34.z, S.c34.w);
-#endif
-            etrace(p, t, s, 9);
-            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 2], (uint32_t)t & 1u);
-            tcgen05_fence_after();
-            if (tid == 0 && s == 0) trace(p, t, 7);
-            etrace(p, t, s, 10);
-            float d[4];
-            tmem_ld4(tacc + kAccD + 2 * up, d);
-            tmem_ld_wait();
-            if (live) *reinterpret_cast<__half2*>(p.F2 + grow * kRnn + j0) = __floats2half2_rn(fmaxf(d[0] + c4.x, 0.f), fmaxf(d[1] + c4.y, 0.f));
-            tcgen05_fence_before();
-            publish_arrive(s, inl, ctrs + 3);
-            if (tid == 0 && s == 0) trace(p, t, 8);
-            etrace(p, t, s, 11);
-        };
-        // ---- E: fc3 + sampling ---------------------------------------------------------------------------------
-        auto stageE = [&](SetState& S, const int s, const int t) {
-            SET_VIEW(s)
-            const uint32_t par = (uint32_t)t & 1u;
-            if (p.mode == 1) {
-                // MOL (vocoder/distribution.py:104-140): CTA 0 of the group has all 30 outputs of a fold in one TMEM
-                // lane.  The four threads of a fold split the Gumbel draws (thread `up` owns Philox block `up`, i.e.
-                // mixtures 4up..4up+3), meet through shared memory, and thread up==2 (which also holds the logistic
-                // uniform, block 2 word 2) finishes the draw.
-                if (sampler) {
+                for (int s = 0; s < GS; ++s) {
+                    int t, stn;
+                    if (!job_of(k, s, skew, p.S, t, stn) || stn != 4) continue;
+                    SET_VIEW(s)
+                    const uint32_t par = (uint32_t)t & 1u;
+                    if (!mol) {
+                        if (s != (warp >> 2)) continue;           // RAW sampler: warps 4s..4s+3 own fold set s (thread = fold)
+                        wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
+                        tcgen05_fence_after();
+                        raw_sampler_e(p, ctl, reinterpret_cast<const float*>(smem + kRawBias), tacc, qd, fold0, nrows, grow, row, t,
+                                      sfold[s], sutt[s], key);
+                        tcgen05_fence_before();
+                        continue;
+                    }
+                    // MOL (vocoder/distribution.py:104-140): all 30 outputs of a fold sit in one TMEM lane.  The four
+                    // threads of a fold split the Gumbel draws (thread `up` owns Philox block `up`, i.e. mixtures
+                    // 4up..4up+3), meet through shared memory, and thread up==2 (which also holds the logistic uniform,
+                    // block 2 word 2) finishes the draw.
                     wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
                     tcgen05_fence_after();
                     if (tid == 0 && s == 0) trace(p, t, 9);
@@ -735,7 +593,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     tmem_ld_wait();
                     const float* sbias = reinterpret_cast<const float*>(smem + kBias);
                     float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch + s * kMolScratchBytes);
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, S.fold, S.utt, (uint32_t)(up < 3 ? up : 2)), key);
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, sfold[s], sutt[s], (uint32_t)(up < 3 ? up : 2)), key);
                     float best = -INFINITY;
                     int kbest = 0;
 #pragma unroll
@@ -775,12 +633,169 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     tcgen05_fence_before();
                     if (tid == 0 && s == 0) trace(p, t, 10);
                 }
-            } else {
-                wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
-                tcgen05_fence_after();
-                raw_stage_e(p, ctl, tacc, cta, fold0, nrows, grow, t, key);
-                tcgen05_fence_before();
             }
+        } else {
+        // per-unit constants of my units: shared memory (every lane of a warp reads the same word: a broadcast), not registers
+        const float* kc0 = reinterpret_cast<const float*>(smem + kConst) + up * 18;
+#define KC(h) (kc0 + (h) * 72)
+        SetState<H> st[NSETS];
+#pragma unroll
+        for (int s = 0; s < NSETS; ++s) {
+            SET_VIEW(s)
+            const FoldDesc fd = p.folds[live ? fold0 + row : 0];
+            st[s].fold = (uint32_t)fd.fold; st[s].utt = (uint32_t)fd.utt;
+            st[s].x = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2 * H; ++i) st[s].h1[i] = st[s].h2[i] = st[s].p3[i] = 0.f;
+        }
+        // conditioning record of unit block h, my unit pair: 4 float4 at
+#define CS_OF(h) (p.CS + (((size_t)vg * p.cs_steps + (t % p.cs_steps)) * p.Mg + row) * cs_rec + ((size_t)(ctab + (h)) * 4 + up) * 4)
+#define J0_OF(h) ((ctab + (h)) * kTcUnits + 2 * up)
+
+        // ---- A: x_{t-1}, GRU1 for my units, publish h1 -------------------------------------------------------
+        auto stageA = [&](SetState<H>& S, const int s, const int t) {
+            SET_VIEW(s)
+            float4 ca[H];
+            float2 cn[H];
+            if (p.cs_done && (t % kExpandSteps) == 0 && live)     // the expansion runs on the spare SMs, a few chunks ahead of us
+                wait_counter(p, ctl, p.cs_done + t / kExpandSteps, (unsigned int)p.B);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                ca[h] = make_float4(0.f, 0.f, 0.f, 0.f); cn[h] = make_float2(0.f, 0.f);
+                if (live) {                                         // issued before the wait on x
+                    const float4* cs = CS_OF(h);
+                    ca[h] = __ldcs(cs); cn[h] = __ldcs(reinterpret_cast<const float2*>(cs + 1));
+                    S.cr[h] = __ldcs(reinterpret_cast<const float2*>(cs + 1) + 1); S.cz[h] = __ldcs(cs + 2); S.c34[h] = __ldcs(cs + 3);
+                }
+            }
+            if (tid == 0) trace(p, t, s == 0 ? 0 : 31);
+            etrace(p, t, s, 0);
+            S.x = 0.f;
+            if (t > 0 && live) wait_x(p, ctl, p.bX + grow, (uint32_t)t, S.x);
+            if (tid == 0 && s == 0) trace(p, t, 1);
+            etrace(p, t, s, 1);
+            float gh[H][8];
+            if (t > 0) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) tmem_ld8(tacc + accB + h * NB_ + 16 * up + 8, gh[h]);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int h = 0; h < H; ++h)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gh[h][i] = 0.f;
+            }
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float* v1 = KC(h);
+                const float* bh1 = KC(h) + 14;
+                const float c1r[2] = {ca[h].x, ca[h].y}, c1z[2] = {ca[h].z, ca[h].w}, c1n[2] = {cn[h].x, cn[h].y};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float r = sigmoid_fast(fmaf(v1[0 + u], S.x, c1r[u]) + gh[h][0 + u]);
+                    const float z = sigmoid_fast(fmaf(v1[2 + u], S.x, c1z[u]) + gh[h][2 + u]);
+                    const float n = tanh_fast(fmaf(v1[4 + u], S.x, c1n[u]) + r * (gh[h][4 + u] + bh1[u]));
+                    S.h1[2 * h + u] = (1.0f - z) * n + z * S.h1[2 * h + u];
+                }
+                if (live) *reinterpret_cast<__half2*>(p.H1 + grow * kRnn + J0_OF(h)) = __floats2half2_rn(S.h1[2 * h], S.h1[2 * h + 1]);
+            }
+            tcgen05_fence_before();
+            publish_arrive(s, inl, ctrs + 0);
+            if (tid == 0 && s == 0) trace(p, t, 2);
+            etrace(p, t, s, 2);
+        };
+        // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 -------------------------------------------
+        auto stageB = [&](SetState<H>& S, const int s, const int t) {
+            SET_VIEW(s)
+            float pb[H][8], gh[H][8];
+            etrace(p, t, s, 3);
+            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 0], (uint32_t)t & 1u);
+            tcgen05_fence_after();
+            if (tid == 0 && s == 0) trace(p, t, 3);
+            etrace(p, t, s, 4);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                tmem_ld8(tacc + accB + h * NB_ + 16 * up, pb[h]);
+                if (t > 0) tmem_ld8(tacc + accC + h * NC_ + 8 * up, gh[h]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gh[h][i] = 0.f;
+                }
+            }
+            tmem_ld_wait();
+            if (tid == 0 && s == 0) trace(p, t, 28);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float* v2 = KC(h) + 6;
+                const float* bh2 = KC(h) + 16;
+                float2 cr = make_float2(0.f, 0.f);
+                float4 cz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) { cr = S.cr[h]; cz = S.cz[h]; }
+                const float c2r[2] = {cr.x, cr.y}, c2z[2] = {cz.x, cz.y}, c2n[2] = {cz.z, cz.w};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float r = sigmoid_fast(pb[h][0 + u] + fmaf(v2[0 + u], S.x, c2r[u]) + gh[h][0 + u]);
+                    const float z = sigmoid_fast(pb[h][2 + u] + fmaf(v2[2 + u], S.x, c2z[u]) + gh[h][2 + u]);
+                    const float n = tanh_fast(pb[h][4 + u] + fmaf(v2[4 + u], S.x, c2n[u]) + r * (gh[h][4 + u] + bh2[u]));
+                    S.h2[2 * h + u] = (1.0f - z) * n + z * S.h2[2 * h + u];
+                    S.p3[2 * h + u] = pb[h][6 + u];
+                }
+                if (live) *reinterpret_cast<__half2*>(p.H2 + grow * kRnn + J0_OF(h)) = __floats2half2_rn(S.h2[2 * h], S.h2[2 * h + 1]);
+            }
+            if (tid == 0 && s == 0) trace(p, t, 29);
+            tcgen05_fence_before();
+            publish_arrive(s, inl, ctrs + 1);
+            if (tid == 0 && s == 0) trace(p, t, 4);
+            etrace(p, t, s, 5);
+        };
+        // ---- C: [gh2' | W_fc1a h2] ; f1 ; publish ------------------------------------------------------------
+        auto stageC = [&](SetState<H>& S, const int s, const int t) {
+            SET_VIEW(s)
+            float pb[H][8];
+            etrace(p, t, s, 6);
+            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 1], (uint32_t)t & 1u);
+            tcgen05_fence_after();
+            if (tid == 0 && s == 0) trace(p, t, 5);
+            etrace(p, t, s, 7);
+#pragma unroll
+            for (int h = 0; h < H; ++h) tmem_ld8(tacc + accC + h * NC_ + 8 * up, pb[h]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float* v3 = KC(h) + 12;
+                float2 c3 = make_float2(0.f, 0.f);
+                if (live) c3 = make_float2(S.c34[h].x, S.c34[h].y);
+                const float f0 = fmaxf(S.p3[2 * h] + pb[h][6] + fmaf(v3[0], S.x, c3.x), 0.f);
+                const float f1 = fmaxf(S.p3[2 * h + 1] + pb[h][7] + fmaf(v3[1], S.x, c3.y), 0.f);
+                if (live) *reinterpret_cast<__half2*>(p.F1 + grow * kRnn + J0_OF(h)) = __floats2half2_rn(f0, f1);
+            }
+            tcgen05_fence_before();
+            publish_arrive(s, inl, ctrs + 2);
+            if (tid == 0 && s == 0) trace(p, t, 6);
+            etrace(p, t, s, 8);
+        };
+        // ---- D: fc2 ; publish ----------------------------------------------------------------------------------
+        auto stageD = [&](SetState<H>& S, const int s, const int t) {
+            SET_VIEW(s)
+            etrace(p, t, s, 9);
+            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 2], (uint32_t)t & 1u);
+            tcgen05_fence_after();
+            if (tid == 0 && s == 0) trace(p, t, 7);
+            etrace(p, t, s, 10);
+            float d[H][4];
+#pragma unroll
+            for (int h = 0; h < H; ++h) tmem_ld4(tacc + accD + h * ND_ + 2 * up, d[h]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float2 c4 = make_float2(0.f, 0.f);
+                if (live) c4 = make_float2(S.c34[h].z, S.c34[h].w);
+                if (live) *reinterpret_cast<__half2*>(p.F2 + grow * kRnn + J0_OF(h)) = __floats2half2_rn(fmaxf(d[h][0] + c4.x, 0.f), fmaxf(d[h][1] + c4.y, 0.f));
+            }
+            tcgen05_fence_before();
+            publish_arrive(s, inl, ctrs + 3);
+            if (tid == 0 && s == 0) trace(p, t, 8);
+            etrace(p, t, s, 11);
         };
 
         for (int k = 0; k < nslot_total; ++k) {
@@ -788,41 +803,37 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             for (int s = 0; s < NSETS; ++s) {
                 int t, stn;
                 if (!job_of(k, s, skew, p.S, t, stn)) continue;
-                if (sampler) {
-                    if (stn == 4) {
-                        if (mol) stageE(st[s], s, t);
-                        else if (s == (warp >> 2)) {          // RAW sampler: warps 4s..4s+3 own fold set s (thread = fold)
-                            SET_VIEW(s)
-                            wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], (uint32_t)t & 1u);
-                            tcgen05_fence_after();
-                            raw_sampler_e(p, ctl, reinterpret_cast<const float*>(smem + kRawBias), tacc, qd, fold0, nrows, grow, row, t,
-                                          st[s].fold, st[s].utt, key);
-                            tcgen05_fence_before();
-                        }
-                    }
-                } else if (stn == 0) stageA(st[s], s, t);
+                if (stn == 0) stageA(st[s], s, t);
                 else if (stn == 1) stageB(st[s], s, t);
                 else if (stn == 2) stageC(st[s], s, t);
                 else if (stn == 3) stageD(st[s], s, t);
-                else if (!has_samplers) stageE(st[s], s, t);
+                else if (!PAIR && !has_samplers) {            // RAW without sampler CTAs: my classes of fc3, then the draw
+                    SET_VIEW(s)
+                    wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], (uint32_t)t & 1u);
+                    tcgen05_fence_after();
+                    raw_stage_e(p, ctl, tacc, cta, fold0, nrows, grow, t, key);
+                    tcgen05_fence_before();
+                }
             }
             if (blockIdx.x == 0 && tid == 0 && (k % 500) == 0 && p.progress) {
                 *reinterpret_cast<volatile int*>(p.progress) = k / 5;
                 __threadfence_system();
             }
         }
+#undef KC
+#undef CS_OF
+#undef J0_OF
+        }
 #undef SET_VIEW
-#undef v1
-#undef v2
-#undef v3
-#undef bh1
-#undef bh2
     }
+#undef VG_OF
     // ---- teardown ---------------------------------------------------------------------------------------------
     if (aborted(p, ctl)) __nanosleep(200000);      // let any TMA still in flight land before the CTA goes away
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 0 && !idle) tmem_dealloc(tmem, kTmemCols);
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 0 && !idle) {
+        if (pairu) tmem_dealloc_pair(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols);
+    }
 }
 
 cudaError_t set_tc_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc_deadline, &cycles, sizeof(cycles)); }
@@ -831,29 +842,48 @@ size_t loop_tc_raw_sampler_image_bytes() { return kRawBias; }
 int loop_tc_raw_sampler_ctas() { return kRawQ; }
 int loop_tc_sampler_ctas(int mode, int raw_samplers) { return mode == 1 ? kTcGroups : (raw_samplers ? kTcGroups * kRawQ : 0); }
 
-// grid: the unit-owning CTAs of both groups, plus (MOL) one sampler CTA per group; cooperative launch because all CTAs
-// spin on each other and must be co-resident
-template <int NSETS>
+// grid: the unit-owning CTAs of both groups, the sampler CTAs, the expander CTAs; cooperative launch because all CTAs spin
+// on each other and must be co-resident.  Pair mode: the same grid as 2-CTA clusters (unit CTAs 2i, 2i+1 form a pair).
+template <int NSETS, bool PAIR>
 static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cudaStream_t stream) {
-    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_tc_kernel<NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
+    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_tc_kernel<NSETS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
     if (err != cudaSuccess) return err;
     TcParams pp = p;
     void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
     const int grid = kTcGroups * kTcCtas + loop_tc_sampler_ctas(p.mode, p.raw_samplers) + (p.cs_done ? p.n_expanders : 0);
+    if (PAIR) {
+        if (grid & 1) return cudaErrorInvalidValue;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = kSmemBytes + 1024; cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative;
+        at[1].val.cooperative = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) ? 1 : 2;
+        return cudaLaunchKernelExC(&cfg, (const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, args);
+    }
     if (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) {
-        wrnn_loop_tc_kernel<NSETS><<<grid, NT, kSmemBytes + 1024, stream>>>(m[0], m[1], m[2], m[3], pp);
+        wrnn_loop_tc_kernel<NSETS, PAIR><<<grid, NT, kSmemBytes + 1024, stream>>>(m[0], m[1], m[2], m[3], pp);
         return cudaGetLastError();
     }
-    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel<NSETS>, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
+    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
 }
 
+// p.nsets = fold sets per group; p.pair: CTA pairs (nsets must be 2 or 4 then)
 cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps /* 4 x CUtensorMap */, cudaStream_t stream) {
     const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmaps);
+    if (p.pair) {
+        if (p.nsets == 2) return launch_loop_tc_n<1, true>(p, m, stream);
+        if (p.nsets == 4) return launch_loop_tc_n<2, true>(p, m, stream);
+        return cudaErrorInvalidValue;
+    }
     switch (p.nsets) {
-        case 1: return launch_loop_tc_n<1>(p, m, stream);
-        case 2: return launch_loop_tc_n<2>(p, m, stream);
-        case 3: return launch_loop_tc_n<3>(p, m, stream);
-        case 4: return launch_loop_tc_n<4>(p, m, stream);
+        case 1: return launch_loop_tc_n<1, false>(p, m, stream);
+        case 2: return launch_loop_tc_n<2, false>(p, m, stream);
+        case 3: return launch_loop_tc_n<3, false>(p, m, stream);
+        case 4: return launch_loop_tc_n<4, false>(p, m, stream);
     }
     return cudaErrorInvalidValue;
 }
