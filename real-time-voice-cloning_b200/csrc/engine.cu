@@ -945,9 +945,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             if (const char* ev = getenv("WRNN_TC_SETS")) nsets = std::max(nsets, std::min(kTcSets, atoi(ev)));
             // RAW with 512 classes: fc3 + the draw on 4 sampler CTAs per group (WRNN_TC_RAWSAMP=0: classes spread over the unit-owning CTAs)
             const bool raw_samplers = e->mode != WRNN_MODE_MOL && e->C == 512 && !(getenv("WRNN_TC_RAWSAMP") && atoi(getenv("WRNN_TC_RAWSAMP")) == 0);
-            // CTA pairs (tcgen05 cta_group::2) whenever fc3 has its own CTAs: an even number of sets per group, set 2s+r on the
-            // rank-r CTA of every pair (WRNN_TC_PAIR=0: one CTA per MMA)
-            const bool pair = (e->mode == WRNN_MODE_MOL || raw_samplers) && !(getenv("WRNN_TC_PAIR") && atoi(getenv("WRNN_TC_PAIR")) == 0);
+            // CTA pairs (tcgen05 cta_group::2), possible whenever fc3 has its own CTAs: an even number of sets per group, set 2s+r
+            // on the rank-r CTA of every pair
+            // (measured: pairs win once a group pipelines three or more sets, i.e. > 512 folds; below that the longer pair MMA
+            //  and the coupling of two CTAs cost ~1 us per stage; WRNN_TC_PAIR=1 / 0 forces the choice)
+            const char* pair_env = getenv("WRNN_TC_PAIR");
+            const bool pair = (e->mode == WRNN_MODE_MOL || raw_samplers) && (pair_env ? atoi(pair_env) != 0 : nsets >= 3);
             if (pair) nsets = nsets <= 2 ? 2 : 4;
             const int nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
             // The expansion is HBM-write-bound (~0.5 ms per GB; 17 GB for a 60 s utterance).  Kernels on different streams
@@ -999,8 +1002,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 if (cs_steps < nchunks * kExpandSteps) tp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
                 tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
                 tp.coef = e->dcoef;
-                tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers)));
-                if (pair && ((kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers) + tp.n_expanders) & 1)) --tp.n_expanders;   // 2-CTA clusters
+                tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers, tp.pair)));
+                if (pair && ((kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers, tp.pair) + tp.n_expanders) & 1)) --tp.n_expanders;   // 2-CTA clusters
                 if (tp.n_expanders <= 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
             }
             if (const char* ev = getenv("WRNN_TC_FLAGS")) tp.flags = atoi(ev);

@@ -316,7 +316,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const bool mol = p.mode == 1;
     const int nmain = kTcGroups * kTcCtas;
     const bool rawq = !mol && p.raw_samplers != 0;                        // RAW, 512 classes: kRawQ sampler CTAs per group
-    const int spg = mol ? 1 : (rawq ? kRawQ : 0);                         // sampler CTAs per group
+    const int spg = mol ? (PAIR ? 2 : 1) : (rawq ? kRawQ : 0);            // sampler CTAs per group (MOL pairs: one per rank)
     const bool has_samplers = spg != 0;
     const int sidx = (int)blockIdx.x - nmain;                             // blocks past the groups: samplers, then expanders
     const bool sampler = sidx >= 0;                                       // (fc3 + the draw)
@@ -327,17 +327,20 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const bool idle = expander;
     constexpr int H = PAIR ? 2 : 1;                                       // unit blocks per epilogue thread
     constexpr int GS = PAIR ? 2 * NSETS : NSETS;                          // fold sets per group
-    const bool pairu = PAIR && !sampler;                                  // this CTA is half of a CTA pair
-    const int rank = pairu ? (cta & 1) : 0;
-    const bool leader = rank == 0;                                        // issues the pair's MMAs, owns the `full` barriers
+    const bool pairu = PAIR && !sampler;                                  // unit-owning CTA, half of a CTA pair
+    const bool pairs = PAIR && rawq && sampler && !expander;              // RAW sampler CTA, half of a pair: 256 classes per pair, N = 256
+    const bool paired = pairu || pairs;
+    const bool ranked = PAIR && !expander;                                // works on the group's sets 2s + rank only (else: on all)
+    const int rank = pairu ? (cta & 1) : (ranked ? (sidx & 1) : 0);       // (MOL pairs: sampler CTA r of a group serves the rank-r sets)
+    const bool leader = !paired || rank == 0;                             // issues the pair's MMAs, owns the `full` barriers
     const int ctab = pairu ? (cta & ~1) : cta;                            // first unit block of my accumulator columns
-    const int nsets = sampler ? GS : NSETS;                               // sets this CTA works on
+    const int nsets = (sampler && !ranked) ? GS : NSETS;                  // sets this CTA works on
     const unsigned int arrivals = PAIR ? kTcCtas / 2 : kTcCtas;           // CTAs that publish a set's activations
     // TMEM columns of a unit-owning CTA, per set: [B | C | D | (E)]; a pair's accumulators are twice as wide
     constexpr uint32_t accB = 0, accC = PAIR ? 128 : 64, accD = PAIR ? 192 : 96, setColsU = PAIR ? 256 : 128;
-    const uint32_t set_cols = sampler ? 128u : setColsU;
+    const uint32_t set_cols = sampler ? (pairs ? 256u : 128u) : setColsU;
     static_assert(NSETS * (PAIR ? 256 : 128) <= kTmemCols && GS <= kTcSets, "TMEM columns");
-#define VG_OF(s) (g * GS + (pairu ? 2 * (s) + rank : (s)))
+#define VG_OF(s) (g * GS + (ranked ? 2 * (s) + rank : (s)))
     const int NE = mol ? 32 : ((rawq && sampler) ? kRawQCols : 16);
     const int ph0 = sampler ? 3 : 0, ph1 = (has_samplers && !sampler) ? 3 : 4;   // stages whose MMAs this CTA runs
     const int skew = (p.flags >> 4) & 7;                                  // stations set s runs behind set s-1 (0: all sets in phase)
@@ -356,7 +359,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         const uint4* src = reinterpret_cast<const uint4*>(rs ? p.wimg_s + (size_t)qd * kRawBias : p.wimg + (size_t)cta * kWBytes + w0);
         uint4* dst = reinterpret_cast<uint4*>(smem + w0);
         for (int i = tid; i < (w1 - w0) / 16; i += NT) dst[i] = src[i];
-        if (rs && tid < kRawQCols) reinterpret_cast<float*>(smem + kRawBias)[tid] = p.bfc3[qd * kRawQCols + tid];
+        if (rs && tid < 2 * kRawQCols)                   // fc3 bias of my quarter (pairs: of the pair's two quarters)
+            reinterpret_cast<float*>(smem + kRawBias)[tid] = pairs ? p.bfc3[(qd & ~1) * kRawQCols + tid] : (tid < kRawQCols ? p.bfc3[qd * kRawQCols + tid] : 0.f);
         fence_proxy_async_smem();
     }
     if (tid == 0) {
@@ -381,7 +385,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     if (expander && p.cs_done)                      // interpolation weights [200][kTaps]: broadcast reads from shared memory
         for (int i = tid; i < kHop * kTaps; i += NT) reinterpret_cast<float*>(smem)[i] = p.coef[i];
     if (warp == 0 && !idle) {
-        if (pairu) tmem_alloc_pair(&ctl->tmem, kTmemCols); else tmem_alloc(&ctl->tmem, kTmemCols);
+        if (paired) tmem_alloc_pair(&ctl->tmem, kTmemCols); else tmem_alloc(&ctl->tmem, kTmemCols);
     }
     tcgen05_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();        // (pair: the partner's barriers are initialised before any TMA completes on them)
@@ -459,7 +463,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                         if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
                         if (ph == 0 && s == 1) trace(p, t, 128 + kb);              // tile timeline of one job: slot free
                         if (go && !aborted(p, ctl)) {
-                            if (pairu) {
+                            if (paired) {
                                 if (leader) mbar_arrive_expect_tx(&ctl->full[slot], 2 * kTcKbPerOp * kb_bytes);
                                 tma_load_3d_pair(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
                             } else {
@@ -486,7 +490,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     if (!job_of(k, s, skew, p.S, t, stn)) continue;
                     const int ph = stn - 1;
                     if (ph < ph0 || ph >= ph1) continue;
-                    const uint32_t idesc = pairu ? umma_idesc_f16(256, 2 * (int)ncol[ph]) : umma_idesc_f16(128, (int)ncol[ph]);
+                    const uint32_t idesc = paired ? umma_idesc_f16(256, 2 * (int)ncol[ph]) : umma_idesc_f16(128, (int)ncol[ph]);
                     const uint32_t dcol = tmem + (uint32_t)s * set_cols + acc[ph];
                     for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
                         const uint32_t slot = q % nslots, round = q / nslots;
@@ -501,7 +505,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                             for (int kk = 0; kk < kTcKbPerOp; ++kk) {
                                 const uint64_t ad = umma_desc_sw128(smem_u32(smem + ring0 + slot * slot_bytes) + kk * kb_bytes);
                                 const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs[ph] + (kb + kk) * ncol[ph] * 128));
-                                if (PAIR && pairu) {
+                                if (PAIR && paired) {
                                     if (kb + kk == 0) umma_f16_pair<false>(dcol, ad, bd, idesc); else umma_f16_pair<true>(dcol, ad, bd, idesc);
                                     umma_f16_pair<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
                                     umma_f16_pair<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
@@ -514,10 +518,10 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                                 }
                             }
                         }
-                        if (PAIR && pairu) umma_commit_pair(&ctl->empty[slot]); else umma_commit(&ctl->empty[slot]);
+                        if (PAIR && paired) umma_commit_pair(&ctl->empty[slot]); else umma_commit(&ctl->empty[slot]);
                         if (ph == 0 && s == 1) trace(p, t, 144 + kb);              // MMAs + commit issued
                     }
-                    if (PAIR && pairu) umma_commit_pair(&ctl->accfull[s * 4 + ph]); else umma_commit(&ctl->accfull[s * 4 + ph]);
+                    if (PAIR && paired) umma_commit_pair(&ctl->accfull[s * 4 + ph]); else umma_commit(&ctl->accfull[s * 4 + ph]);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 3);          // all MMAs of the job issued
                 }
             }
@@ -560,6 +564,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             uint32_t sfold[GS], sutt[GS];
 #pragma unroll
             for (int s = 0; s < GS; ++s) {
+                sfold[s] = sutt[s] = 0u;
+                if (s >= nsets) continue;
                 SET_VIEW(s)
                 const FoldDesc fd = p.folds[live ? fold0 + row : 0];
                 sfold[s] = (uint32_t)fd.fold; sutt[s] = (uint32_t)fd.utt;
@@ -568,15 +574,18 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
 #pragma unroll
                 for (int s = 0; s < GS; ++s) {
                     int t, stn;
-                    if (!job_of(k, s, skew, p.S, t, stn) || stn != 4) continue;
+                    if (s >= nsets || !job_of(k, s, skew, p.S, t, stn) || stn != 4) continue;
                     SET_VIEW(s)
                     const uint32_t par = (uint32_t)t & 1u;
                     if (!mol) {
-                        if (s != (warp >> 2)) continue;           // RAW sampler: warps 4s..4s+3 own fold set s (thread = fold)
+                        // RAW sampler: a group of four warps (thread = fold) per (set, 128 classes): warps 4s..4s+3 own set s; on a
+                        // pair the accumulator is 256 classes wide and warp groups 2s, 2s+1 own its two halves (= quarters qd&~1, +1)
+                        const int wg = warp >> 2, ch = pairs ? (wg & 1) : 0;
+                        if (s != (pairs ? (wg >> 1) : wg)) continue;
                         wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
                         tcgen05_fence_after();
-                        raw_sampler_e(p, ctl, reinterpret_cast<const float*>(smem + kRawBias), tacc, qd, fold0, nrows, grow, row, t,
-                                      sfold[s], sutt[s], key);
+                        raw_sampler_e(p, ctl, reinterpret_cast<const float*>(smem + kRawBias) + ch * kRawQCols, tacc + ch * kRawQCols,
+                                      pairs ? (qd & ~1) + ch : qd, fold0, nrows, grow, row, t, sfold[s], sutt[s], key);
                         tcgen05_fence_before();
                         continue;
                     }
@@ -832,7 +841,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     tcgen05_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 0 && !idle) {
-        if (pairu) tmem_dealloc_pair(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols);
+        if (paired) tmem_dealloc_pair(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols);
     }
 }
 
@@ -840,7 +849,7 @@ cudaError_t set_tc_deadline(long long cycles) { return cudaMemcpyToSymbol(g_tc_d
 size_t loop_tc_weight_image_bytes() { return kWBytes; }
 size_t loop_tc_raw_sampler_image_bytes() { return kRawBias; }
 int loop_tc_raw_sampler_ctas() { return kRawQ; }
-int loop_tc_sampler_ctas(int mode, int raw_samplers) { return mode == 1 ? kTcGroups : (raw_samplers ? kTcGroups * kRawQ : 0); }
+int loop_tc_sampler_ctas(int mode, int raw_samplers, int pair) { return mode == 1 ? kTcGroups * (pair ? 2 : 1) : (raw_samplers ? kTcGroups * kRawQ : 0); }
 
 // grid: the unit-owning CTAs of both groups, the sampler CTAs, the expander CTAs; cooperative launch because all CTAs spin
 // on each other and must be co-resident.  Pair mode: the same grid as 2-CTA clusters (unit CTAs 2i, 2i+1 form a pair).
@@ -850,7 +859,7 @@ static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cud
     if (err != cudaSuccess) return err;
     TcParams pp = p;
     void* args[] = {(void*)&m[0], (void*)&m[1], (void*)&m[2], (void*)&m[3], &pp};
-    const int grid = kTcGroups * kTcCtas + loop_tc_sampler_ctas(p.mode, p.raw_samplers) + (p.cs_done ? p.n_expanders : 0);
+    const int grid = kTcGroups * kTcCtas + loop_tc_sampler_ctas(p.mode, p.raw_samplers, p.pair) + (p.cs_done ? p.n_expanders : 0);
     if (PAIR) {
         if (grid & 1) return cudaErrorInvalidValue;
         cudaLaunchConfig_t cfg = {};

@@ -115,6 +115,22 @@ def test_tc_loop_several_fold_sets_per_group(mode, seed):
     assert len({a["samples"][i, :48].tobytes() for i in range(a["samples"].shape[0])}) == a["samples"].shape[0]
 
 
+@pytest.mark.parametrize("mode,seed,T", [("RAW", 11, 100), ("MOL", 12, 100), ("MOL", 12, 1000)])
+def test_tc_loop_cta_pairs_match_single_ctas(monkeypatch, mode, seed, T):
+    """CTA pairs (tcgen05 cta_group::2; default above 512 folds) against one CTA per MMA, forced either way, on few folds
+    (two sets per group, mostly padding rows) and on three to four sets per group."""
+    from tests.util import norm_mel
+    model, _ = make_model(seed=seed, bits=9, mode=mode)
+    mel = norm_mel(T, 4)
+    monkeypatch.setenv("WRNN_TC_PAIR", "1")
+    a = model.generate_debug(mel, True, 300, 50, want_logits=True, seed=5, max_steps=48, precision=F16)
+    monkeypatch.setenv("WRNN_TC_PAIR", "0")
+    b = model.generate_debug(mel, True, 300, 50, forced=np.pad(a["samples"], ((0, 0), (0, 400 - 48))), want_logits=True, seed=5, max_steps=48,
+                             precision=F16)
+    assert _rel(a["logits"], b["logits"]) < 1e-5
+    assert float((a["samples"] == b["samples"]).mean()) >= 0.999
+
+
 def test_tensor_core_front_end_matches_reference():
     """cond_tc.cu (tcgen05, hi/lo fp16 operand pairs) against the reference's MelResNet output and the fp32 SIMT path."""
     from tests.util import golden, norm_mel
