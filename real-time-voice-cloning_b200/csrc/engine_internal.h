@@ -60,7 +60,10 @@ constexpr int kTcCtas = 64;       // CTAs per group
 constexpr int kTcUnits = 8;       // hidden units per CTA
 constexpr int kTcSets = 4;        // fold sets (<= 128 folds each) a group pipelines through its CTAs
 constexpr int kTcMaxFolds = kTcGroups * kTcSets * 128;
-constexpr int kExpandSteps = 16;   // steps per block of expand_cond = granularity at which the loop may follow the expansion
+#ifndef WRNN_EXPAND_STEPS
+#define WRNN_EXPAND_STEPS 32
+#endif
+constexpr int kExpandSteps = WRNN_EXPAND_STEPS;   // steps per block of expand_cond = granularity at which the loop may follow the expansion
 constexpr int kTcKbPerOp = 2;      // k-blocks (64 columns each) one TMA operation of the loop brings in
 
 struct TcParams {

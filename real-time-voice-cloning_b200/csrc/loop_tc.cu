@@ -424,6 +424,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     asm volatile("bar.sync 8, %0;" ::"n"(NEPI * 32) : "memory");
                 }
                 const FoldDesc fd = p.folds[b];
+                // (tried: prefetch.global.L2 of the next item's table rows -- no gain; 32-step chunks instead of 16: 5 % per step)
                 expand_cond_item_regs(p.TA1, p.TA2, p.TQ1, p.TQ2, coef_s, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.cs_steps, p.Mg,
                                       p.CSw, tid);
                 if (seq >= 2) {
@@ -871,7 +872,13 @@ static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cud
         at[1].val.cooperative = 1;
         cfg.attrs = at;
         cfg.numAttrs = (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) ? 1 : 2;
-        return cudaLaunchKernelExC(&cfg, (const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, args);
+        err = cudaLaunchKernelExC(&cfg, (const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, args);
+        if (err != cudaSuccess && cfg.numAttrs == 2) {      // (a profiler may refuse cooperative cluster launches: the grid fits the
+            cudaGetLastError();                             //  GPU one CTA per SM, so a plain cluster launch is co-resident as well)
+            cfg.numAttrs = 1;
+            err = cudaLaunchKernelExC(&cfg, (const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, args);
+        }
+        return err;
     }
     if (getenv("WRNN_TC_COOP") && atoi(getenv("WRNN_TC_COOP")) == 0) {
         wrnn_loop_tc_kernel<NSETS, PAIR><<<grid, NT, kSmemBytes + 1024, stream>>>(m[0], m[1], m[2], m[3], pp);
