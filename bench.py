@@ -164,7 +164,7 @@ def reference_arm(args, wl):
         "cpu_baseline": dict(vals[-1], value=value),
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(wl):
@@ -174,6 +174,25 @@ def workload_config(wl):
         "256 utterances of 5-20 s" if wl in MULTI else "%d s" % seconds,
         ("batched target=%d overlap=%d" % (target, overlap)) if batched else "unbatched (single fold)"),
         "weights": "random-init rnn_dims=512 fc_dims=512 hop=200", "cache": "L2 flushed (256 MiB write) between timed steps"}
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout: native libraries (e.g. NCCL's version banner) write to fd 1 too, so the
+    run happens with fd 1 pointing at stderr and the line goes to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -188,6 +207,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _guard_stdout()
     wl = args.workload
     if args.precision is None:      # defaults: tensor-core loop; pruned model -> block-sparse cluster loop; single fold -> fp32 loop
         args.precision = "sparse" if wl in PRUNED else ("f32" if not WORKLOADS[wl][3] else "f16")
@@ -348,7 +368,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, sd, mode, mels_raw[0] / np.float32(4.0), batched, target, overlap, args.cpu_seconds)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

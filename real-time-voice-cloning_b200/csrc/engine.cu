@@ -950,7 +950,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             // (measured: pairs win once a group pipelines three or more sets, i.e. > 512 folds; below that the longer pair MMA
             //  and the coupling of two CTAs cost ~1 us per stage; WRNN_TC_PAIR=1 / 0 forces the choice)
             const char* pair_env = getenv("WRNN_TC_PAIR");
-            const bool pair = (e->mode == WRNN_MODE_MOL || raw_samplers) && (pair_env ? atoi(pair_env) != 0 : nsets >= 3);
+            bool pair = (e->mode == WRNN_MODE_MOL || raw_samplers) && (pair_env ? atoi(pair_env) != 0 : nsets >= 3);
+            if (pair) {     // every CTA spins on the others: all 2-CTA clusters must fit the device at once (else: single CTAs)
+                int grid = kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, raw_samplers ? 1 : 0, 1);
+                grid += std::max(0, (e->n_sms - grid) & ~1);
+                if (!loop_tc_pair_fits(nsets, std::min(grid, e->n_sms & ~1))) pair = false;
+            }
             if (pair) nsets = nsets <= 2 ? 2 : 4;
             const int nvg = kTcGroups * nsets, Mg = (B + nvg - 1) / nvg;
             // The expansion is HBM-write-bound (~0.5 ms per GB; 17 GB for a 60 s utterance).  Kernels on different streams

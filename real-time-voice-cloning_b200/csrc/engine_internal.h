@@ -103,7 +103,8 @@ struct TcParams {
 size_t loop_tc_weight_image_bytes();
 size_t loop_tc_raw_sampler_image_bytes();
 int loop_tc_raw_sampler_ctas();
-int loop_tc_sampler_ctas(int mode, int raw_samplers, int pair);   // CTAs past the unit-owning groups that run fc3 + the draw
+int loop_tc_sampler_ctas(int mode, int raw_samplers, int pair);
+bool loop_tc_pair_fits(int nsets, int grid);             // the pair kernel's 2-CTA clusters can all be co-resident on this device   // CTAs past the unit-owning groups that run fc3 + the draw
 cudaError_t set_tc_deadline(long long cycles);
 cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t stream);
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,

@@ -887,6 +887,25 @@ static cudaError_t launch_loop_tc_n(const TcParams& p, const CUtensorMap* m, cud
     return cudaLaunchCooperativeKernel((const void*)wrnn_loop_tc_kernel<NSETS, PAIR>, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
 }
 
+// can `grid` CTAs of the pair kernel be co-resident as 2-CTA clusters on this device? (every TPC must be whole and free)
+template <int NSETS>
+static bool pair_fits_n(int grid) {
+    if (cudaFuncSetAttribute(wrnn_loop_tc_kernel<NSETS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = kSmemBytes + 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wrnn_loop_tc_kernel<NSETS, true>, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return 2 * n >= grid;
+}
+bool loop_tc_pair_fits(int nsets, int grid) { return (grid & 1) == 0 && (nsets <= 2 ? pair_fits_n<1>(grid) : pair_fits_n<2>(grid)); }
+
 // p.nsets = fold sets per group; p.pair: CTA pairs (nsets must be 2 or 4 then)
 cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps /* 4 x CUtensorMap */, cudaStream_t stream) {
     const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmaps);
