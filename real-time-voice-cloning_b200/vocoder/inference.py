@@ -1,6 +1,7 @@
 """Vocoder facade: drop-in for the reference's vocoder/inference.py (load_model :11-53, is_loaded :56-57,
 infer_waveform :59-95, set_seed :97-101) with the B200 engine behind it.  Same names, positional order,
-defaults, return dtype (np.float64, length (T-1)*hop) and exception types/messages."""
+defaults, return dtype (np.float64, length (T-1)*hop) and exception types/messages.  `voc_type='libwavernn'` loads the
+exported `.bin` (libwavernn_bin.py) onto the same engine."""
 import numpy as np
 
 from ..config.hparams import sp, wavernn_fatchord
@@ -35,7 +36,7 @@ def load_state(state_dict, model_type=base.MODEL_TYPE_FATCHORD, devices=None, ov
 
 def load_model(weights_fpath, voc_type=base.VOC_TYPE_PYTORCH, verbose=True, devices=None):
     """inference.py:11.  voc_type 'pytorch' and 'b200' both select this engine (it replaces the PyTorch
-    path); 'libwavernn' .bin files are SURVEY.md section 8(f) "next"."""
+    path); 'libwavernn' decodes the exported .bin (fatchord topology) onto the same engine."""
     global _model, _model_type
     if voc_type in (base.VOC_TYPE_PYTORCH, base.VOC_TYPE_B200):
         import torch  # checkpoint I/O only
@@ -53,8 +54,31 @@ def load_model(weights_fpath, voc_type=base.VOC_TYPE_PYTORCH, verbose=True, devi
             print("Loaded vocoder of model '%s' at path '%s'." % (_model_type, weights_fpath))
             print("Model has been trained to step %d." % (_model[0].get_step()))
     elif voc_type == base.VOC_TYPE_CPP:
-        raise NotImplementedError("libwavernn .bin checkpoints are not handled by the B200 engine yet; "
-                                  "load the .pt checkpoint instead")
+        # inference.py:41-50 hands the path to the C++ vocoder; here the exported (usually pruned) weights are decoded
+        # and run on the B200 engine -- pruned checkpoints take the block-sparse loop.  The .bin carries no hparams:
+        # mode / bits follow from fc3's row count (30 -> MOL, 2**bits -> RAW), everything else must match the fatchord
+        # hparams the engine is built for.  The reference hard-codes the runtimeracer topology on this path
+        # (inference.py:43, FIXME there); that topology is SURVEY.md section 8(f) "next".
+        import copy
+        from . import libwavernn_bin
+        try:
+            state, meta = libwavernn_bin.read_bin(weights_fpath)
+        except OSError:
+            raise RuntimeError("Cannot open file.")                       # WaveRNNVocoder.cpp:24-26
+        hp = copy.deepcopy(wavernn_fatchord)
+        if (meta["res_blocks"], tuple(meta["upsample_factors"]), meta["pad"]) != (hp.res_blocks, tuple(hp.upsample_factors), hp.pad):
+            raise NotImplementedError("libwavernn file was exported with other hparams than the fatchord vocoder "
+                                      "(res_blocks %d, upsample %s, pad %d)" % (meta["res_blocks"], meta["upsample_factors"], meta["pad"]))
+        C = meta["n_classes"]
+        if C == 30:
+            hp.mode = "MOL"
+        elif C >= 2 and (C & (C - 1)) == 0:
+            hp.mode, hp.bits = "RAW", C.bit_length() - 1
+        else:
+            raise NotImplementedError("libwavernn file has %d output classes: neither MOL (30) nor RAW (2**bits)" % C)
+        load_state(state, base.MODEL_TYPE_FATCHORD, devices=devices, override_hp_fatchord=hp)
+        if verbose:
+            print("Loaded vocoder of model '%s' at path '%s'." % (_model_type, weights_fpath))
     else:
         raise NotImplementedError("Invalid vocoder of type '%s' provided. Aborting..." % voc_type)
 
