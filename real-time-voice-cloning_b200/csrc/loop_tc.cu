@@ -594,51 +594,106 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     // threads of a fold split the Gumbel draws (thread `up` owns Philox block `up`, i.e. mixtures
                     // 4up..4up+3), meet through shared memory, and thread up==2 (which also holds the logistic uniform,
                     // block 2 word 2) finishes the draw.
-                    wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
-                    tcgen05_fence_after();
-                    if (tid == 0 && s == 0) trace(p, t, 9);
-                    float lg[32];
-                    tmem_ld8(tacc + 0, lg); tmem_ld8(tacc + 8, lg + 8);
-                    tmem_ld8(tacc + 16, lg + 16); tmem_ld8(tacc + 24, lg + 24);
-                    tmem_ld_wait();
-                    const float* sbias = reinterpret_cast<const float*>(smem + kBias);
-                    float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch + s * kMolScratchBytes);
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, sfold[s], sutt[s], (uint32_t)(up < 3 ? up : 2)), key);
-                    float best = -INFINITY;
-                    int kbest = 0;
+                    // The noise depends on (step, fold) only.  With ONE set per sampler the step is a pure latency chain and the noise
+                    // is drawn while the fc3 MMAs are still running (25.6 vs 26.1 us per step at 213 folds); with several sets per
+                    // sampler the same change measured 4 % slower (41.1 vs 39.3 us at 1024 folds), so those keep the plain order.
+                    if constexpr (GS == 1) {
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)t, sfold[s], sutt[s], (uint32_t)(up < 3 ? up : 2)), key);
+                        float gum[4];
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const int i = up * 4 + w;
-                        if (i < 10) {
-                            const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
-                            float li = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 10; ++q) if (q == i) li = lg[q] + sbias[q];
-                            const float sc = li - __logf(-__logf(um));
-                            if (sc > best) { best = sc; kbest = i; }
-                        }
-                    }
-                    scratch[row * 4 + up] = make_float2(best, __int_as_float(kbest));
-                    asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");
-                    if (up == 2 && live) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {          // candidates of up = 0, 1 come first (lower indices win ties)
-                            const float2 c = scratch[row * 4 + q];
-                            if (c.x >= best && !(c.x == best && __float_as_int(c.y) > kbest)) { best = c.x; kbest = __float_as_int(c.y); }
-                        }
-                        float mean = 0.f, lsc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 10; ++i)
-                            if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
-                        lsc = fmaxf(lsc, -32.23619130191664f);
+                        for (int w = 0; w < 4; ++w) gum[w] = -__logf(-__logf(1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f)));
                         const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
-                        float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
-                        xs = fminf(fmaxf(xs, -1.0f), 1.0f);
-                        p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
-                        const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
-                        ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
-                        if (p.logits_out)
-                            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
+                        const float lnoise = __logf(ul) - __logf(1.0f - ul);
+                        wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
+                        tcgen05_fence_after();
+                        if (tid == 0 && s == 0) trace(p, t, 9);
+                        float lg[32];
+                        tmem_ld8(tacc + 0, lg); tmem_ld8(tacc + 8, lg + 8);
+                        tmem_ld8(tacc + 16, lg + 16); tmem_ld8(tacc + 24, lg + 24);
+                        tmem_ld_wait();
+                        const float* sbias = reinterpret_cast<const float*>(smem + kBias);
+                        float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch + s * kMolScratchBytes);
+                        float best = -INFINITY;
+                        int kbest = 0;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const int i = up * 4 + w;
+                            if (i < 10) {
+                                float li = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 10; ++q) if (q == i) li = lg[q] + sbias[q];
+                                const float sc = li + gum[w];
+                                if (sc > best) { best = sc; kbest = i; }
+                            }
+                        }
+                        scratch[row * 4 + up] = make_float2(best, __int_as_float(kbest));
+                        asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");
+                        if (up == 2 && live) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {          // candidates of up = 0, 1 come first (lower indices win ties)
+                                const float2 c = scratch[row * 4 + q];
+                                if (c.x >= best && !(c.x == best && __float_as_int(c.y) > kbest)) { best = c.x; kbest = __float_as_int(c.y); }
+                            }
+                            float mean = 0.f, lsc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 10; ++i)
+                                if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
+                            lsc = fmaxf(lsc, -32.23619130191664f);
+                            float xs = mean + __expf(lsc) * lnoise;
+                            xs = fminf(fmaxf(xs, -1.0f), 1.0f);
+                            p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
+                            const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
+                            ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
+                            if (p.logits_out)
+                                for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
+                        }
+                    } else {
+                        wait_mbar(p, ctl, &ctl->accfull[s * 4 + 3], par);
+                        tcgen05_fence_after();
+                        if (tid == 0 && s == 0) trace(p, t, 9);
+                        float lg[32];
+                        tmem_ld8(tacc + 0, lg); tmem_ld8(tacc + 8, lg + 8);
+                        tmem_ld8(tacc + 16, lg + 16); tmem_ld8(tacc + 24, lg + 24);
+                        tmem_ld_wait();
+                        const float* sbias = reinterpret_cast<const float*>(smem + kBias);
+                        float2* scratch = reinterpret_cast<float2*>(smem + kMolScratch + s * kMolScratchBytes);
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)t, sfold[s], sutt[s], (uint32_t)(up < 3 ? up : 2)), key);
+                        float best = -INFINITY;
+                        int kbest = 0;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const int i = up * 4 + w;
+                            if (i < 10) {
+                                const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
+                                float li = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 10; ++q) if (q == i) li = lg[q] + sbias[q];
+                                const float sc = li - __logf(-__logf(um));
+                                if (sc > best) { best = sc; kbest = i; }
+                            }
+                        }
+                        scratch[row * 4 + up] = make_float2(best, __int_as_float(kbest));
+                        asm volatile("bar.sync 2, %0;" ::"n"(NEPI * 32) : "memory");
+                        if (up == 2 && live) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {          // candidates of up = 0, 1 come first (lower indices win ties)
+                                const float2 c = scratch[row * 4 + q];
+                                if (c.x >= best && !(c.x == best && __float_as_int(c.y) > kbest)) { best = c.x; kbest = __float_as_int(c.y); }
+                            }
+                            float mean = 0.f, lsc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 10; ++i)
+                                if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
+                            lsc = fmaxf(lsc, -32.23619130191664f);
+                            const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
+                            float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
+                            xs = fminf(fmaxf(xs, -1.0f), 1.0f);
+                            p.samples[(size_t)(fold0 + row) * p.S + t] = xs;
+                            const float fed = p.forced ? p.forced[(size_t)(fold0 + row) * p.S + t] : xs;
+                            ll_store(p.bX + grow, fed, (uint32_t)t + 1u);
+                            if (p.logits_out)
+                                for (int i = 0; i < 30; ++i) p.logits_out[((size_t)(fold0 + row) * p.S + t) * 30 + i] = lg[i] + sbias[i];
+                        }
                     }
                     tcgen05_fence_before();
                     if (tid == 0 && s == 0) trace(p, t, 10);
