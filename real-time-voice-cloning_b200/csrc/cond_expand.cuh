@@ -117,53 +117,32 @@ __device__ __forceinline__ void expand_cond_item_cached(const float4* __restrict
 }
 
 
-#ifndef WRNN_EXPAND_FFMA2
-#define WRNN_EXPAND_FFMA2 1
-#endif
-// {x, y} = fma.rn(w, {qx, qy}, {x, y}) as ONE packed instruction (sm_100 fma.rn.f32x2)
-__device__ __forceinline__ void ffma2(float& x, float& y, float w, float qx, float qy) {
-    unsigned long long acc, ww, qq;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(x), "f"(y));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(qq) : "f"(qx), "f"(qy));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(qq));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc));
-}
-
 // The same work item by 512 threads, thread = ONE hidden unit `j`: the 8 + 5 x 7 table values of the current frame stay in
 // registers (no shared-memory traffic in the step loop: ~2x fewer instructions per record than the cached variant), the
 // interpolation weights come from a copy of `coef` in shared memory (a broadcast read), and the two threads of a unit pair
 // swap four values by shuffle so that each stores 32 contiguous bytes of the pair's 64-byte record.  Same FMA order as
-// the variants above (zero taps are multiplied through instead of skipped: same values).
-// kBulk: the 512 threads stage the 16 KB a step produces (the records of all 256 unit pairs of one fold are contiguous)
-// in shared memory and ONE thread sends it with a bulk asynchronous copy (cp.async.bulk shared -> global).  Per-thread
-// 16-byte global stores sustain only ~27 GB/s per SM here (outstanding-store limit x L2 round trip), which made the
-// expanders the bound of the loop; `stage` = kExpandStageBufs buffers of 16 KB, `bar_id` = a named barrier for the 512
-// workers (one barrier per step: the store of step t - kExpandStageBufs + 1 is known complete before anyone refills it).
-constexpr int kExpandStageBufs = 8;
-template <bool kBulk>
+// the variants above: bit-identical records.
 __device__ __forceinline__ void expand_cond_item_regs(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
                                                       const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                       const float* __restrict__ coef_s, const FoldDesc& fd, int b, int t0, int t1, int cs_steps, int Mg,
-                                                      float4* __restrict__ CS, int j, float4* __restrict__ stage = nullptr, int bar_id = 0) {
+                                                      float4* __restrict__ CS, int j) {
     const int g = b / Mg, row = b - g * Mg;
     const bool odd = (j & 1) != 0;
     float ta[8], tq[kTaps][7];
 #pragma unroll
+    for (int i = 0; i < 8; ++i) ta[i] = 0.f;
+#pragma unroll
     for (int d = 0; d < kTaps; ++d)
 #pragma unroll
         for (int i = 0; i < 7; ++i) tq[d][i] = 0.f;
-    // everything that is the same for all threads of the item advances incrementally (the expanders are issue-bound: no
-    // division or modulo per step).  Items are aligned chunks of the ring, so (t % cs_steps) cannot wrap inside one.
-    int n = fd.n0 + t0;
-    bool valid = n < fd.N;
-    int q0 = valid ? n / kHop : 0, ph = valid ? n - q0 * kHop : 0;
-    float4* out = CS + ((((size_t)g * cs_steps + (t0 % cs_steps)) * Mg + row) * 256 + (j >> 1)) * 4 + (odd ? 2 : 0);
-    const size_t step_stride = (size_t)Mg * 256 * 4;
-    bool reload = true;
+    int key = -1;
     for (int t = t0; t < t1; ++t) {
-        if (reload) {
-            reload = false;
+        const int n = fd.n0 + t;
+        const bool valid = n < fd.N;
+        const int q0 = valid ? n / kHop : 0;
+        const int want = valid ? (fd.tq_row0 + q0) : -2 - fd.ta_row0;
+        if (want != key) {
+            key = want;
             const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
             const float4 x1 = __ldg(TA1 + ra), x2 = __ldg(TA2 + ra);
             ta[0] = x1.x; ta[1] = x1.y; ta[2] = x1.z; ta[3] = x1.w; ta[4] = x2.x; ta[5] = x2.y; ta[6] = x2.z; ta[7] = x2.w;
@@ -180,23 +159,13 @@ __device__ __forceinline__ void expand_cond_item_regs(const float4* __restrict__
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = ta[i];
         if (valid) {
-            const float* cf = coef_s + ph * kTaps;
+            const float* cf = coef_s + (n - q0 * kHop) * kTaps;
 #pragma unroll
             for (int d = 0; d < kTaps; ++d) {
                 const float w = cf[d];
-                // (no `if (w != 0)` here, unlike the variants above: a zero tap leaves the sums unchanged anyway, and five
-                //  load -> compare -> branch sequences per step are a latency chain four warps per scheduler cannot hide)
-                {
-#if WRNN_EXPAND_FFMA2
-                    // packed fp32 FMAs (two IEEE fma.rn per instruction: same bits as the scalar form); a[7] has no mel share
-                    ffma2(a[0], a[1], w, tq[d][0], tq[d][1]);
-                    ffma2(a[2], a[3], w, tq[d][2], tq[d][3]);
-                    ffma2(a[4], a[5], w, tq[d][4], tq[d][5]);
-                    a[6] = fmaf(w, tq[d][6], a[6]);
-#else
+                if (w != 0.f) {
 #pragma unroll
                     for (int i = 0; i < 7; ++i) a[i] = fmaf(w, tq[d][i], a[i]);
-#endif
                 }
             }
         }
@@ -207,34 +176,14 @@ __device__ __forceinline__ void expand_cond_item_regs(const float4* __restrict__
         const float r1 = __shfl_xor_sync(0xffffffffu, odd ? a[1] : a[6], 1);
         const float r2 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
         const float r3 = __shfl_xor_sync(0xffffffffu, odd ? a[4] : a[7], 1);
-        const float4 o0 = odd ? make_float4(r0, a[5], r1, a[6]) : make_float4(a[0], r0, a[1], r1);
-        const float4 o1 = odd ? make_float4(r2, a[3], r3, a[7]) : make_float4(a[2], r2, a[4], r3);
-        if (kBulk) {
-            float4* sb = stage + (size_t)((t - t0) % kExpandStageBufs) * 1024;
-            sb[j * 2] = o0;
-            sb[j * 2 + 1] = o1;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync %0, 512;" ::"r"(bar_id) : "memory");
-            if (j == 0) {
-                const uint32_t src = (uint32_t)__cvta_generic_to_shared(sb);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 16384;" ::"l"(out - (odd ? 2 : 0) - (size_t)(j >> 1) * 4), "r"(src) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kExpandStageBufs - 2) : "memory");
-            }
+        float4* out = CS + ((((size_t)g * cs_steps + (t % cs_steps)) * Mg + row) * 256 + (j >> 1)) * 4 + (odd ? 2 : 0);
+        if (!odd) {
+            __stcs(out + 0, make_float4(a[0], r0, a[1], r1));
+            __stcs(out + 1, make_float4(a[2], r2, a[4], r3));
         } else {
-            __stcs(out + 0, o0);
-            __stcs(out + 1, o1);
+            __stcs(out + 0, make_float4(r0, a[5], r1, a[6]));
+            __stcs(out + 1, make_float4(r2, a[3], r3, a[7]));
         }
-        out += step_stride;
-        ++n;
-        if (valid) {
-            if (++ph == kHop) { ph = 0; ++q0; reload = true; }
-            if (n >= fd.N) { valid = false; reload = true; }      // the rest of the fold is tail padding: bias-only row (Q9)
-        }
-    }
-    if (kBulk && j == 0) {         // the item's records are in global memory before the releaser publishes the chunk
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
     }
 }
 

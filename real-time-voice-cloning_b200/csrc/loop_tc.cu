@@ -425,11 +425,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                 }
                 const FoldDesc fd = p.folds[b];
                 // (tried: prefetch.global.L2 of the next item's table rows -- no gain; 32-step chunks instead of 16: 5 % per step)
-#ifndef WRNN_EXPAND_BULK
-#define WRNN_EXPAND_BULK 0
-#endif
-                expand_cond_item_regs<WRNN_EXPAND_BULK != 0>(p.TA1, p.TA2, p.TQ1, p.TQ2, coef_s, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps),
-                                                             p.cs_steps, p.Mg, p.CSw, tid, reinterpret_cast<float4*>(smem + 4096), 11);
+                expand_cond_item_regs(p.TA1, p.TA2, p.TQ1, p.TQ2, coef_s, fd, b, c * kExpandSteps, min(p.S, (c + 1) * kExpandSteps), p.cs_steps, p.Mg,
+                                      p.CSw, tid);
                 if (seq >= 2) {
                     if (lane == 0) {
                         long long t0 = 0;
