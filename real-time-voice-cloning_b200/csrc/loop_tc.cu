@@ -48,6 +48,7 @@ constexpr int kRing = kWBytes;                          // 4 x 16 KB
 constexpr int kBars = kRing + kSlots * kTileBytes;      // mbarriers + misc
 constexpr int kMolScratchBytes = 128 * 4 * 8;           // [128 rows][4] {score, index} for the cooperative MOL draw, per fold set
 constexpr int kMolScratch = 0;                           // sampler CTA only: the GRU weight area is unused there
+constexpr int kMolRing = kTcSets * kMolScratchBytes;     // MOL sampler CTA: 4 ring slots between the scratch and its fc3 rows at kRing
 constexpr int kBias = kBars + 256;                       // fc3 bias (MOL)
 constexpr int kConst = kBias + 128;                      // per-unit constants of the CTA's 8 units (72 floats)
 // tcgen05.mma always reads 128 rows (16 KB) from a slot base; with slots shorter than that the last slot reads up to
@@ -58,6 +59,7 @@ constexpr int kSmemBytes = (kConst + 512 > kRing + 73728) ? (kConst + 512) : (kR
 constexpr int kRawQ = 4, kRawQCols = 128, kRawBias = kRawQCols * 128 * kNKB;
 static_assert(kRawBias + kRawQCols * 4 <= kRing, "RAW sampler bias overlaps the ring");
 static_assert(kTcSets <= NEPI / 4, "RAW sampler: one group of four epilogue warps per fold set");
+static_assert(kMolRing % 1024 == 0 && kMolRing + 4 * kTcKbPerOp * kTileBytes <= kRing && kRing + 32 * 128 * kNKB <= kBars, "MOL sampler layout");
 // TMEM columns
 constexpr int kAccB = 0, kAccC = 64, kAccD = 96, kAccE = 112, kSetCols = 128, kTmemCols = 512;   // (sampler CTA: fc3 accumulator at column 0 of the set's block)   // per fold set
 
@@ -346,7 +348,11 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     const int skew = (p.flags >> 4) & 7;                                  // stations set s runs behind set s-1 (0: all sets in phase)
     const int nslot_total = 5 * p.S + skew * (nsets - 1);                  // slots of the schedule (job_of)
     const bool deep = has_samplers && !sampler && !(p.flags & 2);
-    const uint32_t ring0 = deep ? kWE : kRing, nslots = deep ? 3u : 2u;       // ring of 32 KB slots (two k-blocks each)
+    // ring of 32 KB slots (two k-blocks each): 3 where the fc3 rows are not resident; the MOL sampler CTA holds only 32 KB of
+    // weights (kept at kRing) and its draw scratch (16 KB at 0), so its ring is the 4 slots in between: all four operations
+    // of a job are in flight at once (the sampler's stage is on every step's chain)
+    const bool molsamp = mol && sampler;
+    const uint32_t ring0 = molsamp ? (uint32_t)kMolRing : (deep ? kWE : kRing), nslots = molsamp ? 4u : (deep ? 3u : 2u);
     constexpr uint32_t slot_bytes = kTcKbPerOp * kTileBytes;
     const uint32_t kb_bytes = (uint32_t)p.tile_bytes;                         // the second k-block of a slot starts here
     // (measured: packing shorter slots so that the 16 KB MMA read of one slot overlaps the TMA target of the next is
@@ -357,7 +363,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         const bool rs = rawq && sampler;                // RAW sampler: its quarter of fc3 (N = 128 tiles) at offset 0
         const int w0 = rs ? 0 : (sampler ? kWE : 0), w1 = rs ? kRawBias : ((has_samplers && !sampler) ? kWE : kWBytes);
         const uint4* src = reinterpret_cast<const uint4*>(rs ? p.wimg_s + (size_t)qd * kRawBias : p.wimg + (size_t)cta * kWBytes + w0);
-        uint4* dst = reinterpret_cast<uint4*>(smem + w0);
+        uint4* dst = reinterpret_cast<uint4*>(smem + (molsamp ? kRing : w0));
         for (int i = tid; i < (w1 - w0) / 16; i += NT) dst[i] = src[i];
         if (rs && tid < 2 * kRawQCols)                   // fc3 bias of my quarter (pairs: of the pair's two quarters)
             reinterpret_cast<float*>(smem + kRawBias)[tid] = pairs ? p.bfc3[(qd & ~1) * kRawQCols + tid] : (tid < kRawQCols ? p.bfc3[qd * kRawQCols + tid] : 0.f);
@@ -481,7 +487,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     } else if (warp == NEPI + 1) {
         // =================================== MMA issuer =====================================================
         if (lane == 0 && leader) {
-            const uint32_t wofs[4] = {kWB, kWC, kWD, (rawq && sampler) ? 0u : (uint32_t)kWE};
+            const uint32_t wofs[4] = {kWB, kWC, kWD, (rawq && sampler) ? 0u : (molsamp ? (uint32_t)kRing : (uint32_t)kWE)};
             const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
             const uint32_t acc[4] = {accB, accC, accD, sampler ? 0u : (uint32_t)kAccE};
             uint32_t q = 0;
