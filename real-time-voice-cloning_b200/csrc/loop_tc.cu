@@ -1,26 +1,25 @@
 // loop_tc.cu -- the autoregressive sample loop on the 5th-gen tensor cores (fp16 operands, fp32 accumulate,
-// fp32 recurrent state): the batched-fold path (BASELINE configs 1, 3, 5).
+// fp32 recurrent state): the batched-fold path (BASELINE configs 1, 3, 5).  DESIGN.md section 4.2 has the full account.
 //
-// Same five-exchange step as loop_f32.cu, restructured for tcgen05:
-//  * 2 groups x 64 CTAs (one CTA per SM).  A group owns one or two SETS of up to 128 folds (MMA M = 128: one fold
-//    per TMEM lane); each of its CTAs owns 8 hidden units of every layer.  With two sets the CTA is software-pipelined:
-//    a stage of set 0 is followed by the same stage of set 1, so while one set's activations travel through L2 and
-//    its MMAs run, the epilogue warps do the other set's math (the resident weights serve 256 folds per group).  Its weight rows -- [W_ih2a|W_fc1a|W_hh1] (stage B),
-//    [W_hh2|W_fc1a] (C), fc2 (D), fc3 (E) -- stay in shared memory as K-major SWIZZLE_128B tiles (fp16,
-//    ~144 KB) for the whole sequence and are the B operand of tcgen05.mma (N = 64/32/16/16|32).
-//  * activations h1, h2, f1, f2 travel as fp16 rows [fold][512] through L2.  A stage = publish my 8 columns,
-//    arrive on the group's counter (release), the producer thread acquires the counter, then TMA-loads the
-//    group's [128 x 512] activation matrix in eight [128 x 64] swizzled tiles through a 4-slot mbarrier ring;
-//    one thread issues 32 tcgen05.mma per stage into TMEM; 16 epilogue warps (thread = fold x 2 units) read the
-//    accumulator with tcgen05.ld and do the GRU / ReLU / sampling math in fp32.
-//  * a TMA operation costs ~0.3-0.4 us whatever its size (measured: tiles of 2 KB and of 16 KB land equally far apart,
-//    and with four sets in flight the tile rate, not the tensor pipe, bounds the step), so one operation brings TWO
-//    k-blocks (a 3-D tensor map [k-block][row][64]: 32 KB) -- four operations per K=512 stage instead of eight.
-//    (Tried and dropped: multicast inside 4-CTA clusters -- L2 already merges up to ~4 readers of a line, no gain;
-//    8-CTA clusters are not co-resident 17 times on B200; replicated exchange matrices -- the extra stores cost more.)
-//  * MOL: fc3 (30 outputs) and the mixture draw run on a dedicated sampler CTA per group (blocks 128..), so no unit-
-//    owning CTA carries an extra stage; the 32 KB this frees in the other CTAs deepens their ring to 6 slots.
-//  * conditioning arrives pre-interpolated per sample (cond.cu: expand_cond), 64 B per thread per step.
+// Same five-exchange step as loop_f32.cu, restructured for tcgen05; one persistent launch with four kinds of CTA:
+//  * unit-owning CTAs, 2 groups x 64 (one CTA per SM).  A group owns one to four SETS of up to 128 folds (one fold per
+//    TMEM lane); each of its CTAs owns 8 hidden units of every layer.  The sets are software-pipelined through the CTA:
+//    while one set's activations travel through L2 and its MMAs run, the epilogue warps do another set's math.  The CTA's
+//    weight rows -- [W_ih2a|W_fc1a|W_hh1] (stage B), [W_hh2|W_fc1a] (C), fc2 (D) -- stay in shared memory as K-major
+//    SWIZZLE_128B tiles (fp16, 112 KB) for the whole sequence and are the B operand of tcgen05.mma (N = 64/32/16).
+//    Above 512 folds the CTAs work as PAIRS (2-CTA clusters, tcgen05 cta_group::2): one M=256 MMA covers a set of each
+//    CTA against both CTAs' weight rows, which halves the TMA operations, MMAs and L2->SM bytes per fold.
+//  * activations h1, h2, f1, f2 travel as fp16 rows [fold][512] through L2.  A stage = publish my columns, arrive on the
+//    set's counter (release, by the publisher warp), the producer thread acquires the counter, then TMA-loads the
+//    set's [128 x 512] activation matrix in four operations of two swizzled [128 x 64] k-blocks (a 3-D tensor map) through
+//    a 3-slot mbarrier ring; one thread issues 32 tcgen05.mma per stage into TMEM; 16 epilogue warps (thread = fold x unit
+//    pair) read the accumulator with tcgen05.ld and do the GRU / ReLU math in fp32.
+//  * sampler CTAs: fc3 and the draw never sit on a unit-owning CTA.  MOL: one CTA per group (per group and rank with
+//    pairs), N=32.  RAW with 512 classes: four CTAs per group with a quarter of fc3 each (as pairs: N=256 per MMA), online
+//    softmax per TMEM lane, {max, sum} partials exchanged as tagged words, inverse-CDF scan in the owning quarter.
+//    (Other class counts: classes spread over the unit-owning CTAs, raw_stage_e.)
+//  * expander CTAs on the remaining SMs produce the per-sample conditioning records (cond_expand.cuh) a few 32-step
+//    chunks ahead of the loop, into a ring with produced / consumed counters.
 //  * "soft abort": a wait that passes its deadline raises a flag; from then on every wait returns at once, so
 //    all warps still walk the same barriers and the kernel ends cleanly (never a hung GPU).
 #include <cstdio>
