@@ -1032,8 +1032,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             for (int i = 0; i < 4; ++i) CU(make_tmap_f16_kblocks(tmaps[i], acts[i], (uint64_t)xrows, kRnn, box_rows, kTcKbPerOp));
             const bool want_trace = getenv("WRNN_TC_TRACE") != nullptr;
             if (want_trace) {
-                CU(e->bFloor.ensure(16 * 192 * sizeof(long long)));
-                CU(cudaMemsetAsync(e->bFloor.p, 0, 16 * 192 * sizeof(long long), st));
+                CU(e->bFloor.ensure((16 * 192 + 148 * 16) * sizeof(long long)));
+                CU(cudaMemsetAsync(e->bFloor.p, 0, (16 * 192 + 148 * 16) * sizeof(long long), st));
                 tp.trace = e->bFloor.as<long long>();
             }
             CU(launch_loop_tc(tp, tmaps, st));
@@ -1047,6 +1047,18 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                         fprintf(f, "\n");
                     }
                     fclose(f);
+                }
+                {   // cross-CTA stamps (globaltimer ns) of one step: one line per unit-owning CTA
+                    std::vector<long long> xs(148 * 16);
+                    CU(cudaMemcpyAsync(xs.data(), e->bFloor.as<long long>() + 16 * 192, xs.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    if (FILE* f = fopen((std::string(getenv("WRNN_TC_TRACE")) + ".skew").c_str(), "w")) {
+                        for (int i = 0; i < kTcGroups * kTcCtas; ++i) {
+                            for (int j = 0; j < 16; ++j) fprintf(f, "%lld ", xs[i * 16 + j]);
+                            fprintf(f, "\n");
+                        }
+                        fclose(f);
+                    }
                 }
                 if (FILE* f = fopen((std::string(getenv("WRNN_TC_TRACE")) + ".abs").c_str(), "w")) {   // step starts (absolute)
                     for (int i = 0; i < 16; ++i) fprintf(f, "%lld\n", tr[i * 192]);

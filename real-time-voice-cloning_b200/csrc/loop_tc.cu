@@ -49,10 +49,14 @@ constexpr int kMolScratchBytes = 128 * 4 * 8;           // [128 rows][4] {score,
 constexpr int kMolScratch = 0;                           // sampler CTA only: the GRU weight area is unused there
 constexpr int kMolRing = kTcSets * kMolScratchBytes;     // MOL sampler CTA: 4 ring slots between the scratch and its fc3 rows at kRing
 constexpr int kBias = kBars + 256;                       // fc3 bias (MOL)
-constexpr int kConst = kBias + 128;                      // per-unit constants of the CTA's 8 units (72 floats)
+constexpr int kConst = kBias + 128;                      // per-unit constants of the CTA's 8 (pairs: 16) units (72 floats each)
+constexpr int kXBuf = kConst + 1024;                     // previous samples of the CTA's sets, [kTcSets][128] floats
+#ifndef WRNN_X_GATHER
+#define WRNN_X_GATHER 0     // 1: one warp polls a set's sample words for the CTA (halves the cross-CTA skew of stage A, tools/tc_skew.py,
+#endif                      //    but the step is not shorter: 40.0 vs 39.3 us at 1024 folds, 26.0 vs 25.7 us at 213)
 // tcgen05.mma always reads 128 rows (16 KB) from a slot base; with slots shorter than that the last slot reads up to
 // 8 KB past the ring (into the control words: harmless garbage rows), so the allocation must cover ring + 72 KB
-constexpr int kSmemBytes = (kConst + 512 > kRing + 73728) ? (kConst + 512) : (kRing + 73728);
+constexpr int kSmemBytes = (kXBuf + kTcSets * 512 > kRing + 73728) ? (kXBuf + kTcSets * 512) : (kRing + 73728);
 // RAW with 512 classes: fc3 + the draw run on kRawQ dedicated sampler CTAs per group, 128 classes (one N=128 MMA tile,
 // 128 KB of resident fc3 rows at offset 0) each; their fc3 bias slice sits in the gap below the ring
 constexpr int kRawQ = 4, kRawQCols = 128, kRawBias = kRawQCols * 128 * kNKB;
@@ -126,6 +130,17 @@ constexpr int kTraceStep0 = 64, kTraceSteps = 16, kTraceSlots = 192;
 __device__ __forceinline__ void trace(const TcParams& p, int t, int slot) {
     if (p.trace && blockIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
         p.trace[(t - kTraceStep0) * kTraceSlots + slot] = clock64();
+}
+
+// cross-CTA skew: every unit-owning CTA stamps %globaltimer (ns, common to all SMs) at a few events of step kTraceStep0 + 8
+// into the area behind CTA 0's timeline: [CTA][16]: 4 s + {0 x arrived, 1 A done, 2 B accumulator ready, 3 D done}
+constexpr int kXSlots = 16;
+__device__ __forceinline__ void xtrace(const TcParams& p, int t, int s, int k) {
+    if (p.trace && threadIdx.x == 0 && t == kTraceStep0 + 8 && s < 4) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.trace[kTraceSteps * kTraceSlots + blockIdx.x * kXSlots + 4 * s + k] = (long long)ns;
+    }
 }
 
 // epilogue timeline of fold sets 0 and 1: slot 32 + 16 s + {0 A enter, 1 x, 2 A done, 3 B enter, 4 B acc, 5 B done, 6 C enter, ...}
@@ -741,9 +756,46 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             if (tid == 0) trace(p, t, s == 0 ? 0 : 31);
             etrace(p, t, s, 0);
             S.x = 0.f;
+#if WRNN_X_GATHER
+            // The previous sample of every fold comes back as a tagged word.  ONE warp polls the set's 128 words (lane = four
+            // rows, two 16-byte loads) and hands them to the other fifteen through shared memory and a named barrier: with all
+            // 512 threads of 64 CTAs spinning on the same eight L2 lines the last CTA saw x 3-7 us after the first
+            // (tools/tc_skew.py), and every stage B waits for the last CTA's stage A.
+            if (t > 0) {
+                float* xb = reinterpret_cast<float*>(smem + kXBuf) + s * 128;
+                if (warp == 0) {
+                    const unsigned long long* w = p.bX + (size_t)vg * 128 + 4 * lane;
+                    uint32_t pending = 0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (4 * lane + 2 * i < nrows) pending |= 1u << i;
+                    long long t0 = 0;
+                    int spins = 0;
+                    while (pending) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if ((pending >> i) & 1u) {
+                                unsigned long long a, b;
+                                ll_load2(w + 2 * i, a, b);
+                                const bool need_b = 4 * lane + 2 * i + 1 < nrows;
+                                if (ll_tag(a) == (uint32_t)t && (!need_b || ll_tag(b) == (uint32_t)t)) {
+                                    xb[4 * lane + 2 * i] = ll_val(a);
+                                    xb[4 * lane + 2 * i + 1] = need_b ? ll_val(b) : 0.f;
+                                    pending &= ~(1u << i);
+                                }
+                            }
+                        if (pending && ((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
+                    }
+                }
+                asm volatile("bar.sync 7, %0;" ::"n"(NEPI * 32) : "memory");
+                if (live) S.x = xb[row];
+            }
+#else
             if (t > 0 && live) wait_x(p, ctl, p.bX + grow, (uint32_t)t, S.x);
+#endif
             if (tid == 0 && s == 0) trace(p, t, 1);
             etrace(p, t, s, 1);
+            xtrace(p, t, s, 0);
             float gh[H][8];
             if (t > 0) {
 #pragma unroll
@@ -773,6 +825,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             publish_arrive(s, inl, ctrs + 0);
             if (tid == 0 && s == 0) trace(p, t, 2);
             etrace(p, t, s, 2);
+            xtrace(p, t, s, 1);
         };
         // ---- B: [W_ih2a h1 | W_fc1a h1 | gh1'] ; GRU2 ; publish h2 -------------------------------------------
         auto stageB = [&](SetState<H>& S, const int s, const int t) {
@@ -783,6 +836,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             tcgen05_fence_after();
             if (tid == 0 && s == 0) trace(p, t, 3);
             etrace(p, t, s, 4);
+            xtrace(p, t, s, 2);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 tmem_ld8(tacc + accB + h * NB_ + 16 * up, pb[h]);
@@ -866,6 +920,7 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
             publish_arrive(s, inl, ctrs + 3);
             if (tid == 0 && s == 0) trace(p, t, 8);
             etrace(p, t, s, 11);
+            xtrace(p, t, s, 3);
         };
 
         for (int k = 0; k < nslot_total; ++k) {
