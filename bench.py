@@ -209,8 +209,9 @@ def main():
     args = ap.parse_args()
     _guard_stdout()
     wl = args.workload
-    if args.precision is None:      # defaults: tensor-core loop; pruned model -> block-sparse cluster loop; single fold -> fp32 loop
-        args.precision = "sparse" if wl in PRUNED else ("f32" if not WORKLOADS[wl][3] else "f16")
+    if args.precision is None:      # defaults = what the facade's PREC_AUTO picks (fatchord_version.resolve_precision): pruned model ->
+        # block-sparse cluster loop; fewer than 24 folds in the call (cfg1: 19, cfg2: 1) -> fp32 loop; else the tensor-core loop
+        args.precision = "sparse" if wl in PRUNED else ("f32" if (not WORKLOADS[wl][3] or wl == "cfg1") else "f16")
     if args.impl == "reference":
         return reference_arm(args, wl)
 

@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("WRNN_B200_LIB") or os.path.join(HERE, "libwavernn_b20
 OK, ERR_INVALID, ERR_NOT_LOADED, ERR_CUDA, ERR_TIMEOUT, ERR_SHAPE, ERR_TOO_SHORT = 0, -1, -2, -3, -4, -5, -6
 MODE_RAW, MODE_MOL = 0, 1
 PREC_F32, PREC_F16, PREC_SPARSE_F32 = 0, 1, 2
+PREC_AUTO = -1        # host-side only: resolved per call by vocoder/models/fatchord_version.py:resolve_precision
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p)
 

@@ -4,6 +4,7 @@ defaults, return dtype (np.float64, length (T-1)*hop) and exception types/messag
 exported `.bin` (libwavernn_bin.py) onto the same engine."""
 import numpy as np
 
+from .. import _native
 from ..config.hparams import sp, wavernn_fatchord
 from .models import base
 
@@ -27,6 +28,7 @@ def load_state(state_dict, model_type=base.MODEL_TYPE_FATCHORD, devices=None, ov
         m, _ = base.init_voc_model(model_type, d, override_hp_fatchord=override_hp_fatchord)
         m.eval()
         m.load_state_dict(state_dict)
+        m.precision = _native.PREC_AUTO       # facade default: the fastest loop for the call (fatchord_version.resolve_precision)
         models.append(m)
     _model, _model_type = models, model_type
     if verbose:

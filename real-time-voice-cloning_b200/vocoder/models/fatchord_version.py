@@ -139,6 +139,17 @@ class WaveRNN(object):
     def launch_count(self):
         return int(self._lib.wrnn_launch_count(self._h))
 
+    def _count_folds(self, arrs, batched, target, overlap):
+        if not batched:
+            return len(arrs)
+        n = 0
+        for a in arrs:
+            try:
+                n += _native.fold_plan(a.shape[1] * self.hop_length, int(target), int(overlap))[0]
+            except Exception:
+                n += 1                            # (the engine reports the bad plan with the reference's message)
+        return n
+
     # ---- the hot path ---------------------------------------------------------------------------------------
     def _request(self, mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback, want_wav=True,
                  **extra):
@@ -167,7 +178,10 @@ class WaveRNN(object):
         rq.overlap = int(overlap) if overlap is not None else 0
         rq.mu_law = 1 if mu_law else 0
         rq.apply_preemphasis = 1 if apply_preemphasis else 0
-        rq.precision = int(extra.get("precision", self.precision))
+        prec = int(extra.get("precision", self.precision))
+        if prec == _native.PREC_AUTO:
+            prec = resolve_precision(self.n_classes, self.sparsity, self._count_folds(arrs, batched, target, overlap))
+        rq.precision = prec
         rq.seed = int(extra.get("seed", self.seed)) & 0xFFFFFFFFFFFFFFFF
         rq.utt_index0 = int(extra.get("utt_index0", 0))
         rq.fold_begin = int(extra.get("fold_begin", 0))
@@ -194,7 +208,8 @@ class WaveRNN(object):
         if rc != _native.OK:
             _raise(self._lib, self._h, rc)
         self.last_timings = dict(ms_h2d=rq.ms_h2d, ms_cond=rq.ms_cond, ms_loop=rq.ms_loop, ms_post=rq.ms_post,
-                                 ms_d2h=rq.ms_d2h, n_folds=rq.n_folds, n_steps=rq.n_steps, n_launches=rq.n_launches)
+                                 ms_d2h=rq.ms_d2h, n_folds=rq.n_folds, n_steps=rq.n_steps, n_launches=rq.n_launches,
+                                 precision=int(rq.precision))
 
     def generate(self, mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback=None):
         """fatchord_version.py:155: mels is (1, 80, T) float32 already divided by max_abs_value; returns
@@ -359,6 +374,23 @@ class WaveRNN(object):
         bar = '#' * done + '-' * (16 - done)
         print('\r| %s %d/%d | Batch Size: %d | Gen Rate: %.1fkHz | ' % (bar, i * b_size, seq_len * b_size, b_size,
                                                                        gen_rate), end='', flush=True)
+
+
+AUTO_F16_MIN_FOLDS = 24
+AUTO_SPARSE_MIN = 0.8
+
+
+def resolve_precision(n_classes, sparsity, n_folds):
+    """Which loop `PREC_AUTO` (the default of the `vocoder.inference` facade) runs, from what was measured on B200 (DESIGN.md
+    section 6): a pruned checkpoint -> the block-sparse cluster loop (62.9x vs 38.8x real-time on cfg4); a dense one with at
+    least AUTO_F16_MIN_FOLDS folds in the call -> the fp16 tensor-core loop (213 folds: 385x vs 52x for the fp32 loop); fewer
+    folds -> the fp32 loop, which is then the faster one AND bit-faithful (19 folds: 39.2x vs 36.2x; one fold: the only
+    loop built for it).  The tensor-core loop exists for 30 (MOL), 512 and 1024 classes."""
+    if sparsity >= AUTO_SPARSE_MIN:          # (the engine builds the cluster images from 0.5 up, but only ~0.8+ fits one cluster)
+        return _native.PREC_SPARSE_F32
+    if n_folds >= AUTO_F16_MIN_FOLDS and n_classes in (30, 512, 1024):
+        return _native.PREC_F16
+    return _native.PREC_F32
 
 
 def _now():

@@ -245,3 +245,26 @@ def test_progress_callback_contract(raw9):
                          progress_callback=lambda i, seq_len, b_size, rate: calls.append((i, seq_len, b_size, rate)))
     assert wav.shape == (29 * 200,)
     assert calls and calls[-1][0] == 1399 and calls[-1][1] == 1400 and calls[-1][2] == 5 and calls[-1][3] > 0
+
+
+def test_facade_default_precision_is_auto(mol):
+    """load_model / load_state leave the engine on PREC_AUTO: the tensor-core loop for calls with many folds, the fp32 loop for
+    few folds and for unbatched generation (fatchord_version.resolve_precision)."""
+    import copy
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    from rtvc_b200.config.hparams import wavernn_fatchord
+    from rtvc_b200.vocoder import inference
+    from tests.util import norm_mel
+    _, sd = mol
+    hp = copy.deepcopy(wavernn_fatchord)
+    hp.bits, hp.mode = 9, "MOL"
+    m = inference.load_state(sd, override_hp_fatchord=hp)
+    assert m.precision == _native.PREC_AUTO
+    w = inference.infer_waveform(norm_mel(960, 1) * 4.0)                   # 12 s, the facade's own fold plan (3000 / 1500): 42 folds
+    assert w.shape == ((960 - 1) * 200,) and np.isfinite(w).all()
+    assert m.last_timings["n_folds"] >= 24 and m.last_timings["precision"] == _native.PREC_F16
+    inference.infer_waveform(norm_mel(160, 1) * 4.0)                       # 2 s: 7 folds
+    assert m.last_timings["n_folds"] < 24 and m.last_timings["precision"] == _native.PREC_F32
+    inference.infer_waveform(norm_mel(40, 1) * 4.0, batched=False)
+    assert m.last_timings["precision"] == _native.PREC_F32

@@ -73,3 +73,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_auto_precision_rule():
+    """The facade's default (PREC_AUTO) picks the loop from the checkpoint and the number of folds in the call."""
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    from rtvc_b200.vocoder.models.fatchord_version import resolve_precision, AUTO_F16_MIN_FOLDS
+    assert resolve_precision(512, 0.0, 1) == _native.PREC_F32                      # unbatched: the fp32 loop
+    assert resolve_precision(512, 0.0, 19) == _native.PREC_F32                     # BASELINE config 1: fp32 is faster and exact
+    assert resolve_precision(512, 0.0, AUTO_F16_MIN_FOLDS) == _native.PREC_F16
+    assert resolve_precision(30, 0.0, 213) == _native.PREC_F16                     # infer_waveform(mel) on a 60 s utterance
+    assert resolve_precision(1024, 0.0, 1024) == _native.PREC_F16
+    assert resolve_precision(256, 0.0, 500) == _native.PREC_F32                    # 8-bit: no tensor-core loop
+    assert resolve_precision(512, 0.9, 500) == _native.PREC_SPARSE_F32            # pruned checkpoint (vocoder/pruner.py)
+    assert resolve_precision(512, 0.6, 500) == _native.PREC_F16
