@@ -88,3 +88,24 @@ def test_auto_precision_rule():
     assert resolve_precision(256, 0.0, 500) == _native.PREC_F32                    # 8-bit: no tensor-core loop
     assert resolve_precision(512, 0.9, 500) == _native.PREC_SPARSE_F32            # pruned checkpoint (vocoder/pruner.py)
     assert resolve_precision(512, 0.6, 500) == _native.PREC_F16
+
+
+def test_spectrogram_handoff_matches_the_callers_arithmetic():
+    """vocoder/handoff.py against a literal restatement of toolbox/toolbox.py:263-265, 309-314, 321."""
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200.vocoder import handoff
+    rng = np.random.default_rng(4)
+    specs = [rng.standard_normal((80, t)).astype(np.float32) for t in (37, 5, 112)]
+    spec, breaks = handoff.concat_specs(specs)
+    assert spec.shape == (80, 154) and breaks == [37, 5, 112]
+    wav = rng.standard_normal((154 - 1) * 200)                      # what infer_waveform returns for T = 154
+    got = handoff.add_breaks(wav, breaks)
+    b_ends = np.cumsum(np.array(breaks) * 200)
+    b_starts = np.concatenate(([0], b_ends[:-1]))
+    wavs = [wav[s:e] for s, e in zip(b_starts, b_ends)]
+    gaps = [np.zeros(int(0.15 * 16000))] * 3
+    want = np.concatenate([i for w, b in zip(wavs, gaps) for i in (w, b)])
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    assert got.shape == ((154 - 1) * 200 + 3 * 2400,)
+    n = handoff.peak_normalize(got)
+    assert np.array_equal(n, want / np.abs(want).max() * 0.97)
