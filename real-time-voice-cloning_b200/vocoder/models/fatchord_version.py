@@ -385,7 +385,8 @@ def resolve_precision(n_classes, sparsity, n_folds):
     section 6): a pruned checkpoint -> the block-sparse cluster loop (62.9x vs 38.8x real-time on cfg4); a dense one with at
     least AUTO_F16_MIN_FOLDS folds in the call -> the fp16 tensor-core loop (213 folds: 385x vs 52x for the fp32 loop); fewer
     folds -> the fp32 loop, which is then the faster one AND bit-faithful (19 folds: 39.2x vs 36.2x; one fold: the only
-    loop built for it).  The tensor-core loop exists for 30 (MOL), 512 and 1024 classes."""
+    loop built for it).  Measured crossover (tools/auto_crossover.py, us per step fp32 / fp16): 14 folds 21.2 / 28.7, 19 folds
+    26.3 / 29.2, 23 folds 27.7 / 29.0, 28 folds 30.6 / 29.0, 37 folds 42.7 / 29.8.  The tensor-core loop exists for 30 (MOL), 512 and 1024 classes."""
     if sparsity >= AUTO_SPARSE_MIN:          # (the engine builds the cluster images from 0.5 up, but only ~0.8+ fits one cluster)
         return _native.PREC_SPARSE_F32
     if n_folds >= AUTO_F16_MIN_FOLDS and n_classes in (30, 512, 1024):
