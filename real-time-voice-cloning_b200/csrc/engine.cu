@@ -1008,6 +1008,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 tp.TA1 = e->bTA1.as<float4>(); tp.TA2 = e->bTA2.as<float4>(); tp.TQ1 = e->bTQ1.as<float4>(); tp.TQ2 = e->bTQ2.as<float4>();
                 tp.coef = e->dcoef;
                 tp.n_expanders = std::max(0, e->n_sms - (kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers, tp.pair)));
+                if (const char* ev = getenv("WRNN_TC_EXPANDERS")) tp.n_expanders = std::max(1, std::min(tp.n_expanders, atoi(ev)));   // (diagnosis: fewer expander CTAs)
                 if (pair && ((kTcGroups * kTcCtas + loop_tc_sampler_ctas(e->mode, tp.raw_samplers, tp.pair) + tp.n_expanders) & 1)) --tp.n_expanders;   // 2-CTA clusters
                 if (tp.n_expanders <= 0) return fail(e, WRNN_ERR_INVALID, "no SM left for the conditioning expanders (WRNN_TC_OVERLAP=0 expands first)");
             }
