@@ -128,7 +128,7 @@ __device__ __forceinline__ bool wait_x(const TcParams& p, Ctl* c, const unsigned
 // optional timeline of one CTA (group 0, CTA 0), steps [kTraceStep0, kTraceStep0+kTraceSteps): SM clocks
 constexpr int kTraceStep0 = 64, kTraceSteps = 16, kTraceSlots = 192;
 __device__ __forceinline__ void trace(const TcParams& p, int t, int slot) {
-    if (p.trace && blockIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
         p.trace[(t - kTraceStep0) * kTraceSlots + slot] = clock64();
 }
 
@@ -463,9 +463,10 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
     if (warp == NEPI) {
         // =================================== TMA producer ===================================================
         // (pair: both CTAs load their own set's rows; the bytes of both complete on the even CTA's `full` barrier)
-        if (lane == 0) {
+        // The whole warp walks the schedule and polls; one ELECTED lane issues (tc_common.cuh: elect_one).
+        {
             const CUtensorMap* maps[4] = {&tmH1, &tmH2, &tmF1, &tmF2};
-            for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
+            if (lane == 0) for (int i = 0; i < 4; ++i) tma_prefetch_desc(maps[i]);
             uint32_t q = 0;
             for (int k = 0; k < nslot_total; ++k) {
                 for (int s = 0; s < nsets; ++s) {
@@ -474,24 +475,27 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     const int ph = stn - 1;                       // stations B..E consume the exchange H1, H2, F1, F2
                     if (ph < ph0 || ph >= ph1) continue;
                     const int vg = VG_OF(s);
-                    const bool ok = wait_counter(p, ctl, p.counters + vg * 4 + ph, arrivals * (unsigned int)(t + 1));
+                    const bool ok = __all_sync(0xffffffffu, wait_counter(p, ctl, p.counters + vg * 4 + ph, arrivals * (unsigned int)(t + 1)));
                     fence_proxy_async();
                     if (s == 0) trace(p, t, 12 + ph);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 0);          // queue timeline: counter seen
+                    const CUtensorMap* map = ph == 0 ? &tmH1 : (ph == 1 ? &tmH2 : (ph == 2 ? &tmF1 : &tmF2));
                     for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
                         const uint32_t slot = q % nslots, round = q / nslots;
                         bool go = ok;
-                        if (round > 0) go = wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1) && go;
+                        if (round > 0) go = __all_sync(0xffffffffu, wait_mbar(p, ctl, &ctl->empty[slot], (round - 1) & 1)) && go;
                         if (ph == 0 && s == 1) trace(p, t, 128 + kb);              // tile timeline of one job: slot free
-                        if (go && !aborted(p, ctl)) {
+                        go = go && !aborted(p, ctl);
+                        if (__all_sync(0xffffffffu, go) && elect_one()) {
                             if (paired) {
                                 if (leader) mbar_arrive_expect_tx(&ctl->full[slot], 2 * kTcKbPerOp * kb_bytes);
-                                tma_load_3d_pair(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
+                                tma_load_3d_pair(smem + ring0 + slot * slot_bytes, map, &ctl->full[slot], 0, vg * 128, kb);
                             } else {
                                 mbar_arrive_expect_tx(&ctl->full[slot], kTcKbPerOp * kb_bytes);
-                                tma_load_3d(smem + ring0 + slot * slot_bytes, maps[ph], &ctl->full[slot], 0, vg * 128, kb);
+                                tma_load_3d(smem + ring0 + slot * slot_bytes, map, &ctl->full[slot], 0, vg * 128, kb);
                             }
                         }
+                        __syncwarp();
                     }
                     if (s == 0) trace(p, t, 16 + ph);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 1);          // last tile issued
@@ -500,10 +504,8 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
         }
     } else if (warp == NEPI + 1) {
         // =================================== MMA issuer =====================================================
-        if (lane == 0 && leader) {
-            const uint32_t wofs[4] = {kWB, kWC, kWD, (rawq && sampler) ? 0u : (molsamp ? (uint32_t)kRing : (uint32_t)kWE)};
-            const uint32_t ncol[4] = {NB_, NC_, ND_, (uint32_t)NE};
-            const uint32_t acc[4] = {accB, accC, accD, sampler ? 0u : (uint32_t)kAccE};
+        // whole warp in the loop, one elected lane issues: no uniformity waterfall around the UTCHMMAs (tc_common.cuh: elect_one)
+        if (leader) {
             uint32_t q = 0;
             for (int k = 0; k < nslot_total; ++k) {
                 for (int s = 0; s < nsets; ++s) {
@@ -511,38 +513,47 @@ wrnn_loop_tc_kernel(const __grid_constant__ CUtensorMap tmH1, const __grid_const
                     if (!job_of(k, s, skew, p.S, t, stn)) continue;
                     const int ph = stn - 1;
                     if (ph < ph0 || ph >= ph1) continue;
-                    const uint32_t idesc = paired ? umma_idesc_f16(256, 2 * (int)ncol[ph]) : umma_idesc_f16(128, (int)ncol[ph]);
-                    const uint32_t dcol = tmem + (uint32_t)s * set_cols + acc[ph];
+                    const uint32_t wofs_ph = ph == 0 ? (uint32_t)kWB : (ph == 1 ? (uint32_t)kWC : (ph == 2 ? (uint32_t)kWD
+                                             : ((rawq && sampler) ? 0u : (molsamp ? (uint32_t)kRing : (uint32_t)kWE))));
+                    const uint32_t ncol_ph = ph == 0 ? (uint32_t)NB_ : (ph == 1 ? (uint32_t)NC_ : (ph == 2 ? (uint32_t)ND_ : (uint32_t)NE));
+                    const uint32_t acc_ph = ph == 0 ? accB : (ph == 1 ? accC : (ph == 2 ? accD : (sampler ? 0u : (uint32_t)kAccE)));
+                    const uint32_t idesc = paired ? umma_idesc_f16(256, 2 * (int)ncol_ph) : umma_idesc_f16(128, (int)ncol_ph);
+                    const uint32_t dcol = tmem + (uint32_t)s * set_cols + acc_ph;
                     for (int kb = 0; kb < kNKB; kb += kTcKbPerOp, ++q) {
                         const uint32_t slot = q % nslots, round = q / nslots;
                         if (s == 0 && ph == 0 && kb < 4) trace(p, t, 24 + kb);
-                        const bool ok = wait_mbar(p, ctl, &ctl->full[slot], round & 1);
+                        const bool ok = __all_sync(0xffffffffu, wait_mbar(p, ctl, &ctl->full[slot], round & 1));
                         tcgen05_fence_after();
                         if (s == 0 && ph == 0 && kb < 4) trace(p, t, 20 + kb);
                         if (kb == 0) trace(p, t, 64 + (ph * 4 + s) * 4 + 2);     // first tile landed
                         if (ph == 0 && s == 1) trace(p, t, 136 + kb);              // tile landed (MMA thread saw it)
-                        if (ok) {
+                        if (elect_one()) {
+                            if (ok) {
 #pragma unroll
-                            for (int kk = 0; kk < kTcKbPerOp; ++kk) {
-                                const uint64_t ad = umma_desc_sw128(smem_u32(smem + ring0 + slot * slot_bytes) + kk * kb_bytes);
-                                const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs[ph] + (kb + kk) * ncol[ph] * 128));
-                                if (PAIR && paired) {
-                                    if (kb + kk == 0) umma_f16_pair<false>(dcol, ad, bd, idesc); else umma_f16_pair<true>(dcol, ad, bd, idesc);
-                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
-                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
-                                    umma_f16_pair<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
-                                } else {
-                                    if (kb + kk == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
-                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
-                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
-                                    umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                for (int kk = 0; kk < kTcKbPerOp; ++kk) {
+                                    const uint64_t ad = umma_desc_sw128(smem_u32(smem + ring0 + slot * slot_bytes) + kk * kb_bytes);
+                                    const uint64_t bd = umma_desc_sw128(smem_u32(smem + wofs_ph + (kb + kk) * ncol_ph * 128));
+                                    if (PAIR && paired) {
+                                        if (kb + kk == 0) umma_f16_pair<false>(dcol, ad, bd, idesc); else umma_f16_pair<true>(dcol, ad, bd, idesc);
+                                        umma_f16_pair<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                                        umma_f16_pair<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                                        umma_f16_pair<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                    } else {
+                                        if (kb + kk == 0) umma_f16_c<false>(dcol, ad, bd, idesc); else umma_f16_c<true>(dcol, ad, bd, idesc);
+                                        umma_f16_c<true>(dcol, umma_desc_advance(ad, 32), umma_desc_advance(bd, 32), idesc);
+                                        umma_f16_c<true>(dcol, umma_desc_advance(ad, 64), umma_desc_advance(bd, 64), idesc);
+                                        umma_f16_c<true>(dcol, umma_desc_advance(ad, 96), umma_desc_advance(bd, 96), idesc);
+                                    }
                                 }
                             }
+                            if (PAIR && paired) umma_commit_pair(&ctl->empty[slot]); else umma_commit(&ctl->empty[slot]);
+                            if (kb + kTcKbPerOp >= kNKB) {
+                                if (PAIR && paired) umma_commit_pair(&ctl->accfull[s * 4 + ph]); else umma_commit(&ctl->accfull[s * 4 + ph]);
+                            }
                         }
-                        if (PAIR && paired) umma_commit_pair(&ctl->empty[slot]); else umma_commit(&ctl->empty[slot]);
+                        __syncwarp();
                         if (ph == 0 && s == 1) trace(p, t, 144 + kb);              // MMAs + commit issued
                     }
-                    if (PAIR && paired) umma_commit_pair(&ctl->accfull[s * 4 + ph]); else umma_commit(&ctl->accfull[s * 4 + ph]);
                     trace(p, t, 64 + (ph * 4 + s) * 4 + 3);          // all MMAs of the job issued
                 }
             }

@@ -12,6 +12,17 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  tcgen05.mma / TMA / tcgen05.commit take their operands from uniform registers: inside an
+// elect.sync region ptxas moves them there with a plain R2UR, while under `if (lane == 0)` it cannot prove the operands
+// warp-uniform and wraps EVERY such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop -- measured on
+// B200 (tools/probes/mma_rate3.cu): 45-118 clocks per MMA under lane == 0 against the tensor pipe's N/2 clocks (TS) or
+// max(N/2, ~40) clocks (SS) under elect.sync.  Every issuing role therefore walks its loop with the whole warp and elects.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
