@@ -71,6 +71,7 @@ struct wrnn_engine {
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor, bCsDone;
     DevBuf wTc, wTcS, bTcExch, bCS;
     DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
+    DevBuf wRs[4], bRsExch;     // role-specialised tensor-core loop (MOL): per-role weight images, exchange matrices + sample words
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
     int spStride[2] = {0, 0};
     DevBuf wCondTc, bCondH;     // tensor-core front end: hi/lo fp16 weights (scaled by 2^8) and activation pairs
@@ -197,6 +198,8 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
         if (err == cudaSuccess) err = set_tc_deadline((long long)(atof(dl) * 1.9e6));
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
         if (err == cudaSuccess) err = set_tc2_deadline((long long)(atof(dl) * 1.9e6));
+    if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
+        if (err == cudaSuccess) err = set_rs_deadline((long long)(atof(dl) * 1.9e6));
     if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
     *out = e;
     return WRNN_OK;
@@ -208,7 +211,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2, &e->wRs[0], &e->wRs[1], &e->wRs[2], &e->wRs[3], &e->bRsExch};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -397,6 +400,45 @@ int wrnn_finalize(wrnn_engine* e) {
                 for (int r = 0; r < C / nq; ++r) put(hs.data() + (size_t)q * simg, C / nq, r, f3w->data.data() + (size_t)(q * (C / nq) + r) * H);
             CU(e->wTcS.ensure(hs.size()));
             CU(cudaMemcpy(e->wTcS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
+    // ---- role-specialised tensor-core loop (MOL, loop_rs.cu): one image per CTA and role, K-major SWIZZLE_128B tiles --------
+    //   T1 (GRU1, units 32c..32c+31): [W_hh1 rows gate*32+u (96)] [fc3 rows (30 of 32)]      T2 (GRU2): [W_ih2a (96)] [W_hh2 (96)]
+    //   T3 (fc1, units 64c..64c+63): [fc1[:, :512] (64)]                                       T4 (fc2): [fc2[:, :512] (64)]
+    if (C == 30) {
+        auto put_tile = [&](unsigned char* tile, int nrows, int r, const float* src) {
+            for (int kb = 0; kb < 8; ++kb)
+                for (int c = 0; c < 8; ++c) {
+                    __half* dst = reinterpret_cast<__half*>(tile + (size_t)kb * nrows * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+                    for (int i = 0; i < 8; ++i) dst[i] = __float2half_rn(src[kb * 64 + c * 8 + i]);
+                }
+        };
+        const float* Wih2a = hl.data() + oWih2a;
+        const float* Wfc1a = hl.data() + oWfc1a;
+        const float* Wfc2a = hl.data() + oWfc2a;
+        const int nct[4] = {kRsT1, kRsT2, kRsT3, kRsT4};
+        for (int role = 0; role < 4; ++role) {
+            const size_t img = loop_rs_image_bytes(role);
+            std::vector<unsigned char> hw((size_t)nct[role] * img, 0);
+            for (int c = 0; c < nct[role]; ++c) {
+                unsigned char* t0 = hw.data() + (size_t)c * img;
+                unsigned char* t1 = t0 + (size_t)96 * 1024;
+                if (role < 2) {
+                    for (int u = 0; u < 32; ++u)
+                        for (int gt = 0; gt < 3; ++gt) {
+                            const size_t r = (size_t)(gt * H + 32 * c + u) * H;
+                            if (role == 0) put_tile(t0, 96, 32 * gt + u, r1hh->data.data() + r);
+                            else { put_tile(t0, 96, 32 * gt + u, Wih2a + r); put_tile(t1, 96, 32 * gt + u, r2hh->data.data() + r); }
+                        }
+                    if (role == 0)
+                        for (int k = 0; k < 30; ++k) put_tile(t1, 32, k, f3w->data.data() + (size_t)k * H);
+                } else {
+                    for (int u = 0; u < 64; ++u) put_tile(t0, 64, u, (role == 2 ? Wfc1a : Wfc2a) + (size_t)(64 * c + u) * H);
+                }
+            }
+            CU(e->wRs[role].ensure(hw.size()));
+            CU(cudaMemcpy(e->wRs[role].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
         }
     }
 
@@ -860,6 +902,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     auto t_start = std::chrono::steady_clock::now();
     float ms_expand = 0.f;
     const int wave = use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch);
+    // role-specialised loop: as many 48-CTA groups as the device holds; WRNN_RS=0 keeps loop_tc.cu for every fold count
+    const int rs_groups_max = std::max(0, e->n_sms / kRsCtas);
+    const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);
         CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
@@ -891,6 +936,66 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             }
             if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
             e->launches += 1;
+        } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wRs[0].p && B <= rs_max_folds) {
+            // ---- role-specialised tensor-core loop (loop_rs.cu): the latency-bound regime, <= 128 folds per 48-CTA group ---------
+            int G = std::min(rs_groups_max, std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
+            if (const char* ev = getenv("WRNN_RS_GROUPS")) G = std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, std::min(rs_groups_max, atoi(ev)));
+            const int Ng = (B + G - 1) / G;
+            const int cs_steps = S;
+            const size_t cs_bytes = (size_t)G * cs_steps * Ng * 4096 * sizeof(float);
+            if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
+            CU(e->bCS.ensure(cs_bytes));
+            CU(cudaEventRecord(e->evx[0], st));
+            CU(launch_expand_cond_rs(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
+                                     e->bFolds.as<FoldDesc>() + w0, B, S, Ng, cs_steps, e->bCS.as<float>(), st));
+            CU(cudaEventRecord(e->evx[1], st));
+            expanded = true;
+            const size_t xbytes = loop_rs_exchange_bytes(G), wbytes = (size_t)G * 128 * sizeof(unsigned long long);
+            CU(e->bRsExch.ensure(xbytes + wbytes));
+            CU(cudaMemsetAsync(e->bRsExch.p, 0xFF, xbytes, st));
+            CU(cudaMemsetAsync(e->bRsExch.as<unsigned char>() + xbytes, 0, wbytes, st));
+            RsParams rp;
+            memset(&rp, 0, sizeof(rp));
+            rp.w1 = e->wRs[0].as<unsigned char>(); rp.w2 = e->wRs[1].as<unsigned char>();
+            rp.w3 = e->wRs[2].as<unsigned char>(); rp.w4 = e->wRs[3].as<unsigned char>();
+            rp.v1 = e->dv1; rp.v2 = e->dv2; rp.v3 = e->dv3; rp.bhn1 = e->dbhn1; rp.bhn2 = e->dbhn2; rp.bfc3 = e->dbfc3;
+            rp.CS = e->bCS.as<float>(); rp.cs_steps = cs_steps; rp.Ng = Ng; rp.G = G;
+            rp.folds = e->bFolds.as<FoldDesc>() + w0;
+            rp.B = B; rp.S = S; rp.seed = rq->seed;
+            rp.X = e->bRsExch.as<uint4>();
+            rp.bX = reinterpret_cast<unsigned long long*>(e->bRsExch.as<unsigned char>() + xbytes);
+            rp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+            rp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            rp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+            rp.progress = e->dProgress;
+            rp.abort_flag = e->dAbort;
+            int* hdbg = nullptr;
+            if (getenv("WRNN_RS_DEBUG") && atoi(getenv("WRNN_RS_DEBUG"))) {     // checkpoints in mapped host memory: readable while the kernel hangs
+                CU(cudaHostAlloc(&hdbg, (size_t)G * kRsCtas * 32 * sizeof(int), cudaHostAllocMapped));
+                memset(hdbg, 0, (size_t)G * kRsCtas * 32 * sizeof(int));
+                CU(cudaHostGetDevicePointer(&rp.dbg, hdbg, 0));
+            }
+            CU(launch_loop_rs(rp, st));
+            if (hdbg) {
+                CU(cudaEventRecord(e->ev[7], st));
+                const auto t_dbg = std::chrono::steady_clock::now();
+                bool dumped = false;
+                while (cudaEventQuery(e->ev[7]) == cudaErrorNotReady) {
+                    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dbg).count();
+                    if (dt > 3.0 && !dumped) {
+                        dumped = true;
+                        for (int c = 0; c < G * kRsCtas; ++c) {
+                            fprintf(stderr, "[rs dbg] cta %3d:", c);
+                            for (int w = 0; w < 20; ++w) fprintf(stderr, " %d:%02x", hdbg[c * 32 + w] >> 8, hdbg[c * 32 + w] & 0xFF);
+                            fprintf(stderr, "\n");
+                        }
+                        fflush(stderr);
+                    }
+                    std::this_thread::sleep_for(std::chrono::milliseconds(10));
+                }
+                cudaFreeHost(hdbg);
+            }
+            e->launches += 2;
         } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wTc2.p && getenv("WRNN_TC_V2") && atoi(getenv("WRNN_TC_V2"))) {
             // (opt-in: measured equal to loop_tc.cu in round 1 -- 27.4 vs 26.6 us/step -- see DESIGN.md section 4.3)
             // ---- cluster-local tensor-core loop (MOL): folds partitioned over independent 16-CTA clusters -----------------

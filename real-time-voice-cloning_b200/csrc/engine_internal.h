@@ -110,6 +110,36 @@ cudaError_t launch_loop_tc(const TcParams& p, const void* tmaps, cudaStream_t st
 cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                const FoldDesc* folds, int B, int S, int Mg, float4* CS, cudaStream_t stream);
 
+// ---- role-specialised tensor-core loop, MOL, <= 128 folds per group (loop_rs.cu) ------------------------------------
+constexpr int kRsT1 = 16, kRsT2 = 16, kRsT3 = 8, kRsT4 = 8;     // CTAs per role: GRU1 (+fc3 + draw), GRU2, fc1, fc2
+constexpr int kRsCtas = kRsT1 + kRsT2 + kRsT3 + kRsT4;          // one group
+constexpr int kRsBufs = 2;                                      // exchange matrices are double-buffered by step parity
+constexpr int kRsMaxFoldsPerGroup = 128;
+struct RsParams {
+    const unsigned char *w1, *w2, *w3, *w4;   // per-role weight images [CTA][loop_rs_image_bytes(role)], shared-memory layout
+    const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
+    const float* CS;             // per-sample conditioning [group][cs_steps][Ng][8][512] fp32 (expand_cond_rs_kernel)
+    int cs_steps;
+    int Ng, G;                   // folds per group (<= 128), groups; fold f = row f % Ng of group f / Ng
+    const FoldDesc* folds;
+    int B, S;
+    unsigned long long seed;
+    uint4* X;                    // exchange: [G][5 matrices][kRsBufs][64 chunks][128 folds] 16-byte chunks; all bytes 0xFF at launch
+    unsigned long long* bX;      // [G][128] sample words {value, tag}; zero at launch
+    float* samples;
+    float* logits_out;
+    const float* forced;
+    int* progress;
+    int* abort_flag;
+    int* dbg;                    // optional mapped host memory [CTA][32] checkpoints (WRNN_RS_DEBUG=1)
+};
+size_t loop_rs_image_bytes(int role);
+size_t loop_rs_exchange_bytes(int groups);
+cudaError_t set_rs_deadline(long long cycles);
+cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream);
+cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
+                                  const FoldDesc* folds, int B, int S, int Ng, int cs_steps, float* CS, cudaStream_t stream);
+
 // ---- cluster-local tensor-core loop, MOL (loop_tc2.cu) --------------------------------------------------------------
 struct Tc2Params {
     const unsigned char* wimg;   // [16][loop_tc2_image_bytes()] per-CTA streams of pre-swizzled weight tiles

@@ -1,0 +1,629 @@
+// loop_rs.cu -- the latency-bound regime of the autoregressive sample loop (<= 128 folds per CTA group, MOL): a
+// ROLE-SPECIALISED tensor-core loop.  DESIGN.md section 4.5 has the measurements behind every choice below.
+//
+// loop_tc.cu gives every CTA a unit slice of EVERY layer, so every CTA pulls every activation matrix (4 x [folds x 512]
+// per step) through a counter + TMA pipeline: ~4.5 us per stage.  Here a CTA owns ONE layer's rows:
+//   T1 x16  GRU1, 32 hidden units each: W_hh1 rows (96) + a full copy of fc3 (MOL: 32 rows)
+//   T2 x16  GRU2, 32 hidden units each: W_ih2[:, :512] rows (96) + W_hh2 rows (96)
+//   T3 x8   fc1, 64 units each          T4 x8   fc2, 64 units each
+// (48 CTAs = one group; G groups split the folds).  Consequences:
+//  * an activation matrix is read by 8-16 CTAs instead of 64, and only ONE on-path matrix per CTA and step;
+//  * fc3 + the mixture draw are replicated on every T1 CTA (same inputs, same Philox counters -> identical samples), so the
+//    sample never travels on the critical path: a step has FOUR exchanges (h1, h2|s2, f1, f2) instead of five;
+//  * the operand with M = 128 rows is the ACTIVATION matrix (TMEM lane = fold), written straight into TENSOR MEMORY by the
+//    threads that receive it (tcgen05.st) and consumed from there (tcgen05.mma, A in TMEM): no shared-memory staging, no
+//    TMA, no proxy fence; at the tensor pipe's N/2 clocks per K=16 step (tools/probes/mma_rate3.cu);
+//  * the exchange has no fence, counter or flag: activations travel as 16-byte chunks [chunk][fold] (8 fp16 of one fold)
+//    whose validity is a GENERATION BIT carried in every half -- bit 14 for |v| < 2 (GRU states, their sum), the sign bit
+//    for ReLU outputs -- so the payload keeps all its precision, a torn chunk can never validate, and nothing is ever
+//    reset (tools/probes/xchg9.cu: sentinel resets cost ~1 us per exchange).  Double-buffered by step parity; generation
+//    = (step / 2) & 1.  Receivers poll one canary chunk per producer, then load everything once and re-poll stragglers;
+//  * the recurrent products W_hh1 h1(t), W_hh2 h2(t) for step t+1 run off the critical path on the same A buffer.
+// Conditioning: per-sample records [group][step][fold][8][512] fp32 (c1 r,z,n | c2 r,z,n | c3 | c4), read by the owning
+// thread only, prefetched before the step's wait.
+// Every wait has a deadline ("soft abort", as loop_tc.cu): a bad build ends with an error code, never a hung GPU.
+#include <cstdio>
+#include <cstdlib>
+#include "engine_internal.h"
+#include "tc_common.cuh"
+
+namespace wrnn {
+
+__device__ long long g_rs_deadline = 1500000000LL;
+
+namespace {
+using namespace tc;
+
+constexpr int NW = 16;                        // ingest / epilogue warps: warp w = (lane quadrant q = w & 3, K quarter / column slice w >> 2)
+constexpr int NT = (NW + 4) * 32;             // + a service warpgroup: the MMA warp and three idle warps (setmaxnreg works on whole warpgroups)
+constexpr int kRegsEpi = 112, kRegsSvc = 32;  // after the hand-over: 16 x 112 + 4 x 32 = 20 x 96, the launch allocation (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
+constexpr int kChunks = kRnn / 8;             // 64 chunks of 8 fp16 per activation row
+constexpr size_t kMatChunks = (size_t)kChunks * 128;     // one buffer of one exchange matrix: [chunk][fold] x 16 bytes = 128 KB
+enum { MH1 = 0, MH2, MS2, MF1, MF2, kMats };
+constexpr uint32_t kTagE = 0x40004000u;       // generation bit of matrices with |v| < 2: bit 14 of every half
+constexpr uint32_t kTagS = 0x80008000u;       // of non-negative matrices (ReLU outputs): the sign bit
+// TMEM columns
+constexpr uint32_t kColA = 0;                 // activation operand, 128 lanes x 256 columns (512 fp16 per lane)
+constexpr uint32_t kColD0 = 256;              // on-path accumulator (T1: W_hh1 h1 [96] lives here too, see below)
+constexpr uint32_t kColD1 = 352;              // second accumulator
+// shared memory: weight tiles (K-major SWIZZLE_128B, [k-block 8][rows N][128 B]) then constants and the control block
+constexpr int kW0 = 0;                                   // first tile: T1 W_hh1 (96 rows), T2 W_ih2a (96), T3 fc1a (64), T4 fc2 (64)
+constexpr int kW1 = 96 * 128 * 8;                        // second tile: T1 fc3 (32 rows), T2 W_hh2 (96)
+constexpr int kWEnd = kW1 + 96 * 128 * 8;                // 196608
+constexpr int kConstOfs = kWEnd;                         // per-unit constants, <= 5 x 64 floats
+constexpr int kCtlOfs = kConstOfs + 2048;
+constexpr int kSmemBytes = kCtlOfs + 256;
+
+struct Ctl {
+    uint64_t abar[4];      // K quarter kq of the A operand is in TMEM (4 warps arrive)
+    uint64_t dbar[2];      // accumulator complete (tcgen05.commit): [0] on-path job, [1] recurrent (off-path) job
+    uint64_t ebar;         // all 16 epilogue warps have read the recurrent accumulator of the previous step
+    uint32_t tmem;
+    int abort_local;
+};
+
+__device__ __forceinline__ bool aborted_local(Ctl* c) { return *reinterpret_cast<volatile int*>(&c->abort_local) != 0; }
+// warp-uniform view of the abort flag (lane 0's): the step loops end together for all lanes of a warp
+__device__ __forceinline__ bool warp_aborted(Ctl* c) { return __shfl_sync(0xffffffffu, aborted_local(c) ? 1 : 0, 0) != 0; }
+__device__ __noinline__ bool spin_check(const RsParams& p, Ctl* c, long long& t0) {
+    if (aborted_local(c)) return true;
+    if (ld_volatile_i32(p.abort_flag) != 0) { *reinterpret_cast<volatile int*>(&c->abort_local) = 1; return true; }
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > g_rs_deadline) {
+        *reinterpret_cast<volatile int*>(&c->abort_local) = 1;
+        atomicExch(p.abort_flag, 1);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool wait_mbar(const RsParams& p, Ctl* c, uint64_t* bar, uint32_t parity) {
+    long long t0 = 0;
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++spins) & 15) == 0 && aborted_local(c)) return false;
+        if ((spins & 1023) == 0 && spin_check(p, c, t0)) return false;
+    }
+    return true;
+}
+
+// optional checkpoints into mapped host memory (WRNN_RS_DEBUG=1): [CTA][32 warps] last (step << 8 | code) of lane 0
+__device__ __forceinline__ void dbg(const RsParams& p, int t, int code) {
+    if (p.dbg && (threadIdx.x & 31) == 0) {
+        *reinterpret_cast<volatile int*>(p.dbg + blockIdx.x * 32 + (threadIdx.x >> 5)) = (t << 8) | code;
+    }
+}
+
+__device__ __forceinline__ uint4 ld_chunk(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_chunk(uint4* p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ bool tags_ok(uint4 v, uint32_t tb, uint32_t want) {
+    return ((((v.x ^ want) | (v.y ^ want) | (v.z ^ want) | (v.w ^ want)) & tb) == 0u);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T, A = 128 lanes x 8 columns (16 fp16 per lane)
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    return __half22float2(h);
+}
+
+// Exchange-side view of a thread: fold lane and the step-independent addresses.
+struct Lane {
+    int q, cs, lane, row;         // lane quadrant, column slice / K quarter, lane, fold row inside the group
+    bool live;
+    uint32_t tlane;               // TMEM address of my lane quadrant, column 0
+};
+
+// Receive one activation matrix (this step's buffer) into the A operand in TMEM: warp (q, kq) takes the 16 chunks
+// [16 kq, 16 kq + 16) of its 32 folds.  `extra` (optional): one more chunk of my row, returned to the caller (T2: my own
+// units of h1).  Lanes 0..15 first poll one canary chunk each (chunk 16 kq + lane of row 32 q + lane), then every lane
+// loads its 16 chunks once and re-polls the ones whose generation bits do not match yet.
+__device__ __forceinline__ void ingest(const RsParams& p, Ctl* ctl, const Lane& L, const uint4* mat, uint32_t tb, uint32_t want, int nrows,
+                                       int extra_chunk, uint4& extra, int dbg_t) {
+    const uint4* base = mat + (size_t)(L.cs * 16) * 128 + L.row;
+    dbg(p, dbg_t, 0x10);
+    {   // canaries
+        const int crow = 32 * L.q + L.lane;
+        const bool poll = L.lane < 16 && crow < nrows;
+        const uint4* cp = mat + (size_t)(L.cs * 16 + (L.lane & 15)) * 128 + crow;
+        long long t0 = 0;
+        int spins = 0;
+        bool ok = !poll;
+        while (true) {
+            if (!ok) ok = tags_ok(ld_chunk(cp), tb, want);
+            if (__all_sync(0xffffffffu, ok)) break;
+            const bool quit = ((++spins) & 255) == 0 && spin_check(p, ctl, t0);     // (spins is warp-uniform)
+            if (__any_sync(0xffffffffu, quit)) break;
+        }
+    }
+    dbg(p, dbg_t, 0x11);
+    uint4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    extra = make_uint4(0u, 0u, 0u, 0u);
+    if (L.live) {
+        uint32_t pending = extra_chunk >= 0 ? 0x1FFFFu : 0xFFFFu;
+        long long t0 = 0;
+        int spins = 0;
+        while (pending) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if ((pending >> i) & 1u) v[i] = ld_chunk(base + (size_t)i * 128);
+            if ((pending >> 16) & 1u) extra = ld_chunk(mat + (size_t)extra_chunk * 128 + L.row);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (((pending >> i) & 1u) && tags_ok(v[i], tb, want)) pending &= ~(1u << i);
+            if (((pending >> 16) & 1u) && tags_ok(extra, tb, want)) pending &= ~(1u << 16);
+            if (pending && ((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
+        }
+    }
+    __syncwarp();
+    dbg(p, dbg_t, 0x12);
+    uint32_t r[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[4 * i + 0] = v[4 * j + i].x & ~tb; r[4 * i + 1] = v[4 * j + i].y & ~tb;
+            r[4 * i + 2] = v[4 * j + i].z & ~tb; r[4 * i + 3] = v[4 * j + i].w & ~tb;
+        }
+        tmem_st16(L.tlane + kColA + (uint32_t)(L.cs * 64 + j * 16), r);
+    }
+    extra.x &= ~tb; extra.y &= ~tb; extra.z &= ~tb; extra.w &= ~tb;
+    tmem_st_wait();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (L.lane == 0) mbar_arrive(&ctl->abar[L.cs]);
+    dbg(p, dbg_t, 0x13);
+}
+
+// Publish 8 values of my fold as one chunk (generation bit in every half).
+__device__ __forceinline__ void publish8(uint4* mat, int chunk, int row, const float* v, uint32_t tb, uint32_t want) {
+    uint4 w;
+    w.x = (pack2(v[0], v[1]) & ~tb) | want; w.y = (pack2(v[2], v[3]) & ~tb) | want;
+    w.z = (pack2(v[4], v[5]) & ~tb) | want; w.w = (pack2(v[6], v[7]) & ~tb) | want;
+    st_chunk(mat + (size_t)chunk * 128 + row, w);
+}
+
+// the MOL draw of one fold from its 30 outputs (vocoder/distribution.py:104-140; same arithmetic as loop_tc.cu)
+__device__ __forceinline__ float mol_draw(const float* lg, const float* sbias, uint32_t t, uint32_t fold, uint32_t utt, uint2 key) {
+    float best = -INFINITY;
+    int kbest = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const uint4 r = philox4x32_10(make_uint4(t, fold, utt, (uint32_t)b), key);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int i = 4 * b + w;
+            if (i < 10) {
+                const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
+                const float sc = lg[i] + sbias[i] - __logf(-__logf(um));
+                if (sc > best) { best = sc; kbest = i; }
+            }
+        }
+        if (b == 2) {
+            float mean = 0.f, lsc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 10; ++i)
+                if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
+            lsc = fmaxf(lsc, -32.23619130191664f);
+            const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
+            const float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
+            return fminf(fmaxf(xs, -1.0f), 1.0f);
+        }
+    }
+    return 0.f;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_constant__ RsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem + kCtlOfs);
+    float* cst = reinterpret_cast<float*>(smem + kConstOfs);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = (int)blockIdx.x / kRsCtas, rc = (int)blockIdx.x % kRsCtas;
+    const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : 3));
+    const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : rc - kRsT1 - kRsT2 - kRsT3));
+    const int fold0 = g * p.Ng, nrows = max(0, min(p.Ng, p.B - fold0));
+    const int S = p.S;
+
+    // ---- one-time setup: weight tiles, constants, barriers, TMEM ------------------------------------------------------
+    {
+        const unsigned char* img = role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
+                                 : role == 1 ? p.w2 + (size_t)cta * kWEnd
+                                 : role == 2 ? p.w3 + (size_t)cta * (64 * 128 * 8) : p.w4 + (size_t)cta * (64 * 128 * 8);
+        const int bytes = role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : 64 * 128 * 8);
+        const uint4* src = reinterpret_cast<const uint4*>(img);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
+        fence_proxy_async_smem();
+    }
+    if (role == 0) {            // [v1 r,z,n | b_hn1] x 32 units, fc3 bias (32)
+        if (tid < 128) { const int a = tid >> 5, u = tid & 31, j = 32 * cta + u; cst[tid] = a < 3 ? p.v1[a * kRnn + j] : p.bhn1[j]; }
+        else if (tid < 160) cst[tid] = (tid - 128) < 30 ? p.bfc3[tid - 128] : 0.f;
+    } else if (role == 1) {     // [v2 r,z,n | b_hn2] x 32 units
+        if (tid < 128) { const int a = tid >> 5, u = tid & 31, j = 32 * cta + u; cst[tid] = a < 3 ? p.v2[a * kRnn + j] : p.bhn2[j]; }
+    } else if (role == 2) {     // v3 x 64 units
+        if (tid < 64) cst[tid] = p.v3[64 * cta + tid];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], 4);
+        mbar_init(&ctl->dbar[0], 1); mbar_init(&ctl->dbar[1], 1);
+        mbar_init(&ctl->ebar, NW);
+        ctl->abort_local = 0;
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&ctl->tmem, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = ctl->tmem;
+    dbg(p, 0, 1);
+    // (register hand-over, first statement of each role's branch below: the service warpgroup gives its registers to the
+    //  16 ingest / epilogue warps, so nothing on the chain spills)
+
+    uint4* const X = p.X + (size_t)g * kMats * kRsBufs * kMatChunks;
+#define MAT(m, t) (X + ((size_t)(m) * kRsBufs + ((t) % kRsBufs)) * kMatChunks)
+#define GEN(t) ((((t) / kRsBufs) & 1) != 0)
+
+    if (warp >= NW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsSvc));     // (one instruction for the whole warpgroup)
+        dbg(p, 0, 2);
+        if (warp == NW) {
+        // =================================== MMA issuer ====================================================================
+        // whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one).  A job = 32 K-steps over the A operand
+        // in TMEM, issued K quarter by K quarter as the ingest warps deliver them.
+        uint32_t n_ingest = 0;
+        auto job = [&](uint32_t dcol, uint32_t wofs, uint32_t N, uint64_t* done, bool wait_e, uint32_t e_par) {
+            const uint32_t idesc = umma_idesc_f16(128, (int)N);
+            for (int kq = 0; kq < 4; ++kq) {
+                dbg(p, (int)n_ingest, 0x20 + kq);
+                wait_mbar(p, ctl, &ctl->abar[kq], n_ingest & 1u);
+                if (kq == 0 && wait_e) wait_mbar(p, ctl, &ctl->ebar, e_par);
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int kk = kq * 8 + k;
+                        const uint64_t bd = umma_desc_advance(umma_desc_sw128(smem_u32(smem + wofs + (uint32_t)(kk >> 2) * N * 128u)), (uint32_t)(kk & 3) * 32u);
+                        umma_ts(tmem + dcol, tmem + kColA + (uint32_t)kk * 8u, bd, idesc, kk > 0 ? 1u : 0u);
+                    }
+                    if (kq == 3) umma_commit(done);
+                }
+                __syncwarp();
+            }
+            ++n_ingest;
+        };
+        if (role == 0) {
+            for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
+                if (t > 0) job(kColD1, kW1, 32, &ctl->dbar[0], false, 0);                       // fc3 f2(t-1)
+                if (t < S) job(kColD0, kW0, 96, &ctl->dbar[1], true, (uint32_t)t & 1u);         // W_hh1 h1(t)
+            }
+        } else if (role == 1) {
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                job(kColD0, kW0, 96, &ctl->dbar[0], false, 0);                                  // W_ih2a h1(t)
+                job(kColD1, kW1, 96, &ctl->dbar[1], true, (uint32_t)t & 1u);                    // W_hh2 h2(t)
+            }
+        } else {
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(kColD0, kW0, 64, &ctl->dbar[0], false, 0);          // fc1a s2(t) / fc2 f1(t)
+        }
+        }
+    } else {
+        // =================================== ingest + epilogue warps ========================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+        dbg(p, 0, 3);
+        Lane L;
+        L.q = warp & 3; L.cs = warp >> 2; L.lane = lane; L.row = 32 * L.q + lane; L.live = L.row < nrows;
+        L.tlane = tmem + ((uint32_t)(32 * L.q) << 16);
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const FoldDesc fd = p.folds[L.live ? fold0 + L.row : 0];
+        const size_t srow = (size_t)(fold0 + L.row) * S;                     // my fold's row of samples / forced
+        unsigned long long* const xw = p.bX + (size_t)g * 128 + L.row;
+        const float* const csrow = p.CS + ((size_t)g * p.cs_steps * p.Ng + L.row) * 4096;   // + (t % cs_steps) * Ng * 4096
+        const size_t cs_step = (size_t)p.Ng * 4096;
+        uint4 extra;
+
+        if (role == 0) {
+            // ---- T1: fc3 + draw of step t-1, GRU1 of step t, then the recurrent product for step t+1 -----------------------
+            float h1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h1[i] = 0.f;
+            const float* v1 = cst + L.cs * 8;                    // [a][32]: + 32 a
+            const float* sbias = cst + 128;
+            for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
+                float c1[24];
+                if (t < S && L.live) {
+                    const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float4 lo = __ldcs(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcs(reinterpret_cast<const float4*>(c + a * 512) + 1);
+                        c1[8 * a + 0] = lo.x; c1[8 * a + 1] = lo.y; c1[8 * a + 2] = lo.z; c1[8 * a + 3] = lo.w;
+                        c1[8 * a + 4] = hi.x; c1[8 * a + 5] = hi.y; c1[8 * a + 6] = hi.z; c1[8 * a + 7] = hi.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) c1[i] = 0.f;
+                }
+                float x = 0.f;
+                if (t > 0) {
+                    // the A buffer is free once the recurrent job of step t-1 has completed
+                    wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
+                    tcgen05_fence_after();
+                    ingest(p, ctl, L, MAT(MF2, t - 1), kTagS, GEN(t - 1) ? kTagS : 0u, nrows, -1, extra, t);
+                    wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)(t - 1) & 1u);
+                    tcgen05_fence_after();
+                    float lg[32];
+                    tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
+                    tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
+                    tmem_ld_wait();
+                    const float xs = mol_draw(lg, sbias, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
+                    x = xs;
+                    if (L.live) {
+                        if (p.forced) x = p.forced[srow + t - 1];
+                        if (cta == 0 && L.cs == 0) {
+                            p.samples[srow + t - 1] = xs;
+                            ll_store(xw, x, (uint32_t)t);
+                            if (p.logits_out)
+                                for (int i = 0; i < 30; ++i) p.logits_out[(srow + t - 1) * 30 + i] = lg[i] + sbias[i];
+                        }
+                    }
+                }
+                if (t == S) break;
+                float gh[24];
+                if (t > 0) {
+                    tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, gh + 8);
+                    tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, gh + 16);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) gh[i] = 0.f;
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->ebar);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float r = sigmoid_fast(fmaf(v1[i], x, c1[i]) + gh[i]);
+                    const float z = sigmoid_fast(fmaf(v1[32 + i], x, c1[8 + i]) + gh[8 + i]);
+                    const float n = tanh_fast(fmaf(v1[64 + i], x, c1[16 + i]) + r * (gh[16 + i] + v1[96 + i]));
+                    h1[i] = (1.0f - z) * n + z * h1[i];
+                }
+                if (L.live) publish8(MAT(MH1, t), 4 * cta + L.cs, L.row, h1, kTagE, GEN(t) ? kTagE : 0u);
+                // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited)
+                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, nrows, -1, extra, t);
+                if (cta == 0 && g == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
+                    *reinterpret_cast<volatile int*>(p.progress) = t;
+                    __threadfence_system();
+                }
+            }
+        } else if (role == 1) {
+            // ---- T2: GRU2 of step t from h1(t); publishes h2 and s2 = h1 + h2; then the recurrent product for step t+1 -------
+            float h2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h2[i] = 0.f;
+            const float* v2 = cst + L.cs * 8;
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                float c2[24];
+                if (L.live) {
+                    const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float4 lo = __ldcs(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcs(reinterpret_cast<const float4*>(c + a * 512) + 1);
+                        c2[8 * a + 0] = lo.x; c2[8 * a + 1] = lo.y; c2[8 * a + 2] = lo.z; c2[8 * a + 3] = lo.w;
+                        c2[8 * a + 4] = hi.x; c2[8 * a + 5] = hi.y; c2[8 * a + 6] = hi.z; c2[8 * a + 7] = hi.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) c2[i] = 0.f;
+                }
+                if (t > 0) {
+                    wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
+                    tcgen05_fence_after();
+                }
+                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, nrows, 4 * cta + L.cs, extra, t);
+                float x = 0.f;
+                if (t > 0 && L.live) {
+                    long long t0 = 0;
+                    int spins = 0;
+                    while (true) {
+                        const unsigned long long w = ll_load(xw);
+                        if (ll_tag(w) == (uint32_t)t) { x = ll_val(w); break; }
+                        if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
+                    }
+                }
+                dbg(p, t, 0x30);
+                wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
+                tcgen05_fence_after();
+                dbg(p, t, 0x31);
+                float pb[24], gh[24];
+                tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, pb); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, pb + 8);
+                tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, pb + 16);
+                if (t > 0) {
+                    tmem_ld8(L.tlane + kColD1 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD1 + 32 + 8 * L.cs, gh + 8);
+                    tmem_ld8(L.tlane + kColD1 + 64 + 8 * L.cs, gh + 16);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) gh[i] = 0.f;
+                }
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->ebar);
+                float s2[8];
+                const float2 e0 = unpack2(extra.x), e1 = unpack2(extra.y), e2 = unpack2(extra.z), e3 = unpack2(extra.w);
+                const float h1o[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float r = sigmoid_fast(pb[i] + fmaf(v2[i], x, c2[i]) + gh[i]);
+                    const float z = sigmoid_fast(pb[8 + i] + fmaf(v2[32 + i], x, c2[8 + i]) + gh[8 + i]);
+                    const float n = tanh_fast(pb[16 + i] + fmaf(v2[64 + i], x, c2[16 + i]) + r * (gh[16 + i] + v2[96 + i]));
+                    h2[i] = (1.0f - z) * n + z * h2[i];
+                    s2[i] = fminf(fmaxf(h1o[i] + h2[i], -1.9990234375f), 1.9990234375f);
+                }
+                if (L.live) {
+                    publish8(MAT(MS2, t), 4 * cta + L.cs, L.row, s2, kTagE, GEN(t) ? kTagE : 0u);
+                    publish8(MAT(MH2, t), 4 * cta + L.cs, L.row, h2, kTagE, GEN(t) ? kTagE : 0u);
+                }
+                ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, nrows, -1, extra, t);
+            }
+        } else {
+            // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
+            const bool fc1 = role == 2;
+            const float* v3 = cst + L.cs * 16;
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                float cc[16];
+                if (L.live) {
+                    const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + 64 * cta + 16 * L.cs);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float4 q4 = __ldcs(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cc[i] = 0.f;
+                }
+                ingest(p, ctl, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t) ? (fc1 ? kTagE : kTagS) : 0u, nrows, -1, extra, t);
+                float x = 0.f;
+                if (fc1 && t > 0 && L.live) {
+                    long long t0 = 0;
+                    int spins = 0;
+                    while (true) {
+                        const unsigned long long w = ll_load(xw);
+                        if (ll_tag(w) == (uint32_t)t) { x = ll_val(w); break; }
+                        if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
+                    }
+                }
+                wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
+                tcgen05_fence_after();
+                float d[16];
+                tmem_ld8(L.tlane + kColD0 + 16 * L.cs, d); tmem_ld8(L.tlane + kColD0 + 16 * L.cs + 8, d + 8);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i] + (fc1 ? fmaf(v3[i], x, cc[i]) : cc[i]), 0.f);
+                if (L.live) {
+                    uint4* m = MAT(fc1 ? MF1 : MF2, t);
+                    const uint32_t want = GEN(t) ? kTagS : 0u;
+                    publish8(m, 8 * cta + 2 * L.cs, L.row, d, kTagS, want);
+                    publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
+                }
+            }
+        }
+    }
+#undef MAT
+#undef GEN
+    // ---- teardown ---------------------------------------------------------------------------------------------------
+    dbg(p, 0, 0xFF);
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// per-sample conditioning records of the role-specialised loop: CS[group][step][fold][8][512] fp32
+// (c1 r,z,n | c2 r,z,n | c3 | c4), same interpolation and FMA order as cond_expand.cuh.  grid = (folds, step blocks),
+// 512 threads = hidden units.
+__global__ void __launch_bounds__(512) expand_cond_rs_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2,
+                                                             const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
+                                                             const float* __restrict__ coef, const FoldDesc* __restrict__ folds, int S, int Ng,
+                                                             int cs_steps, int steps_per_block, float* __restrict__ CS) {
+    const int b = blockIdx.x, j = threadIdx.x;
+    const int g = b / Ng, row = b - g * Ng;
+    const FoldDesc fd = folds[b];
+    const int t0 = blockIdx.y * steps_per_block, t1 = min(S, t0 + steps_per_block);
+    float ta[8], tq[kTaps][7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ta[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < kTaps; ++d)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) tq[d][i] = 0.f;
+    int key = -1;
+    for (int t = t0; t < t1; ++t) {
+        const int n = fd.n0 + t;
+        const bool valid = n < fd.N;
+        const int q0 = valid ? n / kHop : 0;
+        const int want = valid ? (fd.tq_row0 + q0) : -2 - fd.ta_row0;
+        if (want != key) {
+            key = want;
+            const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
+            const float4 x1 = __ldg(TA1 + ra), x2 = __ldg(TA2 + ra);
+            ta[0] = x1.x; ta[1] = x1.y; ta[2] = x1.z; ta[3] = x1.w; ta[4] = x2.x; ta[5] = x2.y; ta[6] = x2.z; ta[7] = x2.w;
+            if (valid) {
+#pragma unroll
+                for (int d = 0; d < kTaps; ++d) {
+                    const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
+                    const float4 q1 = __ldg(TQ1 + rq), q2 = __ldg(TQ2 + rq);
+                    tq[d][0] = q1.x; tq[d][1] = q1.y; tq[d][2] = q1.z; tq[d][3] = q1.w; tq[d][4] = q2.x; tq[d][5] = q2.y; tq[d][6] = q2.z;
+                }
+            }
+        }
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = ta[i];
+        if (valid) {
+            const float* cf = coef + (n - q0 * kHop) * kTaps;
+#pragma unroll
+            for (int d = 0; d < kTaps; ++d) {
+                const float w = __ldg(cf + d);
+                if (w != 0.f) {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) a[i] = fmaf(w, tq[d][i], a[i]);
+                }
+            }
+        }
+        float* out = CS + (((size_t)g * cs_steps + (t % cs_steps)) * Ng + row) * 4096 + j;
+        __stcs(out + 0 * 512, a[0]); __stcs(out + 1 * 512, a[1]); __stcs(out + 2 * 512, a[2]);      // c1 r, z, n
+        __stcs(out + 3 * 512, a[4]); __stcs(out + 4 * 512, a[5]); __stcs(out + 5 * 512, a[6]);      // c2 r, z, n
+        __stcs(out + 6 * 512, a[3]); __stcs(out + 7 * 512, a[7]);                                    // c3 (fc1), c4 (fc2)
+    }
+}
+
+cudaError_t set_rs_deadline(long long cycles) { return cudaMemcpyToSymbol(g_rs_deadline, &cycles, sizeof(cycles)); }
+size_t loop_rs_image_bytes(int role) { return role == 0 ? (size_t)kW1 + 32 * 128 * 8 : (role == 1 ? (size_t)kWEnd : (size_t)64 * 128 * 8); }
+size_t loop_rs_exchange_bytes(int groups) { return (size_t)groups * kMats * kRsBufs * kMatChunks * 16; }
+
+cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
+                                  const FoldDesc* folds, int B, int S, int Ng, int cs_steps, float* CS, cudaStream_t stream) {
+    const int spb = 64;
+    dim3 grid(B, (S + spb - 1) / spb);
+    expand_cond_rs_kernel<<<grid, 512, 0, stream>>>(TA1, TA2, TQ1, TQ2, coef, folds, S, Ng, cs_steps, spb, CS);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
+    if (err != cudaSuccess) return err;
+    RsParams pp = p;
+    void* args[] = {&pp};
+    const int grid = p.G * kRsCtas;
+    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_rs_kernel, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
+}
+
+}  // namespace wrnn
