@@ -960,6 +960,8 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.w3 = e->wRs[2].as<unsigned char>(); rp.w4 = e->wRs[3].as<unsigned char>();
             rp.v1 = e->dv1; rp.v2 = e->dv2; rp.v3 = e->dv3; rp.bhn1 = e->dbhn1; rp.bhn2 = e->dbhn2; rp.bfc3 = e->dbfc3;
             rp.CS = e->bCS.as<float>(); rp.cs_steps = cs_steps; rp.Ng = Ng; rp.G = G;
+            rp.offpath_delay_ns = getenv("WRNN_RS_DELAY_NS") ? atoi(getenv("WRNN_RS_DELAY_NS")) : 2500;
+            rp.canary_all = getenv("WRNN_RS_CANARY_ALL") ? atoi(getenv("WRNN_RS_CANARY_ALL")) : 0;
             rp.folds = e->bFolds.as<FoldDesc>() + w0;
             rp.B = B; rp.S = S; rp.seed = rq->seed;
             rp.X = e->bRsExch.as<uint4>();
@@ -975,7 +977,28 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 memset(hdbg, 0, (size_t)G * kRsCtas * 32 * sizeof(int));
                 CU(cudaHostGetDevicePointer(&rp.dbg, hdbg, 0));
             }
+            const char* rs_trace = getenv("WRNN_RS_TRACE");
+            const size_t trace_n = (size_t)G * kRsCtas * 8 * 48;
+            if (rs_trace) {
+                CU(e->bFloor.ensure(trace_n * sizeof(unsigned long long)));
+                CU(cudaMemsetAsync(e->bFloor.p, 0, trace_n * sizeof(unsigned long long), st));
+                rp.trace = e->bFloor.as<unsigned long long>();
+            }
             CU(launch_loop_rs(rp, st));
+            if (rs_trace) {
+                std::vector<unsigned long long> tr(trace_n);
+                CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (FILE* f = fopen(rs_trace, "w")) {
+                    for (int c = 0; c < G * kRsCtas; ++c)
+                        for (int k = 0; k < 8; ++k) {
+                            fprintf(f, "%d %d", c, k);
+                            for (int j = 0; j < 48; ++j) fprintf(f, " %llu", tr[((size_t)c * 8 + k) * 48 + j]);
+                            fprintf(f, "\n");
+                        }
+                    fclose(f);
+                }
+            }
             if (hdbg) {
                 CU(cudaEventRecord(e->ev[7], st));
                 const auto t_dbg = std::chrono::steady_clock::now();

@@ -120,6 +120,8 @@ struct RsParams {
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
     const float* CS;             // per-sample conditioning [group][cs_steps][Ng][8][512] fp32 (expand_cond_rs_kernel)
     int cs_steps;
+    int canary_all;              // phase 1 of an ingest waits for all producers' canaries (1) or the first one (0)
+    int offpath_delay_ns;        // T1 waits this long before it reads h1(t) for the recurrent product (the T2 CTAs read it first)
     int Ng, G;                   // folds per group (<= 128), groups; fold f = row f % Ng of group f / Ng
     const FoldDesc* folds;
     int B, S;
@@ -132,6 +134,7 @@ struct RsParams {
     int* progress;
     int* abort_flag;
     int* dbg;                    // optional mapped host memory [CTA][32] checkpoints (WRNN_RS_DEBUG=1)
+    unsigned long long* trace;   // optional [CTA][8 steps][16 events] %globaltimer stamps (WRNN_RS_TRACE=path)
 };
 size_t loop_rs_image_bytes(int role);
 size_t loop_rs_exchange_bytes(int groups);

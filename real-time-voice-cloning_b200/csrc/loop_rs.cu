@@ -24,6 +24,7 @@
 // Every wait has a deadline ("soft abort", as loop_tc.cu): a bad build ends with an error code, never a hung GPU.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "engine_internal.h"
 #include "tc_common.cuh"
 
@@ -36,7 +37,7 @@ using namespace tc;
 
 constexpr int NW = 16;                        // ingest / epilogue warps: warp w = (lane quadrant q = w & 3, K quarter / column slice w >> 2)
 constexpr int NT = (NW + 4) * 32;             // + a service warpgroup: the MMA warp and three idle warps (setmaxnreg works on whole warpgroups)
-constexpr int kRegsEpi = 112, kRegsSvc = 32;  // after the hand-over: 16 x 112 + 4 x 32 = 20 x 96, the launch allocation (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
+constexpr int kRegsEpi = 104, kRegsSvc = 64;  // after the hand-over: 16 x 104 + 4 x 64 = 20 x 96, the launch allocation (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
 constexpr int kChunks = kRnn / 8;             // 64 chunks of 8 fp16 per activation row
 constexpr size_t kMatChunks = (size_t)kChunks * 128;     // one buffer of one exchange matrix: [chunk][fold] x 16 bytes = 128 KB
 enum { MH1 = 0, MH2, MS2, MF1, MF2, kMats };
@@ -76,10 +77,14 @@ __device__ __noinline__ bool spin_check(const RsParams& p, Ctl* c, long long& t0
     }
     return false;
 }
+// kSleep: the 16 ingest / epilogue warps wait for the accumulator while the MMA warp issues: every instruction they spend
+// polling is an issue slot the MMA warp does not get (measured: +30 clocks per MMA), so they back off between tries
+template <bool kSleep = false>
 __device__ __forceinline__ bool wait_mbar(const RsParams& p, Ctl* c, uint64_t* bar, uint32_t parity) {
     long long t0 = 0;
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (kSleep) __nanosleep(100);
         if (((++spins) & 15) == 0 && aborted_local(c)) return false;
         if ((spins & 1023) == 0 && spin_check(p, c, t0)) return false;
     }
@@ -90,6 +95,26 @@ __device__ __forceinline__ bool wait_mbar(const RsParams& p, Ctl* c, uint64_t* b
 __device__ __forceinline__ void dbg(const RsParams& p, int t, int code) {
     if (p.dbg && (threadIdx.x & 31) == 0) {
         *reinterpret_cast<volatile int*>(p.dbg + blockIdx.x * 32 + (threadIdx.x >> 5)) = (t << 8) | code;
+    }
+}
+
+// optional timeline (WRNN_RS_TRACE=path): %globaltimer (ns, common to all SMs) of steps [kTraceStep0, +kTraceSteps) per CTA,
+// written by lane 0 of warp 0 (events 0..8) and of the MMA warp (9..12): [CTA][step][16]
+constexpr int kTraceStep0 = 96, kTraceSteps = 8;
+__device__ __forceinline__ void trace(const RsParams& p, int t, int ev) {
+    if (p.trace && (threadIdx.x == 0 || threadIdx.x == NW * 32) && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + ev] = ns;
+    }
+}
+
+// per-K-quarter events of the first ingest of a step: lane 0 of warps (q = 0, cs): slots 16 + 4 cs + {0 canaries, 1 loaded, 2 in TMEM}
+__device__ __forceinline__ void trace_kq(const RsParams& p, int t, int ev0, int cs, int k) {
+    if (p.trace && ev0 == 1 && (threadIdx.x & 127) == 0 && threadIdx.x < NW * 32 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 16 + 4 * cs + k] = ns;
     }
 }
 
@@ -104,11 +129,11 @@ __device__ __forceinline__ void st_chunk(uint4* p, uint4 v) {
 __device__ __forceinline__ bool tags_ok(uint4 v, uint32_t tb, uint32_t want) {
     return ((((v.x ^ want) | (v.y ^ want) | (v.z ^ want) | (v.w ^ want)) & tb) == 0u);
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+        "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -120,6 +145,16 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+template <bool kAcc>
+__device__ __forceinline__ void umma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    if (kAcc)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -145,63 +180,93 @@ struct Lane {
 // [16 kq, 16 kq + 16) of its 32 folds.  `extra` (optional): one more chunk of my row, returned to the caller (T2: my own
 // units of h1).  Lanes 0..15 first poll one canary chunk each (chunk 16 kq + lane of row 32 q + lane), then every lane
 // loads its 16 chunks once and re-polls the ones whose generation bits do not match yet.
-__device__ __forceinline__ void ingest(const RsParams& p, Ctl* ctl, const Lane& L, const uint4* mat, uint32_t tb, uint32_t want, int nrows,
-                                       int extra_chunk, uint4& extra, int dbg_t) {
+// (inlined on purpose: as a real call the ABI spills around it cost more than the code size saves -- 25.8 vs 19.2 us per step)
+struct IngestOut { uint4 extra; float x; };
+__device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const Lane& L, const uint4* mat, uint32_t tb, uint32_t want,
+                                         int extra_chunk, int dbg_t, int ev0, const unsigned long long* xw, uint32_t xtag) {
+    uint4 extra;
+    float xval = 0.f;
     const uint4* base = mat + (size_t)(L.cs * 16) * 128 + L.row;
     dbg(p, dbg_t, 0x10);
-    {   // canaries
-        const int crow = 32 * L.q + L.lane;
-        const bool poll = L.lane < 16 && crow < nrows;
-        const uint4* cp = mat + (size_t)(L.cs * 16 + (L.lane & 15)) * 128 + crow;
+    {   // phase 1: one canary chunk per lane (chunk 16 kq + (lane & 15) of my own row) until the first producer of this K
+        // quarter shows this step's generation (p.canary_all: until all do) -- one light load per lane and pass while the data
+        // is still far away; the full passes of phase 2 then overlap the arrival of the remaining producers
+        const uint4* cp = mat + (size_t)(L.cs * 16 + (L.lane & 15)) * 128 + L.row;
         long long t0 = 0;
         int spins = 0;
-        bool ok = !poll;
-        while (true) {
-            if (!ok) ok = tags_ok(ld_chunk(cp), tb, want);
-            if (__all_sync(0xffffffffu, ok)) break;
+        const bool any_live = __any_sync(0xffffffffu, L.live);
+        bool ok = !L.live;
+        while (any_live) {
+            if (!ok || !p.canary_all) ok = L.live ? tags_ok(ld_chunk(cp), tb, want) : p.canary_all != 0;
+            if (p.canary_all ? __all_sync(0xffffffffu, ok) : __any_sync(0xffffffffu, ok)) break;
             const bool quit = ((++spins) & 255) == 0 && spin_check(p, ctl, t0);     // (spins is warp-uniform)
             if (__any_sync(0xffffffffu, quit)) break;
         }
     }
     dbg(p, dbg_t, 0x11);
+    trace(p, dbg_t, ev0);
+    trace_kq(p, dbg_t, ev0, L.cs, 0);
+    unsigned long long xword = 0ull;
+    if (xw) xword = ll_load(xw);            // the sample word was published before this matrix: its load rides along with phase 2
+    // phase 2: full passes (16 loads at immediate offsets, one OR-reduction of the generation bits) until everything matches.
+    // Lean on purpose: at 16 warps per SM every instruction of this path costs ~4 clocks of the step.
     uint4 v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* xp = mat + (size_t)(extra_chunk >= 0 ? extra_chunk : 0) * 128 + L.row;
     extra = make_uint4(0u, 0u, 0u, 0u);
-    if (L.live) {
-        uint32_t pending = extra_chunk >= 0 ? 0x1FFFFu : 0xFFFFu;
+    int passes = 0;
+    {
         long long t0 = 0;
         int spins = 0;
-        while (pending) {
+        uint32_t bad;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if ((pending >> i) & 1u) v[i] = ld_chunk(base + (size_t)i * 128);
-            if ((pending >> 16) & 1u) extra = ld_chunk(mat + (size_t)extra_chunk * 128 + L.row);
+        for (int i = 0; i < 16; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        do {
+            ++passes;
+            if (L.live) {          // (padding rows are not fetched: the pass is bound by the SM's ~90 B/clk from L2)
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (((pending >> i) & 1u) && tags_ok(v[i], tb, want)) pending &= ~(1u << i);
-            if (((pending >> 16) & 1u) && tags_ok(extra, tb, want)) pending &= ~(1u << 16);
-            if (pending && ((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
-        }
+                for (int i = 0; i < 16; ++i) v[i] = ld_chunk(base + i * 128);
+                if (extra_chunk >= 0) extra = ld_chunk(xp);
+            }
+            bad = (extra_chunk >= 0) ? ((extra.x ^ want) | (extra.y ^ want) | (extra.z ^ want) | (extra.w ^ want)) : 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bad |= (v[i].x ^ want) | (v[i].y ^ want) | (v[i].z ^ want) | (v[i].w ^ want);
+            bad = L.live ? (bad & tb) : 0u;
+        } while (bad != 0u && !(((++spins) & 255) == 0 && spin_check(p, ctl, t0)));
     }
     __syncwarp();
     dbg(p, dbg_t, 0x12);
-    uint32_t r[16];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            r[4 * i + 0] = v[4 * j + i].x & ~tb; r[4 * i + 1] = v[4 * j + i].y & ~tb;
-            r[4 * i + 2] = v[4 * j + i].z & ~tb; r[4 * i + 3] = v[4 * j + i].w & ~tb;
+    trace(p, dbg_t, ev0 + 1);
+    trace_kq(p, dbg_t, ev0, L.cs, 1);
+    if (p.trace && threadIdx.x == 0 && dbg_t >= kTraceStep0 && dbg_t < kTraceStep0 + kTraceSteps)
+        p.trace[((size_t)blockIdx.x * kTraceSteps + (dbg_t - kTraceStep0)) * 48 + (ev0 == 1 ? 13 : 14)] = (unsigned long long)passes;
+    if (xw) {
+        long long t0 = 0;
+        int spins = 0;
+        while (L.live && ll_tag(xword) != xtag) {
+            xword = ll_load(xw);
+            if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
         }
-        tmem_st16(L.tlane + kColA + (uint32_t)(L.cs * 64 + j * 16), r);
+        xval = L.live ? ll_val(xword) : 0.f;
     }
-    extra.x &= ~tb; extra.y &= ~tb; extra.z &= ~tb; extra.w &= ~tb;
+    if (want != 0u) {          // generation 1: the bit is set in every half; take it out (generation 0 needs nothing)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i].x ^= tb; v[i].y ^= tb; v[i].z ^= tb; v[i].w ^= tb; }
+        extra.x ^= tb; extra.y ^= tb; extra.z ^= tb; extra.w ^= tb;
+    }
+    if (__any_sync(0xffffffffu, L.live)) {       // (a quadrant of padding rows keeps whatever it holds: its accumulator rows are never read)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_st16(L.tlane + kColA + (uint32_t)(L.cs * 64 + j * 16), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
     tmem_st_wait();
     tcgen05_fence_before();
     __syncwarp();
     if (L.lane == 0) mbar_arrive(&ctl->abar[L.cs]);
     dbg(p, dbg_t, 0x13);
+    trace(p, dbg_t, ev0 + 2);
+    trace_kq(p, dbg_t, ev0, L.cs, 2);
+    IngestOut o;
+    o.extra = extra; o.x = xval;
+    return o;
 }
 
 // Publish 8 values of my fold as one chunk (generation bit in every half).
@@ -212,34 +277,72 @@ __device__ __forceinline__ void publish8(uint4* mat, int chunk, int row, const f
     st_chunk(mat + (size_t)chunk * 128 + row, w);
 }
 
-// the MOL draw of one fold from its 30 outputs (vocoder/distribution.py:104-140; same arithmetic as loop_tc.cu)
-__device__ __forceinline__ float mol_draw(const float* lg, const float* sbias, uint32_t t, uint32_t fold, uint32_t utt, uint2 key) {
-    float best = -INFINITY;
-    int kbest = 0;
+// the MOL draw of one fold from its 30 outputs (vocoder/distribution.py:104-140; same arithmetic as loop_tc.cu), in two
+// halves: the noise depends on (step, fold) only and is drawn while the step's activations are still travelling
+struct MolNoise { float gum[10]; float lnoise; };
+__device__ __forceinline__ void mol_noise(MolNoise& nz, uint32_t t, uint32_t fold, uint32_t utt, uint2 key) {
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const uint4 r = philox4x32_10(make_uint4(t, fold, utt, (uint32_t)b), key);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int i = 4 * b + w;
-            if (i < 10) {
-                const float um = 1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f);
-                const float sc = lg[i] + sbias[i] - __logf(-__logf(um));
-                if (sc > best) { best = sc; kbest = i; }
-            }
+            if (i < 10) nz.gum[i] = -__logf(-__logf(1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f)));
         }
         if (b == 2) {
-            float mean = 0.f, lsc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 10; ++i)
-                if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
-            lsc = fmaxf(lsc, -32.23619130191664f);
             const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
-            const float xs = mean + __expf(lsc) * (__logf(ul) - __logf(1.0f - ul));
-            return fminf(fmaxf(xs, -1.0f), 1.0f);
+            nz.lnoise = __logf(ul) - __logf(1.0f - ul);
         }
     }
-    return 0.f;
+}
+__device__ __forceinline__ float mol_draw(const float* lg, const float* sbias, const MolNoise& nz) {
+    float best = -INFINITY;
+    int kbest = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const float sc = lg[i] + sbias[i] + nz.gum[i];
+        if (sc > best) { best = sc; kbest = i; }
+    }
+    float mean = 0.f, lsc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
+    lsc = fmaxf(lsc, -32.23619130191664f);
+    const float xs = mean + __expf(lsc) * nz.lnoise;
+    return fminf(fmaxf(xs, -1.0f), 1.0f);
+}
+
+// One MMA job: D[128 folds x N] = A (TMEM, 512 fp16 per lane) x W^T (shared memory tile [k-block][N][64]); issued K quarter by K
+// quarter as the ingest warps deliver them.  Whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one); a K
+// step is one add on the descriptor and one UTCHMMA.  One rolled copy of the code for every job of every role.
+__device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t w_smem, uint32_t N, uint32_t d, uint32_t a0, uint32_t a_par,
+                                     uint64_t* done, bool wait_e, uint32_t e_par, int tt, int ev) {
+    const uint32_t idesc = umma_idesc_f16(128, (int)N);
+    const uint64_t bd0 = umma_desc_sw128(w_smem);
+    const uint32_t kb_step = N * 8u;                      // one k-block of the tile, in descriptor units of 16 bytes
+    // The four K quarters reach TMEM within ~0.3 us of each other, and one wait + fence + elect round costs as much as
+    // eight MMAs: wait for all four, then issue the 32 K steps in one go.
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) wait_mbar(p, ctl, &ctl->abar[kq], a_par);
+    if (wait_e) wait_mbar(p, ctl, &ctl->ebar, e_par);
+    tcgen05_fence_after();
+    trace(p, tt, ev);
+    if (elect_one()) {
+        uint64_t bd = bd0;
+        uint32_t a = a0;
+#pragma unroll 1
+        for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_ts(d, a, bd + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                a += 8u;
+            }
+            bd += kb_step;
+        }
+        umma_commit(done);
+    }
+    __syncwarp();
+    trace(p, tt, ev + 1);
 }
 
 }  // namespace
@@ -303,38 +406,22 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         // whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one).  A job = 32 K-steps over the A operand
         // in TMEM, issued K quarter by K quarter as the ingest warps deliver them.
         uint32_t n_ingest = 0;
-        auto job = [&](uint32_t dcol, uint32_t wofs, uint32_t N, uint64_t* done, bool wait_e, uint32_t e_par) {
-            const uint32_t idesc = umma_idesc_f16(128, (int)N);
-            for (int kq = 0; kq < 4; ++kq) {
-                dbg(p, (int)n_ingest, 0x20 + kq);
-                wait_mbar(p, ctl, &ctl->abar[kq], n_ingest & 1u);
-                if (kq == 0 && wait_e) wait_mbar(p, ctl, &ctl->ebar, e_par);
-                tcgen05_fence_after();
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int kk = kq * 8 + k;
-                        const uint64_t bd = umma_desc_advance(umma_desc_sw128(smem_u32(smem + wofs + (uint32_t)(kk >> 2) * N * 128u)), (uint32_t)(kk & 3) * 32u);
-                        umma_ts(tmem + dcol, tmem + kColA + (uint32_t)kk * 8u, bd, idesc, kk > 0 ? 1u : 0u);
-                    }
-                    if (kq == 3) umma_commit(done);
-                }
-                __syncwarp();
-            }
+        auto job = [&](uint32_t N, uint32_t dcol, uint32_t wofs, uint64_t* done, bool wait_e, uint32_t e_par, int tt, int ev) {
+            mma_job(p, ctl, smem_u32(smem + wofs), N, tmem + dcol, tmem + kColA, n_ingest & 1u, done, wait_e, e_par, tt, ev);
             ++n_ingest;
         };
         if (role == 0) {
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
-                if (t > 0) job(kColD1, kW1, 32, &ctl->dbar[0], false, 0);                       // fc3 f2(t-1)
-                if (t < S) job(kColD0, kW0, 96, &ctl->dbar[1], true, (uint32_t)t & 1u);         // W_hh1 h1(t)
+                if (t > 0) job(32u, kColD1, kW1, &ctl->dbar[0], false, 0, t, 9);                       // fc3 f2(t-1)
+                if (t < S) job(96u, kColD0, kW0, &ctl->dbar[1], true, (uint32_t)t & 1u, t, 11);         // W_hh1 h1(t)
             }
         } else if (role == 1) {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                job(kColD0, kW0, 96, &ctl->dbar[0], false, 0);                                  // W_ih2a h1(t)
-                job(kColD1, kW1, 96, &ctl->dbar[1], true, (uint32_t)t & 1u);                    // W_hh2 h2(t)
+                job(96u, kColD0, kW0, &ctl->dbar[0], false, 0, t, 9);                             // W_ih2a h1(t)
+                job(96u, kColD1, kW1, &ctl->dbar[1], true, (uint32_t)t & 1u, t, 11);                    // W_hh2 h2(t)
             }
         } else {
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(kColD0, kW0, 64, &ctl->dbar[0], false, 0);          // fc1a s2(t) / fc2 f1(t)
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(64u, kColD0, kW0, &ctl->dbar[0], false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
         }
         }
     } else {
@@ -344,14 +431,13 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         Lane L;
         L.q = warp & 3; L.cs = warp >> 2; L.lane = lane; L.row = 32 * L.q + lane; L.live = L.row < nrows;
         L.tlane = tmem + ((uint32_t)(32 * L.q) << 16);
+        const bool warp_live = 32 * L.q < nrows;       // a warp whose 32 rows are all padding skips the arithmetic (frees issue slots)
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         const FoldDesc fd = p.folds[L.live ? fold0 + L.row : 0];
         const size_t srow = (size_t)(fold0 + L.row) * S;                     // my fold's row of samples / forced
         unsigned long long* const xw = p.bX + (size_t)g * 128 + L.row;
         const float* const csrow = p.CS + ((size_t)g * p.cs_steps * p.Ng + L.row) * 4096;   // + (t % cs_steps) * Ng * 4096
         const size_t cs_step = (size_t)p.Ng * 4096;
-        uint4 extra;
-
         if (role == 0) {
             // ---- T1: fc3 + draw of step t-1, GRU1 of step t, then the recurrent product for step t+1 -----------------------
             float h1[8];
@@ -360,6 +446,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             const float* v1 = cst + L.cs * 8;                    // [a][32]: + 32 a
             const float* sbias = cst + 128;
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
+                trace(p, t, 0);
                 float c1[24];
                 if (t < S && L.live) {
                     const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs;
@@ -375,17 +462,20 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 }
                 float x = 0.f;
                 if (t > 0) {
+                    MolNoise nz;
+                    if (warp_live) mol_noise(nz, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
                     // the A buffer is free once the recurrent job of step t-1 has completed
                     wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
-                    ingest(p, ctl, L, MAT(MF2, t - 1), kTagS, GEN(t - 1) ? kTagS : 0u, nrows, -1, extra, t);
-                    wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)(t - 1) & 1u);
+                    ingest(p, ctl, L, MAT(MF2, t - 1), kTagS, GEN(t - 1) ? kTagS : 0u, -1, t, 1, nullptr, 0u);
+                    wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
+                    trace(p, t, 4);
                     float lg[32];
                     tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
                     tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
                     tmem_ld_wait();
-                    const float xs = mol_draw(lg, sbias, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
+                    const float xs = warp_live ? mol_draw(lg, sbias, nz) : 0.f;
                     x = xs;
                     if (L.live) {
                         if (p.forced) x = p.forced[srow + t - 1];
@@ -410,6 +500,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->ebar);
+                if (warp_live) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float r = sigmoid_fast(fmaf(v1[i], x, c1[i]) + gh[i]);
@@ -418,8 +509,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     h1[i] = (1.0f - z) * n + z * h1[i];
                 }
                 if (L.live) publish8(MAT(MH1, t), 4 * cta + L.cs, L.row, h1, kTagE, GEN(t) ? kTagE : 0u);
-                // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited)
-                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, nrows, -1, extra, t);
+                }
+                trace(p, t, 5);
+                // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited).
+                // Off the critical path: wait until the T2 CTAs have read the same lines for the on-path product.
+                __nanosleep(p.offpath_delay_ns);
+                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
                 if (cta == 0 && g == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
                     *reinterpret_cast<volatile int*>(p.progress) = t;
                     __threadfence_system();
@@ -432,6 +527,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             for (int i = 0; i < 8; ++i) h2[i] = 0.f;
             const float* v2 = cst + L.cs * 8;
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                trace(p, t, 0);
                 float c2[24];
                 if (L.live) {
                     const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs;
@@ -449,21 +545,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
                 }
-                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, nrows, 4 * cta + L.cs, extra, t);
-                float x = 0.f;
-                if (t > 0 && L.live) {
-                    long long t0 = 0;
-                    int spins = 0;
-                    while (true) {
-                        const unsigned long long w = ll_load(xw);
-                        if (ll_tag(w) == (uint32_t)t) { x = ll_val(w); break; }
-                        if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
-                    }
-                }
+                const IngestOut io = ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, 4 * cta + L.cs, t, 1, t > 0 ? xw : nullptr, (uint32_t)t);
+                const float x = io.x;
+                const uint4 extra = io.extra;
                 dbg(p, t, 0x30);
-                wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
+                wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
                 tcgen05_fence_after();
                 dbg(p, t, 0x31);
+                trace(p, t, 4);
                 float pb[24], gh[24];
                 tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, pb); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, pb + 8);
                 tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, pb + 16);
@@ -481,6 +570,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 float s2[8];
                 const float2 e0 = unpack2(extra.x), e1 = unpack2(extra.y), e2 = unpack2(extra.z), e3 = unpack2(extra.w);
                 const float h1o[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+                if (warp_live) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float r = sigmoid_fast(pb[i] + fmaf(v2[i], x, c2[i]) + gh[i]);
@@ -493,13 +583,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     publish8(MAT(MS2, t), 4 * cta + L.cs, L.row, s2, kTagE, GEN(t) ? kTagE : 0u);
                     publish8(MAT(MH2, t), 4 * cta + L.cs, L.row, h2, kTagE, GEN(t) ? kTagE : 0u);
                 }
-                ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, nrows, -1, extra, t);
+                }
+                trace(p, t, 5);
+                ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
             }
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
             const bool fc1 = role == 2;
             const float* v3 = cst + L.cs * 16;
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                trace(p, t, 0);
                 float cc[16];
                 if (L.live) {
                     const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + 64 * cta + 16 * L.cs);
@@ -509,19 +602,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; ++i) cc[i] = 0.f;
                 }
-                ingest(p, ctl, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t) ? (fc1 ? kTagE : kTagS) : 0u, nrows, -1, extra, t);
-                float x = 0.f;
-                if (fc1 && t > 0 && L.live) {
-                    long long t0 = 0;
-                    int spins = 0;
-                    while (true) {
-                        const unsigned long long w = ll_load(xw);
-                        if (ll_tag(w) == (uint32_t)t) { x = ll_val(w); break; }
-                        if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
-                    }
-                }
-                wait_mbar(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
+                const float x = ingest(p, ctl, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t) ? (fc1 ? kTagE : kTagS) : 0u, -1, t, 1,
+                                       (fc1 && t > 0) ? xw : nullptr, (uint32_t)t).x;
+                wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
                 tcgen05_fence_after();
+                trace(p, t, 4);
                 float d[16];
                 tmem_ld8(L.tlane + kColD0 + 16 * L.cs, d); tmem_ld8(L.tlane + kColD0 + 16 * L.cs + 8, d + 8);
                 tmem_ld_wait();
@@ -534,6 +619,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     publish8(m, 8 * cta + 2 * L.cs, L.row, d, kTagS, want);
                     publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
                 }
+                trace(p, t, 5);
             }
         }
     }
