@@ -938,16 +938,34 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             e->launches += 1;
         } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wRs[0].p && B <= rs_max_folds) {
             // ---- role-specialised tensor-core loop (loop_rs.cu): the latency-bound regime, <= 128 folds per 48-CTA group ---------
-            int G = std::min(rs_groups_max, std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
+            // groups: two leave 52 SMs to the expanders (three groups run the loop 4 % faster but starve them)
+            int G = std::min(std::min(rs_groups_max, 2), std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
+            G = std::max(G, (B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup);
             if (const char* ev = getenv("WRNN_RS_GROUPS")) G = std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, std::min(rs_groups_max, atoi(ev)));
             const int Ng = (B + G - 1) / G;
-            const int cs_steps = S;
+            // Conditioning records (16 KB per fold and step) are produced INSIDE the loop kernel by expander CTAs on the SMs the
+            // groups leave free, into a ring sized to stay resident in L2 (WRNN_RS_RING_MB, default 56 MB): produced / consumed
+            // counters per chunk of kRsChunk steps order the two sides.  WRNN_RS_EXPAND=0 (or no SM left): the whole table is
+            // expanded before the launch.
+            const int n_exp = e->n_sms - G * kRsCtas;
+            const bool ring = n_exp >= 1 && !(getenv("WRNN_RS_EXPAND") && atoi(getenv("WRNN_RS_EXPAND")) == 0);
+            const int nchunks = (S + kRsChunk - 1) / kRsChunk;
+            int cs_steps = nchunks * kRsChunk;
+            if (ring) {
+                const size_t chunk_bytes = (size_t)G * Ng * 4096 * sizeof(float) * kRsChunk;
+                const size_t budget = (size_t)(getenv("WRNN_RS_RING_MB") ? atoll(getenv("WRNN_RS_RING_MB")) : 56) << 20;
+                const int ring_chunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(3, budget / chunk_bytes));
+                cs_steps = ring_chunks * kRsChunk;
+            }
             const size_t cs_bytes = (size_t)G * cs_steps * Ng * 4096 * sizeof(float);
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
             CU(e->bCS.ensure(cs_bytes));
+            CU(e->bCsDone.ensure((size_t)2 * nchunks * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(e->bCsDone.p, 0, (size_t)2 * nchunks * sizeof(unsigned int), st));
             CU(cudaEventRecord(e->evx[0], st));
-            CU(launch_expand_cond_rs(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
-                                     e->bFolds.as<FoldDesc>() + w0, B, S, Ng, cs_steps, e->bCS.as<float>(), st));
+            if (!ring)
+                CU(launch_expand_cond_rs(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
+                                         e->bFolds.as<FoldDesc>() + w0, B, S, Ng, cs_steps, e->bCS.as<float>(), st));
             CU(cudaEventRecord(e->evx[1], st));
             expanded = true;
             const size_t xbytes = loop_rs_exchange_bytes(G), wbytes = (size_t)G * 128 * sizeof(unsigned long long);
@@ -960,6 +978,14 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.w3 = e->wRs[2].as<unsigned char>(); rp.w4 = e->wRs[3].as<unsigned char>();
             rp.v1 = e->dv1; rp.v2 = e->dv2; rp.v3 = e->dv3; rp.bhn1 = e->dbhn1; rp.bhn2 = e->dbhn2; rp.bfc3 = e->dbfc3;
             rp.CS = e->bCS.as<float>(); rp.cs_steps = cs_steps; rp.Ng = Ng; rp.G = G;
+            if (ring) {
+                rp.cs_done = e->bCsDone.as<unsigned int>(); rp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
+                rp.CSw = e->bCS.as<float>();
+                rp.TA1 = e->bTA1.as<float4>(); rp.TA2 = e->bTA2.as<float4>(); rp.TQ1 = e->bTQ1.as<float4>(); rp.TQ2 = e->bTQ2.as<float4>();
+                rp.coef = e->dcoef;
+                rp.n_expanders = n_exp;
+                if (const char* ev = getenv("WRNN_RS_EXPANDERS")) rp.n_expanders = std::max(1, std::min(n_exp, atoi(ev)));
+            }
             rp.offpath_delay_ns = getenv("WRNN_RS_DELAY_NS") ? atoi(getenv("WRNN_RS_DELAY_NS")) : 2500;
             rp.canary_all = getenv("WRNN_RS_CANARY_ALL") ? atoi(getenv("WRNN_RS_CANARY_ALL")) : 0;
             rp.folds = e->bFolds.as<FoldDesc>() + w0;

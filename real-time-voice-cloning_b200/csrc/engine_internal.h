@@ -115,11 +115,18 @@ constexpr int kRsT1 = 16, kRsT2 = 16, kRsT3 = 8, kRsT4 = 8;     // CTAs per role
 constexpr int kRsCtas = kRsT1 + kRsT2 + kRsT3 + kRsT4;          // one group
 constexpr int kRsBufs = 2;                                      // exchange matrices are double-buffered by step parity
 constexpr int kRsMaxFoldsPerGroup = 128;
+constexpr int kRsChunk = 4;                                     // steps per chunk of conditioning records (granularity of the ring's counters)
 struct RsParams {
     const unsigned char *w1, *w2, *w3, *w4;   // per-role weight images [CTA][loop_rs_image_bytes(role)], shared-memory layout
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;
     const float* CS;             // per-sample conditioning [group][cs_steps][Ng][8][512] fp32 (expand_cond_rs_kernel)
-    int cs_steps;
+    int cs_steps;                // steps the ring holds (a multiple of kRsChunk; == the padded S when everything is expanded up front)
+    // expander CTAs past the groups (cs_done != nullptr): per-frame tables in, records out, one produced / consumed counter per chunk
+    unsigned int *cs_done, *cs_consumed;
+    float* CSw;
+    const float4 *TA1, *TA2, *TQ1, *TQ2;
+    const float* coef;
+    int n_expanders;
     int canary_all;              // phase 1 of an ingest waits for all producers' canaries (1) or the first one (0)
     int offpath_delay_ns;        // T1 waits this long before it reads h1(t) for the recurrent product (the T2 CTAs read it first)
     int Ng, G;                   // folds per group (<= 128), groups; fold f = row f % Ng of group f / Ng

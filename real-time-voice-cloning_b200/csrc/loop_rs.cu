@@ -345,6 +345,60 @@ __device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t w_
     trace(p, tt, ev + 1);
 }
 
+// Per-sample conditioning records of the role-specialised loop: CS[group][step % cs_steps][fold][8][512] fp32
+// (c1 r,z,n | c2 r,z,n | c3 | c4), same interpolation and FMA order as cond_expand.cuh.  One call = steps [t0, t1) of one
+// fold by 512 threads (thread j = hidden unit j); every store is a coalesced 128 bytes per warp.
+__device__ __forceinline__ void expand_item_rs(const float4* __restrict__ TA1, const float4* __restrict__ TA2, const float4* __restrict__ TQ1,
+                                               const float4* __restrict__ TQ2, const float* __restrict__ coef, const FoldDesc& fd, int g, int row,
+                                               int t0, int t1, int cs_steps, int Ng, float* __restrict__ CS, int j) {
+    float ta[8], tq[kTaps][7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ta[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < kTaps; ++d)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) tq[d][i] = 0.f;
+    int key = -1;
+    for (int t = t0; t < t1; ++t) {
+        const int n = fd.n0 + t;
+        const bool valid = n < fd.N;
+        const int q0 = valid ? n / kHop : 0;
+        const int want = valid ? (fd.tq_row0 + q0) : -2 - fd.ta_row0;
+        if (want != key) {
+            key = want;
+            const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
+            const float4 x1 = __ldg(TA1 + ra), x2 = __ldg(TA2 + ra);
+            ta[0] = x1.x; ta[1] = x1.y; ta[2] = x1.z; ta[3] = x1.w; ta[4] = x2.x; ta[5] = x2.y; ta[6] = x2.z; ta[7] = x2.w;
+            if (valid) {
+#pragma unroll
+                for (int d = 0; d < kTaps; ++d) {
+                    const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
+                    const float4 q1 = __ldg(TQ1 + rq), q2 = __ldg(TQ2 + rq);
+                    tq[d][0] = q1.x; tq[d][1] = q1.y; tq[d][2] = q1.z; tq[d][3] = q1.w; tq[d][4] = q2.x; tq[d][5] = q2.y; tq[d][6] = q2.z;
+                }
+            }
+        }
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = ta[i];
+        if (valid) {
+            const float* cf = coef + (n - q0 * kHop) * kTaps;
+#pragma unroll
+            for (int d = 0; d < kTaps; ++d) {
+                const float w = cf[d];
+                if (w != 0.f) {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) a[i] = fmaf(w, tq[d][i], a[i]);
+                }
+            }
+        }
+        float* out = CS + (((size_t)g * cs_steps + (t % cs_steps)) * Ng + row) * 4096 + j;
+        __stcs(out + 0 * 512, a[0]); __stcs(out + 1 * 512, a[1]); __stcs(out + 2 * 512, a[2]);      // c1 r, z, n
+        __stcs(out + 3 * 512, a[4]); __stcs(out + 4 * 512, a[5]); __stcs(out + 5 * 512, a[6]);      // c2 r, z, n
+        __stcs(out + 6 * 512, a[3]); __stcs(out + 7 * 512, a[7]);                                    // c3 (fc1), c4 (fc2)
+    }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_constant__ RsParams p) {
@@ -358,9 +412,51 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : rc - kRsT1 - kRsT2 - kRsT3));
     const int fold0 = g * p.Ng, nrows = max(0, min(p.Ng, p.B - fold0));
     const int S = p.S;
+    const bool expander = (int)blockIdx.x >= p.G * kRsCtas;        // CTAs past the groups produce the conditioning records
+    const unsigned int consumers = (unsigned int)(p.G * kRsCtas * NW);   // warps that read every record chunk
+
+    if (expander) {
+        // =================================== conditioning expander ==========================================================
+        // work item = (chunk of kRsChunk steps, fold), chunk-major, so chunks complete in the order the loop consumes them;
+        // CS is a ring of cs_steps steps (L2-resident by construction: engine.cu sizes it), refilled behind the loop:
+        // cs_done[c] counts the folds of chunk c that are written, cs_consumed[c] the consumer warps that have read it.
+        if (tid == 0) ctl->abort_local = 0;
+        for (int i = tid; i < kHop * kTaps; i += NT) reinterpret_cast<float*>(smem)[i] = p.coef[i];
+        __syncthreads();
+        if (warp < NW) {
+            const float* coef_s = reinterpret_cast<const float*>(smem);
+            const int e_idx = (int)blockIdx.x - p.G * kRsCtas;
+            const int nchunks = (S + kRsChunk - 1) / kRsChunk, ring_chunks = p.cs_steps / kRsChunk;
+            const long long nitems = (long long)nchunks * p.B;
+            int waited = -1;
+            for (long long it = e_idx; it < nitems && !aborted_local(ctl); it += p.n_expanders) {
+                const int c = (int)(it / p.B), b = (int)(it - (long long)c * p.B);
+                if (c >= ring_chunks && c != waited) {          // chunk c overwrites chunk c - ring_chunks: every consumer must be past it
+                    waited = c;
+                    if (tid == 0) {
+                        long long t0 = 0;
+                        int spins = 0;
+                        while (true) {
+                            unsigned int v;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cs_consumed + (c - ring_chunks)) : "memory");
+                            if (v >= consumers) break;
+                            __nanosleep(200);
+                            if (((++spins) & 63) == 0 && spin_check(p, ctl, t0)) break;
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+                }
+                expand_item_rs(p.TA1, p.TA2, p.TQ1, p.TQ2, coef_s, p.folds[b], b / p.Ng, b % p.Ng, c * kRsChunk, min(S, (c + 1) * kRsChunk),
+                               p.cs_steps, p.Ng, p.CSw, tid);
+                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+                if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_done + c) : "memory");
+            }
+        }
+        return;
+    }
 
     // ---- one-time setup: weight tiles, constants, barriers, TMEM ------------------------------------------------------
-    {
+    if ((int)blockIdx.x < p.G * kRsCtas) {
         const unsigned char* img = role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
                                  : role == 1 ? p.w2 + (size_t)cta * kWEnd
                                  : role == 2 ? p.w3 + (size_t)cta * (64 * 128 * 8) : p.w4 + (size_t)cta * (64 * 128 * 8);
@@ -385,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         ctl->abort_local = 0;
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&ctl->tmem, 512);
+    if (warp == 0 && (int)blockIdx.x < p.G * kRsCtas) tmem_alloc(&ctl->tmem, 512);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -438,6 +534,29 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         unsigned long long* const xw = p.bX + (size_t)g * 128 + L.row;
         const float* const csrow = p.CS + ((size_t)g * p.cs_steps * p.Ng + L.row) * 4096;   // + (t % cs_steps) * Ng * 4096
         const size_t cs_step = (size_t)p.Ng * 4096;
+        // the expanders run a few chunks ahead: before the first step of a chunk, lane 0 acquires its counter
+        auto cs_wait = [&](int t) {
+            if (p.cs_done && (t % kRsChunk) == 0) {
+                if (lane == 0) {
+                    long long t0 = 0;
+                    int spins = 0;
+                    while (true) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cs_done + t / kRsChunk) : "memory");
+                        if (v >= (unsigned int)p.B) break;
+                        if (((++spins) & 63) == 0 && spin_check(p, ctl, t0)) break;
+                    }
+                }
+                __syncwarp();
+            }
+        };
+        // ... and after the last step of a chunk (its records are in registers and used) the warp hands the ring slot back
+        auto cs_release = [&](int t) {
+            if (p.cs_done && ((t % kRsChunk) == kRsChunk - 1 || t == S - 1)) {
+                __syncwarp();
+                if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_consumed + t / kRsChunk) : "memory");
+            }
+        };
         if (role == 0) {
             // ---- T1: fc3 + draw of step t-1, GRU1 of step t, then the recurrent product for step t+1 -----------------------
             float h1[8];
@@ -448,11 +567,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
                 trace(p, t, 0);
                 float c1[24];
+                if (t < S) cs_wait(t);
                 if (t < S && L.live) {
                     const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const float4 lo = __ldcs(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcs(reinterpret_cast<const float4*>(c + a * 512) + 1);
+                        const float4 lo = __ldcg(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcg(reinterpret_cast<const float4*>(c + a * 512) + 1);
                         c1[8 * a + 0] = lo.x; c1[8 * a + 1] = lo.y; c1[8 * a + 2] = lo.z; c1[8 * a + 3] = lo.w;
                         c1[8 * a + 4] = hi.x; c1[8 * a + 5] = hi.y; c1[8 * a + 6] = hi.z; c1[8 * a + 7] = hi.w;
                     }
@@ -515,6 +635,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 // Off the critical path: wait until the T2 CTAs have read the same lines for the on-path product.
                 __nanosleep(p.offpath_delay_ns);
                 ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
+                cs_release(t);
                 if (cta == 0 && g == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
                     *reinterpret_cast<volatile int*>(p.progress) = t;
                     __threadfence_system();
@@ -529,11 +650,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
                 trace(p, t, 0);
                 float c2[24];
+                cs_wait(t);
                 if (L.live) {
                     const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const float4 lo = __ldcs(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcs(reinterpret_cast<const float4*>(c + a * 512) + 1);
+                        const float4 lo = __ldcg(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcg(reinterpret_cast<const float4*>(c + a * 512) + 1);
                         c2[8 * a + 0] = lo.x; c2[8 * a + 1] = lo.y; c2[8 * a + 2] = lo.z; c2[8 * a + 3] = lo.w;
                         c2[8 * a + 4] = hi.x; c2[8 * a + 5] = hi.y; c2[8 * a + 6] = hi.z; c2[8 * a + 7] = hi.w;
                     }
@@ -586,6 +708,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 }
                 trace(p, t, 5);
                 ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
+                cs_release(t);
             }
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
@@ -594,10 +717,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
                 trace(p, t, 0);
                 float cc[16];
+                cs_wait(t);
                 if (L.live) {
                     const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + 64 * cta + 16 * L.cs);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 q4 = __ldcs(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
+                    for (int i = 0; i < 4; ++i) { const float4 q4 = __ldcg(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) cc[i] = 0.f;
@@ -620,6 +744,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
                 }
                 trace(p, t, 5);
+                cs_release(t);
             }
         }
     }
@@ -639,56 +764,9 @@ __global__ void __launch_bounds__(512) expand_cond_rs_kernel(const float4* __res
                                                              const float4* __restrict__ TQ1, const float4* __restrict__ TQ2,
                                                              const float* __restrict__ coef, const FoldDesc* __restrict__ folds, int S, int Ng,
                                                              int cs_steps, int steps_per_block, float* __restrict__ CS) {
-    const int b = blockIdx.x, j = threadIdx.x;
-    const int g = b / Ng, row = b - g * Ng;
-    const FoldDesc fd = folds[b];
-    const int t0 = blockIdx.y * steps_per_block, t1 = min(S, t0 + steps_per_block);
-    float ta[8], tq[kTaps][7];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ta[i] = 0.f;
-#pragma unroll
-    for (int d = 0; d < kTaps; ++d)
-#pragma unroll
-        for (int i = 0; i < 7; ++i) tq[d][i] = 0.f;
-    int key = -1;
-    for (int t = t0; t < t1; ++t) {
-        const int n = fd.n0 + t;
-        const bool valid = n < fd.N;
-        const int q0 = valid ? n / kHop : 0;
-        const int want = valid ? (fd.tq_row0 + q0) : -2 - fd.ta_row0;
-        if (want != key) {
-            key = want;
-            const size_t ra = (size_t)(fd.ta_row0 + (valid ? q0 : fd.T)) * kRnn + j;
-            const float4 x1 = __ldg(TA1 + ra), x2 = __ldg(TA2 + ra);
-            ta[0] = x1.x; ta[1] = x1.y; ta[2] = x1.z; ta[3] = x1.w; ta[4] = x2.x; ta[5] = x2.y; ta[6] = x2.z; ta[7] = x2.w;
-            if (valid) {
-#pragma unroll
-                for (int d = 0; d < kTaps; ++d) {
-                    const size_t rq = (size_t)(fd.tq_row0 + q0 + d) * kRnn + j;
-                    const float4 q1 = __ldg(TQ1 + rq), q2 = __ldg(TQ2 + rq);
-                    tq[d][0] = q1.x; tq[d][1] = q1.y; tq[d][2] = q1.z; tq[d][3] = q1.w; tq[d][4] = q2.x; tq[d][5] = q2.y; tq[d][6] = q2.z;
-                }
-            }
-        }
-        float a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = ta[i];
-        if (valid) {
-            const float* cf = coef + (n - q0 * kHop) * kTaps;
-#pragma unroll
-            for (int d = 0; d < kTaps; ++d) {
-                const float w = __ldg(cf + d);
-                if (w != 0.f) {
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) a[i] = fmaf(w, tq[d][i], a[i]);
-                }
-            }
-        }
-        float* out = CS + (((size_t)g * cs_steps + (t % cs_steps)) * Ng + row) * 4096 + j;
-        __stcs(out + 0 * 512, a[0]); __stcs(out + 1 * 512, a[1]); __stcs(out + 2 * 512, a[2]);      // c1 r, z, n
-        __stcs(out + 3 * 512, a[4]); __stcs(out + 4 * 512, a[5]); __stcs(out + 5 * 512, a[6]);      // c2 r, z, n
-        __stcs(out + 6 * 512, a[3]); __stcs(out + 7 * 512, a[7]);                                    // c3 (fc1), c4 (fc2)
-    }
+    const int b = blockIdx.x;
+    const int t0 = blockIdx.y * steps_per_block;
+    expand_item_rs(TA1, TA2, TQ1, TQ2, coef, folds[b], b / Ng, b % Ng, t0, min(S, t0 + steps_per_block), cs_steps, Ng, CS, threadIdx.x);
 }
 
 cudaError_t set_rs_deadline(long long cycles) { return cudaMemcpyToSymbol(g_rs_deadline, &cycles, sizeof(cycles)); }
@@ -708,7 +786,7 @@ cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream) {
     if (err != cudaSuccess) return err;
     RsParams pp = p;
     void* args[] = {&pp};
-    const int grid = p.G * kRsCtas;
+    const int grid = p.G * kRsCtas + (p.cs_done ? p.n_expanders : 0);
     return cudaLaunchCooperativeKernel((const void*)wrnn_loop_rs_kernel, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
 }
 
