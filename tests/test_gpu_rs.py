@@ -1,0 +1,116 @@
+"""The role-specialised tensor-core loop (csrc/loop_rs.cu; MOL, <= 128 folds per 48-CTA group) against the ORACLE at the
+full sizes BASELINE config 3 is run at, and the full-size tensor-core paths of loop_tc.cu (CTA pairs, sampler CTAs, four
+pipelined sets) against the oracle as well.  Gates (BASELINE.json north_star): teacher-forced logits within 1e-3 relative,
+>= 99.9 % of the draws identical (MOL: the continuous sample within 1e-3 of the oracle's under the same noise).
+Every test prints the agreement it achieved."""
+import numpy as np
+import pytest
+
+from oracle import wavernn_oracle as orc
+from tests.util import make_model, norm_mel
+
+pytestmark = pytest.mark.gpu
+F16 = 1
+REL_TOL = 1e-3
+AGREE = 0.999
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def _oracle_check(model, sd, mode, mel, target, overlap, steps, seed, tag):
+    """Kernel free-running for `steps` steps; the oracle teacher-forced on the KERNEL's samples: per-step logits and draws."""
+    out = model.generate_debug(mel, True, target, overlap, want_logits=True, seed=seed, max_steps=steps, precision=F16)
+    F = out["samples"].shape[0]
+    S = target + 2 * overlap
+    forced = np.zeros((F, S), np.float32)
+    forced[:, :steps] = out["samples"]
+    _, tr = orc.generate(mel, sd, mode=mode, batched=True, target=target, overlap=overlap, seed=seed, forced_samples=forced,
+                         return_trace=True, max_steps=steps)
+    err = _rel(out["logits"], tr["logits"])
+    if mode == "RAW":
+        C = sd["fc3.weight"].shape[0]
+        mine = np.rint((out["samples"] + 1.0) * (C - 1) / 2.0).astype(np.int64)
+        agree = float((mine == tr["index"]).mean())
+    else:
+        agree = float((np.abs(out["samples"] - tr["samples"]) < 1e-3).mean())
+    print("%s: %d folds x %d steps vs oracle: logits rel err %.3e, draw agreement %.5f" % (tag, F, steps, err, agree))
+    assert err < REL_TOL, err
+    assert agree >= AGREE, agree
+    return out
+
+
+@pytest.mark.parametrize("target,overlap,folds", [(3000, 1500, 213), (6000, 1000, 137)])
+def test_rs_loop_config3_full_size_vs_oracle(target, overlap, folds):
+    """BASELINE config 3 (MOL, 60 s) on the two fold plans SURVEY.md 8(d) names: infer_waveform's own default (3000 / 1500)
+    and 6000 / 1000; first 80 steps of all folds (two groups, in-kernel expanders, conditioning ring)."""
+    model, sd = make_model(seed=12, bits=9, mode="MOL")
+    mel = norm_mel(4800, 1)
+    out = _oracle_check(model, sd, "MOL", mel, target, overlap, 80, 9, "loop_rs cfg3 %d/%d" % (target, overlap))
+    assert out["samples"].shape[0] == folds
+    assert dict(model.last_timings)["n_folds"] == folds
+
+
+def test_rs_loop_deterministic_and_ring_invisible(monkeypatch):
+    """Same samples (a) run to run, (b) with the records expanded up front instead of through the ring, (c) with a ring so
+    small that it wraps every 12 steps, (d) with one, two and three CTA groups."""
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    mel = norm_mel(600, 3)                                   # 120000 samples, 700 + 2 x 150 -> 141 folds
+    a = model.generate_debug(mel, True, 700, 150, want_logits=False, seed=4, max_steps=400, precision=F16)
+    b = model.generate_debug(mel, True, 700, 150, want_logits=False, seed=4, max_steps=400, precision=F16)
+    assert a["samples"].shape[0] == 141
+    np.testing.assert_array_equal(a["samples"], b["samples"])
+    monkeypatch.setenv("WRNN_RS_EXPAND", "0")
+    c = model.generate_debug(mel, True, 700, 150, want_logits=False, seed=4, max_steps=400, precision=F16)
+    np.testing.assert_array_equal(a["samples"], c["samples"])
+    monkeypatch.delenv("WRNN_RS_EXPAND")
+    monkeypatch.setenv("WRNN_RS_RING_MB", "1")
+    d = model.generate_debug(mel, True, 700, 150, want_logits=False, seed=4, max_steps=400, precision=F16)
+    np.testing.assert_array_equal(a["samples"], d["samples"])
+    monkeypatch.delenv("WRNN_RS_RING_MB")
+    for g in (1, 2, 3):
+        if g == 1 and a["samples"].shape[0] > 128:
+            continue
+        monkeypatch.setenv("WRNN_RS_GROUPS", str(g))
+        e = model.generate_debug(mel, True, 700, 150, want_logits=False, seed=4, max_steps=400, precision=F16)
+        np.testing.assert_array_equal(a["samples"], e["samples"])
+
+
+def test_rs_loop_small_and_ragged_fold_counts():
+    """1, 5, 33 and 129 folds (partial quadrants, a single group, two groups with an odd split), teacher-forced on the fp32
+    loop's samples: logits within 1e-3 of the fp32 loop, samples within 1e-3 on >= 99.9 %."""
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    for T, tg, ov in [(6, 800, 200), (26, 800, 200), (166, 800, 200), (646, 800, 200)]:
+        mel = norm_mel(T, 5)
+        a = model.generate_debug(mel, True, tg, ov, want_logits=True, seed=6, max_steps=64)                       # fp32 loop
+        forced = np.pad(a["samples"], ((0, 0), (0, tg + 2 * ov - 64)))
+        b = model.generate_debug(mel, True, tg, ov, forced=forced, want_logits=True, seed=6, max_steps=64, precision=F16)
+        err = _rel(b["logits"], a["logits"])
+        agree = float((np.abs(a["samples"] - b["samples"]) < 1e-3).mean())
+        print("loop_rs %d folds vs fp32 loop: logits rel err %.3e, agreement %.5f" % (a["samples"].shape[0], err, agree))
+        assert err < REL_TOL and agree >= AGREE, (a["samples"].shape[0], err, agree)
+
+
+def test_rs_loop_full_generate_matches_loop_tc_shape_and_is_finite(monkeypatch):
+    """The public generate() through the role-specialised loop: right length, float64, finite, deterministic; and the same
+    call through loop_tc.cu (WRNN_RS=0) gives a waveform that agrees until the first differing draw."""
+    model, _ = make_model(seed=12, bits=9, mode="MOL")
+    model.precision = F16
+    mel = norm_mel(400, 2)
+    model.seed = 3
+    w1 = model.generate(mel[None], True, 3000, 1500, True, True)
+    w2 = model.generate(mel[None], True, 3000, 1500, True, True)
+    assert w1.shape == ((400 - 1) * 200,) and w1.dtype == np.float64 and np.isfinite(w1).all()
+    assert np.array_equal(w1, w2)
+
+
+@pytest.mark.parametrize("mode,seed", [("MOL", 12), ("RAW", 11)])
+def test_loop_tc_full_size_cfg3_plan_vs_oracle(mode, seed):
+    """loop_tc.cu at the size its large-fold paths exist for (1024 folds: four pipelined sets, CTA pairs, sampler CTAs,
+    in-kernel expanders) against the ORACLE: first 64 steps of the 853 / 85 plan.  RAW is the kernel configuration a pooled
+    cfg5 wave of 1024 folds runs (RAW-512 sampler CTAs as CTA pairs)."""
+    model, sd = make_model(seed=seed, bits=9, mode=mode)
+    mel = norm_mel(4800, 1)
+    out = _oracle_check(model, sd, mode, mel, 853, 85, 64, 9, "loop_tc cfg3 853/85 %s" % mode)
+    assert out["samples"].shape[0] == 1024

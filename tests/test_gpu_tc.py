@@ -35,7 +35,7 @@ def test_tc_pair_gemm_self_test(model, N):
 
 # ---- the fp16 tensor-core loop ("bf16/fp16 weights stated separately" in the north_star) ---------------------
 # Measured on CPU by emulating fp16 rounding of weights and activations in the oracle: logits within ~4e-4
-# relative, ~99.94 % identical draws on the random-init model.  Gates used here: 1e-3 relative, 99.8 % draws.
+# relative, ~99.94 % identical draws on the random-init model.  Gates used here: 1e-3 relative, 99.9 % draws (the north_star's); every test prints what it achieved.
 F16 = 1
 
 
@@ -61,7 +61,7 @@ def test_tc_loop_raw_teacher_forced_vs_reference():
     agree = float((mine[:, :-1] == ref_idx).mean())
     print("fp16 loop: logits rel err %.2e, draw agreement %.5f" % (err, agree))
     assert err < 1e-3
-    assert agree >= 0.998
+    assert agree >= 0.999
 
 
 def test_tc_loop_mol_teacher_forced_vs_reference():
@@ -79,7 +79,7 @@ def test_tc_loop_mol_teacher_forced_vs_reference():
     d = np.abs(out["samples"][:, :-1] - ref)
     print("fp16 loop MOL: logits rel err %.2e, samples within 1e-3: %.5f" % (err, float((d < 1e-3).mean())))
     assert err < 1e-3
-    assert float((d < 1e-3).mean()) >= 0.998
+    assert float((d < 1e-3).mean()) >= 0.999
 
 
 def test_tc_loop_matches_f32_loop_many_folds():
@@ -93,7 +93,7 @@ def test_tc_loop_matches_f32_loop_many_folds():
     c = model.generate_debug(mel, True, 300, 50, forced=forced, want_logits=True, seed=5, max_steps=60)
     assert a["samples"].shape[0] > 100
     assert _rel(b["logits"], c["logits"]) < 1e-3
-    assert float((b["samples"] == c["samples"]).mean()) >= 0.998
+    assert float((b["samples"] == c["samples"]).mean()) >= 0.999
 
 
 @pytest.mark.parametrize("mode,seed", [("RAW", 11), ("MOL", 12)])
@@ -108,9 +108,9 @@ def test_tc_loop_several_fold_sets_per_group(mode, seed):
     assert a["samples"].shape[0] > 256
     assert _rel(a["logits"], b["logits"]) < 1e-3
     if mode == "RAW":
-        assert float((a["samples"] == b["samples"]).mean()) >= 0.998
+        assert float((a["samples"] == b["samples"]).mean()) >= 0.999
     else:
-        assert float((np.abs(a["samples"] - b["samples"]) < 1e-3).mean()) >= 0.998
+        assert float((np.abs(a["samples"] - b["samples"]) < 1e-3).mean()) >= 0.999
     # rows of different sets must not be mixed up: every fold differs from its neighbours
     assert len({a["samples"][i, :48].tobytes() for i in range(a["samples"].shape[0])}) == a["samples"].shape[0]
 
@@ -146,7 +146,8 @@ def test_full_size_config3_cta_pairs_vs_f32_loop(mode, seed):
         agree = float((a["samples"] == b["samples"]).mean())
     else:
         agree = float((np.abs(a["samples"] - b["samples"]) < 2e-3).mean())       # continuous output: same mixture, same noise
-    assert agree >= 0.998, agree
+    print('full-size fp16 vs fp32 loop (%s): agreement %.5f' % (mode, agree))
+    assert agree >= 0.999, agree
     model.precision = F16
     model.seed = 3
     w1 = model.generate(mel[None], True, 853, 85, True, True)
@@ -184,7 +185,7 @@ def test_cluster_local_tc_loop_mol(monkeypatch):
     out = model.generate_debug(mel, True, int(g["target"]), int(g["overlap"]), forced=forced, want_logits=True,
                                seed=int(g["seed"]), precision=F16)
     assert _rel(out["logits"][:, ::8], g["logits_sub"]) < 1e-3
-    assert float((np.abs(out["samples"][:, :-1] - ref) < 1e-3).mean()) >= 0.998
+    assert float((np.abs(out["samples"][:, :-1] - ref) < 1e-3).mean()) >= 0.999
     # many folds: several clusters, partially filled last cluster
     mel2 = norm_mel(400, 4)
     a = model.generate_debug(mel2, True, 300, 50, want_logits=True, seed=5, max_steps=40, precision=F16)
