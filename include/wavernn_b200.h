@@ -67,6 +67,9 @@ int64_t wrnn_get_step(const wrnn_engine* e);
 int wrnn_finalize(wrnn_engine* e);
 /* fraction of zero 1x4 groups found in [rnn1.hh, rnn2.ih, rnn2.hh, fc1, fc2, fc3] at finalize        */
 double wrnn_sparsity(const wrnn_engine* e);
+/* 1 when the block-sparse loop can run this checkpoint (its compressed per-CTA images fit one cluster's shared memory);
+ * a pruned checkpoint that does not fit runs the dense loops instead (vocoder/pruner.py:60-88 leaves the tensors dense). */
+int wrnn_sparse_available(const wrnn_engine* e);
 
 /* Index arithmetic of WaveRNN.fold_with_overlap -- fatchord_version.py:315-326 (pure host).         */
 int wrnn_fold_plan(int64_t total_len, int64_t target, int64_t overlap, int64_t* num_folds, int64_t* padded_len);

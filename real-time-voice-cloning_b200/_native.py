@@ -46,7 +46,7 @@ class Request(C.Structure):
 
 
 EXPORTS = ["wrnn_create", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
-           "wrnn_finalize", "wrnn_sparsity", "wrnn_fold_plan", "wrnn_generate", "wrnn_condition", "wrnn_condition_tc", "wrnn_postprocess",
+           "wrnn_finalize", "wrnn_sparsity", "wrnn_sparse_available", "wrnn_fold_plan", "wrnn_generate", "wrnn_condition", "wrnn_condition_tc", "wrnn_postprocess",
            "wrnn_xfade_unfold", "wrnn_barrier_floor", "wrnn_cluster_floor", "wrnn_debug_umma_rate", "wrnn_debug_tc_gemm", "wrnn_debug_tc_gemm2", "wrnn_launch_count"]
 
 _lib = None
@@ -73,6 +73,7 @@ def load():
     lib.wrnn_finalize.argtypes = [vp]
     lib.wrnn_sparsity.argtypes = [vp]
     lib.wrnn_sparsity.restype = C.c_double
+    lib.wrnn_sparse_available.argtypes = [vp]
     lib.wrnn_fold_plan.argtypes = [i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]
     lib.wrnn_generate.argtypes = [vp, C.POINTER(Request)]
     lib.wrnn_condition.argtypes = [vp, vp, i32, vp, vp]

@@ -171,7 +171,7 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     if (!out) return WRNN_ERR_INVALID;
     *out = nullptr;
     if (mode != WRNN_MODE_RAW && mode != WRNN_MODE_MOL) return WRNN_ERR_INVALID;
-    if (mode == WRNN_MODE_RAW && (bits < 8 || bits > 10)) return WRNN_ERR_INVALID;
+    if (mode == WRNN_MODE_RAW && (bits < 8 || bits > 10)) return WRNN_ERR_INVALID;      // (header: RAW 8..10 bits; the reference trains 9 / 10)
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return WRNN_ERR_CUDA;
     wrnn_engine* e = new wrnn_engine();
@@ -216,6 +216,7 @@ int wrnn_destroy(wrnn_engine* e) {
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->evx) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return WRNN_OK;
@@ -236,6 +237,7 @@ int wrnn_set_tensor(wrnn_engine* e, const char* name, const float* data, const i
 int wrnn_set_step(wrnn_engine* e, int64_t step) { if (!e) return WRNN_ERR_INVALID; e->step = step; return WRNN_OK; }
 int64_t wrnn_get_step(const wrnn_engine* e) { return e ? e->step : -1; }
 double wrnn_sparsity(const wrnn_engine* e) { return e ? e->sparsity : 0.0; }
+int wrnn_sparse_available(const wrnn_engine* e) { return (e && (e->spStride[0] || e->spStride[1])) ? 1 : 0; }
 int64_t wrnn_launch_count(const wrnn_engine* e) { return e ? e->launches : 0; }
 
 int wrnn_finalize(wrnn_engine* e) {
@@ -1358,6 +1360,7 @@ int wrnn_postprocess(wrnn_engine* e, const float* samples, int64_t num_folds, in
     if (!e || !samples || !wav || num_folds < 1 || S < 1) return WRNN_ERR_INVALID;
     if (T <= 20) return fail(e, WRNN_ERR_TOO_SHORT, "mel has <= 20 frames (fatchord_version.py:253-255)");
     if (batched && overlap <= 0) return fail(e, WRNN_ERR_INVALID, "overlap == 0 (fatchord_version.py:394)");
+    if (batched && S < 2 * (int64_t)overlap) return fail(e, WRNN_ERR_INVALID, "folds shorter than 2 * overlap (fatchord_version.py:376)");
     CU(cudaSetDevice(e->device));
     const int target = batched ? (int)S - 2 * overlap : 0;
     PostUtt u;

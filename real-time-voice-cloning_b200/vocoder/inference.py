@@ -130,32 +130,51 @@ def infer_waveform(mel, normalize=True, batched=True, target=None, overlap=None,
     mel = np.ascontiguousarray(mel, dtype=np.float32)
     seed = _next_seed()
     if len(_model) == 1 or not batched:
-        m = _model[0]
-        m.seed = seed
-        return m.generate(mel[None, ...], batched, target, overlap, hp_wavernn.mu_law, sp.preemphasize, progress_callback)
-    return _infer_sharded(mel, target, overlap, hp_wavernn.mu_law, sp.preemphasize, seed)
+        return _model[0].generate(mel[None, ...], batched, target, overlap, hp_wavernn.mu_law, sp.preemphasize, progress_callback,
+                                  seed=seed)
+    return _infer_sharded(mel, target, overlap, hp_wavernn.mu_law, sp.preemphasize, seed, progress_callback)
 
 
-def _infer_sharded(mel, target, overlap, mu_law, preemph, seed):
+def _infer_sharded(mel, target, overlap, mu_law, preemph, seed, progress_callback=None):
+    """Fold ranges of ONE utterance on several engines.  The precision is chosen once from the utterance's total fold count
+    (not per shard), the shards write straight into one (F, S) sample matrix, and progress_callback keeps the reference's
+    contract (fatchord_version.py:234-236: (i, seq_len, b_size, gen_rate_kHz)) with b_size = all folds of the utterance and
+    i = the slowest shard's step."""
+    import threading
     from concurrent.futures import ThreadPoolExecutor
     from .. import _native
+    from .models.fatchord_version import resolve_precision
     T = mel.shape[1]
     F, _ = _native.fold_plan(T * sp.hop_size, target, overlap)
+    S = target + 2 * overlap
     n = min(len(_model), F)
     bounds = [F * i // n for i in range(n + 1)]
+    m0 = _model[0]
+    prec = m0.precision
+    if prec == _native.PREC_AUTO:
+        prec = resolve_precision(m0.n_classes, m0.sparsity, F, m0.sparse_available)
+    samples = np.empty((F, S), np.float32)
+    steps, lock = [0] * n, threading.Lock()
 
     def work(i):
-        return _model[i].generate_debug(mel, True, target, overlap, fold_begin=bounds[i], fold_end=bounds[i + 1],
-                                        seed=seed)["samples"]
+        cb = None
+        if progress_callback is not None:
+            def cb(step, seq_len, b_size, rate, i=i):
+                with lock:
+                    steps[i] = step
+                    progress_callback(min(steps), seq_len, F, rate * F / max(1, b_size))
+        samples[bounds[i]:bounds[i + 1]] = _model[i].generate_debug(mel, True, target, overlap, fold_begin=bounds[i], fold_end=bounds[i + 1],
+                                                                    seed=seed, precision=prec, progress_callback=cb)["samples"]
     with ThreadPoolExecutor(max_workers=n) as ex:
-        parts = list(ex.map(work, range(n)))
-    samples = np.concatenate(parts, axis=0)
-    return _model[0].postprocess(samples, True, overlap, T, mu_law, preemph)
+        list(ex.map(work, range(n)))
+    return m0.postprocess(samples, True, overlap, T, mu_law, preemph)
 
 
-def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=None, utt_index0=0):
+def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=None, utt_index0=0, progress_callback=None):
     """Many utterances: sharded by utterance across the loaded engines (BASELINE config 5); inside one
-    engine all folds share persistent-loop launches.  Returns a list of float64 arrays."""
+    engine all folds share persistent-loop launches.  Returns a list of float64 arrays.  The loop precision is chosen ONCE
+    from the corpus' total fold count, so the result does not depend on how it is sharded; progress_callback (if given) is
+    called with the reference's four arguments for every shard's launches."""
     if _model is None or _model_type is None:
         raise Exception("Please load Wave-RNN in memory before using it")
     from concurrent.futures import ThreadPoolExecutor
@@ -164,6 +183,11 @@ def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=Non
     overlap = hp_wavernn.gen_overlap if overlap is None else overlap
     mels = [np.ascontiguousarray(m / sp.max_abs_value if normalize else m, dtype=np.float32) for m in mels]
     seed = _next_seed()
+    from .models.fatchord_version import resolve_precision
+    m0 = _model[0]
+    prec = m0.precision
+    if prec == _native.PREC_AUTO:
+        prec = resolve_precision(m0.n_classes, m0.sparsity, m0._count_folds(mels, batched, target, overlap), m0.sparse_available)
     n = min(len(_model), len(mels))
     # balance by total frames: longest first onto the lightest shard
     order = sorted(range(len(mels)), key=lambda i: -mels[i].shape[1])
@@ -176,10 +200,6 @@ def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=Non
 
     def work(k):
         m = _model[k]
-        m.seed = seed
-        res = []
-        for i in sorted(shards[k]):       # one call per utterance index keeps utt counters global
-            res.append((i, None))
         idx = sorted(shards[k])
         # contiguous runs share a call; non-contiguous indices need their own utt_index0
         runs, start = [], 0
@@ -189,7 +209,7 @@ def infer_waveforms(mels, normalize=True, batched=True, target=None, overlap=Non
                 start = j
         for run in runs:
             wavs = m.generate_batch([mels[i] for i in run], batched, target, overlap, hp_wavernn.mu_law,
-                                    sp.preemphasize, utt_index0=utt_index0 + run[0])
+                                    sp.preemphasize, progress_callback, utt_index0=utt_index0 + run[0], seed=seed, precision=prec)
             for i, w in zip(run, wavs):
                 out[i] = w
     with ThreadPoolExecutor(max_workers=n) as ex:

@@ -11,6 +11,7 @@ Deliberate differences from the reference (DESIGN.md "quirks"):
   * Q4: RAW sampling is inverse-CDF on one uniform per (step, fold) (north_star's replayable rule).
 """
 import ctypes as C
+import threading
 import time
 
 import numpy as np
@@ -74,8 +75,11 @@ class WaveRNN(object):
         self._h = C.c_void_p()
         rc = self._lib.wrnn_create(self.device_index, bits, _native.MODE_RAW if mode == 'RAW' else _native.MODE_MOL,
                                    C.byref(self._h))
+        if rc == _native.ERR_INVALID:
+            raise ValueError("wrnn_create: unsupported bits=%r / mode=%r (RAW takes 8..10 bits)" % (bits, mode))
         if rc != _native.OK:
             raise RuntimeError("wrnn_create failed (%d): no usable CUDA device %d" % (rc, self.device_index))
+        self._lock = threading.Lock()        # a handle is not re-entrant (include/wavernn_b200.h): calls on it are serialised here
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -86,7 +90,8 @@ class WaveRNN(object):
     # ---- checkpoint I/O (vocoder/inference.py:21-36, train.py:316-324 layout) ---------------------------
     def load_state_dict(self, state_dict, strict=True):
         """Accepts torch tensors or numpy arrays keyed like the reference state_dict.  A pruned checkpoint
-        is the same dense dict with zeros (vocoder/pruner.py:55-58); its block pattern is re-derived."""
+        is the same dense dict with zeros (vocoder/pruner.py:55-58); its block pattern is re-derived.
+        strict=True (torch's default): a missing tensor is a RuntimeError (the engine reports which one)."""
         state = {}
         for name, value in state_dict.items():
             if hasattr(value, "detach"):
@@ -136,6 +141,11 @@ class WaveRNN(object):
         return float(self._lib.wrnn_sparsity(self._h))
 
     @property
+    def sparse_available(self):
+        """The block-sparse loop can run this checkpoint (its compressed images fit one cluster's shared memory)."""
+        return bool(self._lib.wrnn_sparse_available(self._h))
+
+    @property
     def launch_count(self):
         return int(self._lib.wrnn_launch_count(self._h))
 
@@ -180,7 +190,8 @@ class WaveRNN(object):
         rq.apply_preemphasis = 1 if apply_preemphasis else 0
         prec = int(extra.get("precision", self.precision))
         if prec == _native.PREC_AUTO:
-            prec = resolve_precision(self.n_classes, self.sparsity, self._count_folds(arrs, batched, target, overlap))
+            prec = resolve_precision(self.n_classes, self.sparsity, self._count_folds(arrs, batched, target, overlap),
+                                     self.sparse_available)
         rq.precision = prec
         rq.seed = int(extra.get("seed", self.seed)) & 0xFFFFFFFFFFFFFFFF
         rq.utt_index0 = int(extra.get("utt_index0", 0))
@@ -204,33 +215,41 @@ class WaveRNN(object):
         return rq, arrs, wav, offsets, keep
 
     def _run(self, rq):
-        rc = self._lib.wrnn_generate(self._h, C.byref(rq))
-        if rc != _native.OK:
-            _raise(self._lib, self._h, rc)
+        with self._lock:
+            rc = self._lib.wrnn_generate(self._h, C.byref(rq))
+            if rc != _native.OK:
+                _raise(self._lib, self._h, rc)
         self.last_timings = dict(ms_h2d=rq.ms_h2d, ms_cond=rq.ms_cond, ms_loop=rq.ms_loop, ms_post=rq.ms_post,
                                  ms_d2h=rq.ms_d2h, n_folds=rq.n_folds, n_steps=rq.n_steps, n_launches=rq.n_launches,
                                  precision=int(rq.precision))
 
-    def generate(self, mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback=None):
+    def generate(self, mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback=None, seed=None):
         """fatchord_version.py:155: mels is (1, 80, T) float32 already divided by max_abs_value; returns
-        np.float64[(T-1)*hop].  Raises ValueError for T <= 20 like the reference's broadcast error (Q8)."""
+        np.float64[(T-1)*hop].  Raises ValueError for T <= 20 like the reference's broadcast error (Q8).
+        `seed` (extension): Philox key of this call; default self.seed."""
+        extra = {} if seed is None else dict(seed=seed)
         rq, arrs, wav, offsets, keep = self._request([mels], batched, target, overlap, mu_law, apply_preemphasis,
-                                                     progress_callback)
+                                                     progress_callback, **extra)
         self._run(rq)
         return wav[:(arrs[0].shape[1] - 1) * self.hop_length]
 
     def generate_batch(self, mels_list, batched, target, overlap, mu_law, apply_preemphasis, progress_callback=None,
-                       utt_index0=0):
+                       utt_index0=0, seed=None, precision=None):
         """Many utterances in one call: their folds are pooled into the same persistent-loop launches
         (BASELINE config 5).  Returns a list of float64 arrays.  Utterance i uses Philox utterance
         counter utt_index0 + i, so the result does not depend on how a corpus is sharded."""
+        extra = dict(utt_index0=utt_index0)
+        if seed is not None:
+            extra["seed"] = seed
+        if precision is not None:
+            extra["precision"] = precision
         rq, arrs, wav, offsets, keep = self._request(mels_list, batched, target, overlap, mu_law, apply_preemphasis,
-                                                     progress_callback, utt_index0=utt_index0)
+                                                     progress_callback, **extra)
         self._run(rq)
         return [wav[offsets[i]:offsets[i + 1]].copy() for i in range(len(arrs))]
 
     def generate_debug(self, mels, batched, target, overlap, forced=None, max_steps=0, want_logits=False,
-                       fold_begin=0, fold_end=0, seed=None, utt_index0=0, precision=None):
+                       fold_begin=0, fold_end=0, seed=None, utt_index0=0, precision=None, progress_callback=None):
         """Parity hook: runs the loop and returns dict(samples (F,S), logits (F,S,C) or None).  `forced`
         (F,S) float32 replaces the fed-back samples (teacher forcing on the reference's samples)."""
         extra = dict(max_steps=max_steps, fold_begin=fold_begin, fold_end=fold_end, utt_index0=utt_index0)
@@ -238,7 +257,7 @@ class WaveRNN(object):
             extra["seed"] = seed
         if precision is not None:
             extra["precision"] = precision
-        rq, arrs, _, _, keep = self._request([mels], batched, target, overlap, True, True, None, want_wav=False, **extra)
+        rq, arrs, _, _, keep = self._request([mels], batched, target, overlap, True, True, progress_callback, want_wav=False, **extra)
         T = arrs[0].shape[1]
         N = T * self.hop_length
         if batched:
@@ -326,8 +345,9 @@ class WaveRNN(object):
         samples = np.ascontiguousarray(samples, dtype=np.float32)
         F, S = samples.shape
         wav = np.empty((T - 1) * self.hop_length, np.float64)
-        rc = self._lib.wrnn_postprocess(self._h, samples.ctypes.data, F, S, 1 if batched else 0, int(overlap), int(T),
-                                        1 if mu_law else 0, 1 if apply_preemphasis else 0, wav.ctypes.data)
+        with self._lock:
+            rc = self._lib.wrnn_postprocess(self._h, samples.ctypes.data, F, S, 1 if batched else 0, int(overlap), int(T),
+                                            1 if mu_law else 0, 1 if apply_preemphasis else 0, wav.ctypes.data)
         if rc != _native.OK:
             _raise(self._lib, self._h, rc)
         return wav
@@ -377,19 +397,24 @@ class WaveRNN(object):
 
 
 AUTO_F16_MIN_FOLDS = 24
+AUTO_F16_MIN_FOLDS_MOL = 12
 AUTO_SPARSE_MIN = 0.8
 
 
-def resolve_precision(n_classes, sparsity, n_folds):
+def resolve_precision(n_classes, sparsity, n_folds, sparse_available=True):
     """Which loop `PREC_AUTO` (the default of the `vocoder.inference` facade) runs, from what was measured on B200 (DESIGN.md
-    section 6): a pruned checkpoint -> the block-sparse cluster loop (62.9x vs 38.8x real-time on cfg4); a dense one with at
-    least AUTO_F16_MIN_FOLDS folds in the call -> the fp16 tensor-core loop (213 folds: 385x vs 52x for the fp32 loop); fewer
-    folds -> the fp32 loop, which is then the faster one AND bit-faithful (19 folds: 39.2x vs 36.2x; one fold: the only
-    loop built for it).  Measured crossover (tools/auto_crossover.py, us per step fp32 / fp16): 14 folds 21.2 / 28.7, 19 folds
-    26.3 / 29.2, 23 folds 27.7 / 29.0, 28 folds 30.6 / 29.0, 37 folds 42.7 / 29.8.  The tensor-core loop exists for 30 (MOL), 512 and 1024 classes."""
-    if sparsity >= AUTO_SPARSE_MIN:          # (the engine builds the cluster images from 0.5 up, but only ~0.8+ fits one cluster)
+    section 6): a pruned checkpoint whose compressed images fit one cluster -> the block-sparse cluster loop (62.9x vs 38.8x
+    real-time on cfg4; a pruned checkpoint that does NOT fit falls through to the dense loops -- its tensors are dense with
+    zeros, vocoder/pruner.py:55-58); a dense one with at least AUTO_F16_MIN_FOLDS folds in the call -> the fp16 tensor-core
+    loops (MOL up to 384 folds: loop_rs.cu, 18.7 us per step whatever the fold count; else loop_tc.cu); fewer folds -> the
+    fp32 loop, which is then the faster one AND bit-faithful (19 folds: 39.2x vs 36.2x; one fold: the only loop built for
+    it).  Measured crossover (tools/auto_crossover.py, us per step fp32 / fp16): 14 folds 21.2 / 28.7, 19 folds 26.3 / 29.2,
+    23 folds 27.7 / 29.0, 28 folds 30.6 / 29.0, 37 folds 42.7 / 29.8; MOL on loop_rs.cu crosses at ~12 folds.
+    The tensor-core loops exist for 30 (MOL), 512 and 1024 classes."""
+    if sparsity >= AUTO_SPARSE_MIN and sparse_available:
         return _native.PREC_SPARSE_F32
-    if n_folds >= AUTO_F16_MIN_FOLDS and n_classes in (30, 512, 1024):
+    min_folds = AUTO_F16_MIN_FOLDS_MOL if n_classes == 30 else AUTO_F16_MIN_FOLDS
+    if n_folds >= min_folds and n_classes in (30, 512, 1024):
         return _native.PREC_F16
     return _native.PREC_F32
 

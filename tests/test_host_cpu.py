@@ -48,8 +48,9 @@ def test_drop_in_surface():
     sig = inspect.signature(inference.infer_waveform)
     assert list(sig.parameters)[:6] == ["mel", "normalize", "batched", "target", "overlap", "progress_callback"]
     assert [p.default for p in sig.parameters.values()][:6] == [inspect._empty, True, True, None, None, None]
-    assert list(inspect.signature(WaveRNN.generate).parameters)[1:] == [
-        "mels", "batched", "target", "overlap", "mu_law", "apply_preemphasis", "progress_callback"]
+    gen = inspect.signature(WaveRNN.generate).parameters
+    assert list(gen)[1:8] == ["mels", "batched", "target", "overlap", "mu_law", "apply_preemphasis", "progress_callback"]
+    assert all(p.default is not inspect._empty for p in list(gen.values())[7:])      # extensions (seed) are optional keywords
     assert list(inspect.signature(inference.load_model).parameters)[:3] == ["weights_fpath", "voc_type", "verbose"]
     assert (base.VOC_TYPE_CPP, base.VOC_TYPE_PYTORCH, base.MODEL_TYPE_FATCHORD) == ("libwavernn", "pytorch", "fatchord-wavernn")
     assert not inference.is_loaded()
