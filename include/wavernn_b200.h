@@ -48,7 +48,7 @@ typedef void (*wrnn_progress_fn)(int64_t i, int64_t seq_len, int64_t b_size, dou
 
 /* base.init_voc_model(MODEL_TYPE_FATCHORD, device, override_hp_fatchord) -- vocoder/models/base.py:18-48.
  * Fixed topology of the named hparams (rnn_dims=fc_dims=512, compute/res_out=128, res_blocks=10,
- * upsample (5,5,8), hop 200, pad 2, feat 80); `bits` in {9,10} for RAW; MOL has 30 outputs.        */
+ * upsample (5,5,8), hop 200, pad 2, feat 80); `bits` 8..10 for RAW (the reference trains 9 and 10); MOL has 30 outputs; anything else: WRNN_ERR_INVALID. */
 int wrnn_create(int device, int bits, int mode, wrnn_engine** out);
 int wrnn_destroy(wrnn_engine* e);
 const char* wrnn_last_error(const wrnn_engine* e);
@@ -105,7 +105,9 @@ typedef struct {
     /* ---- timings filled by the call (milliseconds, CUDA events on the engine's stream) ----------- */
     float ms_h2d, ms_cond, ms_loop, ms_post, ms_d2h;
     int32_t n_folds, n_steps, n_launches;
+    int32_t loop_kernel;        /* which loop ran the last wave: WRNN_LOOP_F32 / _TC / _RS / _SPARSE / _TC2     */
 } wrnn_request;
+enum { WRNN_LOOP_F32 = 0, WRNN_LOOP_TC = 1, WRNN_LOOP_RS = 2, WRNN_LOOP_SPARSE = 3, WRNN_LOOP_TC2 = 4 };
 
 /* WaveRNN.generate(mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback)
  * -- fatchord_version.py:155-259 -- for one or many utterances, end to end on the GPU:

@@ -6,6 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WRNN_B200_LIB") or os.path.join(HERE, "libwavernn_b200.so")   # override: A/B timing of kernel variants
 
+LOOP_KERNELS = {0: "wrnn_loop_f32_kernel", 1: "wrnn_loop_tc_kernel", 2: "wrnn_loop_rs_kernel", 3: "wrnn_loop_sparse_kernel", 4: "wrnn_loop_tc2_kernel"}
 OK, ERR_INVALID, ERR_NOT_LOADED, ERR_CUDA, ERR_TIMEOUT, ERR_SHAPE, ERR_TOO_SHORT = 0, -1, -2, -3, -4, -5, -6
 MODE_RAW, MODE_MOL = 0, 1
 PREC_F32, PREC_F16, PREC_SPARSE_F32 = 0, 1, 2
@@ -41,7 +42,7 @@ class Request(C.Structure):
         ("samples", C.c_void_p),
         ("logits", C.c_void_p),
         ("ms_h2d", C.c_float), ("ms_cond", C.c_float), ("ms_loop", C.c_float), ("ms_post", C.c_float), ("ms_d2h", C.c_float),
-        ("n_folds", C.c_int32), ("n_steps", C.c_int32), ("n_launches", C.c_int32),
+        ("n_folds", C.c_int32), ("n_steps", C.c_int32), ("n_launches", C.c_int32), ("loop_kernel", C.c_int32),
     ]
 
 

@@ -938,6 +938,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             }
             if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
             e->launches += 1;
+            rq->loop_kernel = WRNN_LOOP_SPARSE;
         } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wRs[0].p && B <= rs_max_folds) {
             // ---- role-specialised tensor-core loop (loop_rs.cu): the latency-bound regime, <= 128 folds per 48-CTA group ---------
             // groups: two leave 52 SMs to the expanders (three groups run the loop 4 % faster but starve them)
@@ -1013,6 +1014,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 rp.trace = e->bFloor.as<unsigned long long>();
             }
             CU(launch_loop_rs(rp, st));
+            rq->loop_kernel = WRNN_LOOP_RS;
             if (rs_trace) {
                 std::vector<unsigned long long> tr(trace_n);
                 CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1081,6 +1083,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 tp.trace = e->bFloor.as<long long>();
             }
             CU(launch_loop_tc2(tp, ncl, st));
+            rq->loop_kernel = WRNN_LOOP_TC2;
             if (want_trace2) {
                 std::vector<long long> tr(16 * 32);
                 CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -1194,6 +1197,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 tp.trace = e->bFloor.as<long long>();
             }
             CU(launch_loop_tc(tp, tmaps, st));
+            rq->loop_kernel = WRNN_LOOP_TC;
             if (want_trace) {
                 std::vector<long long> tr(16 * 192);
                 CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -1247,6 +1251,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         p.progress = e->dProgress;
         p.abort_flag = e->dAbort;
         CU(launch_loop_f32(p, st));
+        rq->loop_kernel = WRNN_LOOP_F32;
         e->launches += 1;
         }
         CU(cudaEventRecord(e->ev[7], st));

@@ -221,7 +221,7 @@ class WaveRNN(object):
                 _raise(self._lib, self._h, rc)
         self.last_timings = dict(ms_h2d=rq.ms_h2d, ms_cond=rq.ms_cond, ms_loop=rq.ms_loop, ms_post=rq.ms_post,
                                  ms_d2h=rq.ms_d2h, n_folds=rq.n_folds, n_steps=rq.n_steps, n_launches=rq.n_launches,
-                                 precision=int(rq.precision))
+                                 precision=int(rq.precision), loop_kernel=_native.LOOP_KERNELS.get(int(rq.loop_kernel), "?"))
 
     def generate(self, mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback=None, seed=None):
         """fatchord_version.py:155: mels is (1, 80, T) float32 already divided by max_abs_value; returns
