@@ -947,7 +947,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             if (const char* ev = getenv("WRNN_RS_GROUPS")) G = std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, std::min(rs_groups_max, atoi(ev)));
             const int Ng = (B + G - 1) / G;
             // Conditioning records (16 KB per fold and step) are produced INSIDE the loop kernel by expander CTAs on the SMs the
-            // groups leave free, into a ring sized to stay resident in L2 (WRNN_RS_RING_MB, default 56 MB): produced / consumed
+            // groups leave free, into a ring sized to stay resident in L2 (WRNN_RS_RING_MB, default 48 MB: three 4-step chunks at 213 folds): produced / consumed
             // counters per chunk of kRsChunk steps order the two sides.  WRNN_RS_EXPAND=0 (or no SM left): the whole table is
             // expanded before the launch.
             const int n_exp = e->n_sms - G * kRsCtas;
@@ -956,7 +956,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             int cs_steps = nchunks * kRsChunk;
             if (ring) {
                 const size_t chunk_bytes = (size_t)G * Ng * 4096 * sizeof(float) * kRsChunk;
-                const size_t budget = (size_t)(getenv("WRNN_RS_RING_MB") ? atoll(getenv("WRNN_RS_RING_MB")) : 56) << 20;
+                const size_t budget = (size_t)(getenv("WRNN_RS_RING_MB") ? atoll(getenv("WRNN_RS_RING_MB")) : 48) << 20;
                 const int ring_chunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(3, budget / chunk_bytes));
                 cs_steps = ring_chunks * kRsChunk;
             }
@@ -1013,7 +1013,35 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 CU(cudaMemsetAsync(e->bFloor.p, 0, trace_n * sizeof(unsigned long long), st));
                 rp.trace = e->bFloor.as<unsigned long long>();
             }
+            // the ring is the only large buffer the kernel rewrites: pin it in L2 for the launch (persisting access window)
+            bool l2_window = false;
+            if (ring && !(getenv("WRNN_RS_L2_PERSIST") && atoi(getenv("WRNN_RS_L2_PERSIST")) == 0)) {
+                int max_win = 0, max_persist = 0;
+                cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+                if (max_win > 0 && max_persist > 0) {
+                    const size_t want = std::min<size_t>(cs_bytes, (size_t)max_persist);
+                    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                        cudaStreamAttrValue av;
+                        memset(&av, 0, sizeof(av));
+                        av.accessPolicyWindow.base_ptr = e->bCS.p;
+                        av.accessPolicyWindow.num_bytes = std::min<size_t>(cs_bytes, (size_t)max_win);
+                        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)av.accessPolicyWindow.num_bytes);
+                        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+                        l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+                    }
+                    cudaGetLastError();
+                }
+            }
             CU(launch_loop_rs(rp, st));
+            if (l2_window) {
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.num_bytes = 0;
+                cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+                cudaGetLastError();
+            }
             rq->loop_kernel = WRNN_LOOP_RS;
             if (rs_trace) {
                 std::vector<unsigned long long> tr(trace_n);
