@@ -262,6 +262,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None     # host-side rendezvous that leaves the GPUs idle
 
     import __graft_entry__ as entry
     entry.build()
@@ -426,6 +427,8 @@ def main():
                                       "loop": loop_block(m5, "f16")}
         del c5
         barrier()
+        if world > 1:
+            dist.barrier(group=cpu_group)        # (an NCCL barrier would park a spinning kernel on the GPUs rank 0 is about to use)
         # (2) ONE utterance, its folds split into contiguous ranges over all GPUs of the box, driven from one process (rank 0)
         #     through the public infer_waveform: host threads, host gather of the samples, post chain on GPU 0 -- all timed
         if world > 1 and rank == 0:
@@ -445,6 +448,8 @@ def main():
                                                            "GPU, host gather + crossfade on GPU 0 inside the timed region (inference._infer_sharded)" % world}
             except Exception as e:
                 sharded["cfg3ref_fold_sharded"] = {"error": str(e)[:300]}
+        if world > 1:
+            dist.barrier(group=cpu_group)
         barrier()
     if rank != 0:
         if world > 1:
