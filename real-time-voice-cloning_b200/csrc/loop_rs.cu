@@ -109,6 +109,12 @@ __device__ __forceinline__ void trace(const RsParams& p, int t, int ev) {
     }
 }
 
+// SM-clock stamps of warp 0 / lane 0 inside an epilogue (slots 32 + k): the globaltimer ticks too coarsely (32-256 ns) for these
+__device__ __forceinline__ void ctrace(const RsParams& p, int t, int k) {
+    if (p.trace && threadIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
+        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 32 + k] = (unsigned long long)clock64();
+}
+
 // per-K-quarter events of the first ingest of a step: lane 0 of warps (q = 0, cs): slots 16 + 4 cs + {0 canaries, 1 loaded, 2 in TMEM}
 __device__ __forceinline__ void trace_kq(const RsParams& p, int t, int ev0, int cs, int k) {
     if (p.trace && ev0 == 1 && (threadIdx.x & 127) == 0 && threadIdx.x < NW * 32 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
@@ -157,8 +163,23 @@ __device__ __forceinline__ void umma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint
                      "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// exp / reciprocal as ONE special-function instruction each (ex2.approx.ftz / rcp.approx.ftz): __expf and __fdividef wrap
+// the same MUFU operations in three more instructions of denormal handling, and the GRU epilogues are instruction-bound
+// (24 exp + 24 reciprocals per thread and step).  Results differ from __expf only below 1e-38, where a sigmoid is 0 or 1.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)), 1.0f); }
+// per-unit constants live in shared memory: read them with ld.shared (the generic pointer would cost a generic LD each)
+__device__ __forceinline__ float4 lds4(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void lds8(const float* p, float* out) {
+    const float4 a = lds4(p), b = lds4(p + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -206,6 +227,7 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const L
     dbg(p, dbg_t, 0x11);
     trace(p, dbg_t, ev0);
     trace_kq(p, dbg_t, ev0, L.cs, 0);
+    if (ev0 == 1) ctrace(p, dbg_t, 8);
     unsigned long long xword = 0ull;
     if (xw) xword = ll_load(xw);            // the sample word was published before this matrix: its load rides along with phase 2
     // phase 2: full passes (16 loads at immediate offsets, one OR-reduction of the generation bits) until everything matches.
@@ -237,6 +259,7 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const L
     dbg(p, dbg_t, 0x12);
     trace(p, dbg_t, ev0 + 1);
     trace_kq(p, dbg_t, ev0, L.cs, 1);
+    if (ev0 == 1) ctrace(p, dbg_t, 9);
     if (p.trace && threadIdx.x == 0 && dbg_t >= kTraceStep0 && dbg_t < kTraceStep0 + kTraceSteps)
         p.trace[((size_t)blockIdx.x * kTraceSteps + (dbg_t - kTraceStep0)) * 48 + (ev0 == 1 ? 13 : 14)] = (unsigned long long)passes;
     if (xw) {
@@ -248,6 +271,7 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const L
         }
         xval = L.live ? ll_val(xword) : 0.f;
     }
+    if (ev0 == 1) ctrace(p, dbg_t, 10);
     if (want != 0u) {          // generation 1: the bit is set in every half; take it out (generation 0 needs nothing)
 #pragma unroll
         for (int i = 0; i < 16; ++i) { v[i].x ^= tb; v[i].y ^= tb; v[i].z ^= tb; v[i].w ^= tb; }
@@ -264,6 +288,7 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const L
     dbg(p, dbg_t, 0x13);
     trace(p, dbg_t, ev0 + 2);
     trace_kq(p, dbg_t, ev0, L.cs, 2);
+    if (ev0 == 1) ctrace(p, dbg_t, 11);
     IngestOut o;
     o.extra = extra; o.x = xval;
     return o;
@@ -590,13 +615,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
                     ingest(p, ctl, L, MAT(MF2, t - 1), kTagS, GEN(t - 1) ? kTagS : 0u, -1, t, 1, nullptr, 0u);
+                    ctrace(p, t, 0);
                     wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
                     trace(p, t, 4);
+                    ctrace(p, t, 1);
                     float lg[32];
                     tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
                     tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
                     tmem_ld_wait();
+                    ctrace(p, t, 2);
                     const float xs = warp_live ? mol_draw(lg, sbias, nz) : 0.f;
                     x = xs;
                     if (L.live) {
@@ -610,6 +638,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     }
                 }
                 if (t == S) break;
+                ctrace(p, t, 3);
                 float gh[24];
                 if (t > 0) {
                     tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, gh + 8);
@@ -622,17 +651,22 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->ebar);
+                ctrace(p, t, 4);
                 if (warp_live) {
+                float kr[8], kz[8], kn[8], kb[8];
+                lds8(v1, kr); lds8(v1 + 32, kz); lds8(v1 + 64, kn); lds8(v1 + 96, kb);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float r = sigmoid_fast(fmaf(v1[i], x, c1[i]) + gh[i]);
-                    const float z = sigmoid_fast(fmaf(v1[32 + i], x, c1[8 + i]) + gh[8 + i]);
-                    const float n = tanh_fast(fmaf(v1[64 + i], x, c1[16 + i]) + r * (gh[16 + i] + v1[96 + i]));
-                    h1[i] = (1.0f - z) * n + z * h1[i];
+                    const float r = sigmoid_fast(fmaf(kr[i], x, c1[i]) + gh[i]);
+                    const float z = sigmoid_fast(fmaf(kz[i], x, c1[8 + i]) + gh[8 + i]);
+                    const float n = tanh_fast(fmaf(kn[i], x, c1[16 + i]) + r * (gh[16 + i] + kb[i]));
+                    h1[i] = fmaf(z, h1[i] - n, n);
                 }
+                ctrace(p, t, 5);
                 if (L.live) publish8(MAT(MH1, t), 4 * cta + L.cs, L.row, h1, kTagE, GEN(t) ? kTagE : 0u);
                 }
                 trace(p, t, 5);
+                ctrace(p, t, 6);
                 // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited).
                 // Off the critical path: wait until the T2 CTAs have read the same lines for the on-path product.
                 __nanosleep(p.offpath_delay_ns);
@@ -673,10 +707,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 const float x = io.x;
                 const uint4 extra = io.extra;
                 dbg(p, t, 0x30);
+                ctrace(p, t, 0);
                 wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
                 tcgen05_fence_after();
                 dbg(p, t, 0x31);
                 trace(p, t, 4);
+                ctrace(p, t, 1);
                 float pb[24], gh[24];
                 tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, pb); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, pb + 8);
                 tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, pb + 16);
@@ -691,24 +727,29 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->ebar);
+                ctrace(p, t, 4);
                 float s2[8];
                 const float2 e0 = unpack2(extra.x), e1 = unpack2(extra.y), e2 = unpack2(extra.z), e3 = unpack2(extra.w);
                 const float h1o[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
                 if (warp_live) {
+                float kr[8], kz[8], kn[8], kb[8];
+                lds8(v2, kr); lds8(v2 + 32, kz); lds8(v2 + 64, kn); lds8(v2 + 96, kb);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float r = sigmoid_fast(pb[i] + fmaf(v2[i], x, c2[i]) + gh[i]);
-                    const float z = sigmoid_fast(pb[8 + i] + fmaf(v2[32 + i], x, c2[8 + i]) + gh[8 + i]);
-                    const float n = tanh_fast(pb[16 + i] + fmaf(v2[64 + i], x, c2[16 + i]) + r * (gh[16 + i] + v2[96 + i]));
-                    h2[i] = (1.0f - z) * n + z * h2[i];
+                    const float r = sigmoid_fast(pb[i] + fmaf(kr[i], x, c2[i]) + gh[i]);
+                    const float z = sigmoid_fast(pb[8 + i] + fmaf(kz[i], x, c2[8 + i]) + gh[8 + i]);
+                    const float n = tanh_fast(pb[16 + i] + fmaf(kn[i], x, c2[16 + i]) + r * (gh[16 + i] + kb[i]));
+                    h2[i] = fmaf(z, h2[i] - n, n);
                     s2[i] = fminf(fmaxf(h1o[i] + h2[i], -1.9990234375f), 1.9990234375f);
                 }
+                ctrace(p, t, 5);
                 if (L.live) {
                     publish8(MAT(MS2, t), 4 * cta + L.cs, L.row, s2, kTagE, GEN(t) ? kTagE : 0u);
                     publish8(MAT(MH2, t), 4 * cta + L.cs, L.row, h2, kTagE, GEN(t) ? kTagE : 0u);
                 }
                 }
                 trace(p, t, 5);
+                ctrace(p, t, 6);
                 ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
                 cs_release(t);
             }

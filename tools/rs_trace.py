@@ -10,7 +10,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3ref"
 path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "rs_trace.txt")
 if not os.path.exists(path) or os.environ.get("RS_TRACE_RUN"):
     env = dict(os.environ, WRNN_RS_TRACE=path)
-    subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", "1", "--warmup", "1", "--no-cpu-baseline"], env=env,
+    subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-extras"], env=env,
                    stdout=subprocess.DEVNULL, check=True)
 rows = np.loadtxt(path, dtype=np.int64)
 ncta = rows[:, 0].max() + 1
@@ -44,10 +44,12 @@ for g in range(min(G, 1)):
                     continue
                 line += " | %s %.2f..%.2f" % (evn[j], np.nanmin(v) / 1e3, np.nanmax(v) / 1e3)
             line += passes(cs, k)
-            mm = ev[cs, k, 32:42]
-            dl = np.nanmean(mm[:, 1:] - mm[:, :1], axis=0)
-            line += "\n        MMA warp clocks since job start: " + " ".join("%s %.0f" % (n, v) for n, v in zip(
-                ["kq0 ready", "kq0 issued", "kq1 ready", "kq1 issued", "kq2 ready", "kq2 issued", "kq3 ready", "kq3 issued", "complete"], dl))
+            cl = np.nanmean(ev[cs, 1:8, 32:44], axis=(0, 1))          # SM clocks of warp 0, mean over CTAs of the role and steps
+            nm = {0: "wait MMA", 1: "MMA done", 2: "logits loaded", 3: "drawn", 4: "acc loaded", 5: "math done", 6: "published",
+                  8: "canaries", 9: "loaded", 10: "checked", 11: "in TMEM"}
+            order = [8, 9, 10, 11, 0, 1, 2, 3, 4, 5, 6]
+            base = cl[8]
+            line += "\n        warp-0 clocks since its canaries: " + " | ".join("%s %.0f" % (nm[j], cl[j] - base) for j in order if not np.isnan(cl[j]))
             for q in range(4):
                 line += "\n        K quarter %d:" % q
                 for j, nm in enumerate(["canaries", "loaded", "in TMEM"]):
