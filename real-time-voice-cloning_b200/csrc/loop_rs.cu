@@ -35,7 +35,8 @@ __device__ long long g_rs_deadline = 1500000000LL;
 namespace {
 using namespace tc;
 
-constexpr int NW = 16;                        // ingest / epilogue warps: warp w = (lane quadrant q = w & 3, K quarter / column slice w >> 2)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NW = 16;                        // ingest / epilogue warps: warp w = (lane quadrant q = w & 3, column slice cs = w >> 2)
 constexpr int NT = (NW + 4) * 32;             // + a service warpgroup: the MMA warp and three idle warps (setmaxnreg works on whole warpgroups)
 constexpr int kRegsEpi = 104, kRegsSvc = 64;  // after the hand-over: 16 x 104 + 4 x 64 = 20 x 96, the launch allocation (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
 constexpr int kChunks = kRnn / 8;             // 64 chunks of 8 fp16 per activation row
@@ -50,26 +51,32 @@ constexpr uint32_t kColD1 = 352;              // second accumulator
 // shared memory: weight tiles (K-major SWIZZLE_128B, [k-block 8][rows N][128 B]) then constants and the control block
 constexpr int kW0 = 0;                                   // first tile: T1 W_hh1 (96 rows), T2 W_ih2a (96), T3 fc1a (64), T4 fc2 (64)
 constexpr int kW1 = 96 * 128 * 8;                        // second tile: T1 fc3 (32 rows), T2 W_hh2 (96)
+constexpr int kNoiseOfs = kW1 + 32 * 128 * 8;            // T1 only: the step's mixture noise, [12][512 threads] floats (24 KB behind the fc3 tile)
 constexpr int kWEnd = kW1 + 96 * 128 * 8;                // 196608
 constexpr int kConstOfs = kWEnd;                         // per-unit constants, <= 5 x 64 floats
 constexpr int kCtlOfs = kConstOfs + 2048;
 constexpr int kSmemBytes = kCtlOfs + 256;
+static_assert(kNoiseOfs + 12 * 512 * 4 <= kWEnd, "T1 noise buffer");
 
 struct Ctl {
-    uint64_t abar[4];      // K quarter kq of the A operand is in TMEM (4 warps arrive)
+    uint64_t abar[4];      // K quarter kq of the A operand is in TMEM (all 16 warps arrive)
     uint64_t dbar[2];      // accumulator complete (tcgen05.commit): [0] on-path job, [1] recurrent (off-path) job
     uint64_t ebar;         // all 16 epilogue warps have read the recurrent accumulator of the previous step
     uint32_t tmem;
     int abort_local;
 };
+// barriers are addressed by their 32-bit shared-memory address (ctl_s + offset): the generic -> shared conversion of a pointer
+// costs ~10 uniform instructions wherever the compiler rematerialises it, and every instruction of the chain counts
+constexpr uint32_t kBarA = 0, kBarD = 32, kBarE = 48;
 
 __device__ __forceinline__ bool aborted_local(Ctl* c) { return *reinterpret_cast<volatile int*>(&c->abort_local) != 0; }
 // warp-uniform view of the abort flag (lane 0's): the step loops end together for all lanes of a warp
-__device__ __forceinline__ bool warp_aborted(Ctl* c) { return __shfl_sync(0xffffffffu, aborted_local(c) ? 1 : 0, 0) != 0; }
-__device__ __noinline__ bool spin_check(const RsParams& p, Ctl* c, long long& t0) {
+__device__ __forceinline__ bool warp_aborted(Ctl* c) { return __shfl_sync(FULL, aborted_local(c) ? 1 : 0, 0) != 0; }
+// slow path of every wait (each 256th or 1024th try): abort flags and the deadline.  t0 (the clock at the first slow check) is
+// passed BY VALUE: by reference it lived in local memory and every wait paid a store for it.
+__device__ __noinline__ bool spin_check(const RsParams& p, Ctl* c, long long t0) {
     if (aborted_local(c)) return true;
     if (ld_volatile_i32(p.abort_flag) != 0) { *reinterpret_cast<volatile int*>(&c->abort_local) = 1; return true; }
-    if (t0 == 0) t0 = clock64();
     if (clock64() - t0 > g_rs_deadline) {
         *reinterpret_cast<volatile int*>(&c->abort_local) = 1;
         atomicExch(p.abort_flag, 1);
@@ -77,50 +84,69 @@ __device__ __noinline__ bool spin_check(const RsParams& p, Ctl* c, long long& t0
     }
     return false;
 }
+#define RS_SPIN_CHECK(mask) ((((++spins) & (mask)) == 0) && ((t0 = (t0 == 0 ? clock64() : t0)), spin_check(p, ctl, t0)))
+
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 // kSleep: the 16 ingest / epilogue warps wait for the accumulator while the MMA warp issues: every instruction they spend
 // polling is an issue slot the MMA warp does not get (measured: +30 clocks per MMA), so they back off between tries
 template <bool kSleep = false>
-__device__ __forceinline__ bool wait_mbar(const RsParams& p, Ctl* c, uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool wait_mbar(const RsParams& p, Ctl* ctl, uint32_t bar, uint32_t parity) {
     long long t0 = 0;
     int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (kSleep) __nanosleep(100);
-        if (((++spins) & 15) == 0 && aborted_local(c)) return false;
-        if ((spins & 1023) == 0 && spin_check(p, c, t0)) return false;
+    while (!mbar_try_wait_s(bar, parity)) {
+        if (kSleep) __nanosleep(64);
+        if (RS_SPIN_CHECK(1023)) return false;
     }
     return true;
 }
 
-// optional checkpoints into mapped host memory (WRNN_RS_DEBUG=1): [CTA][32 warps] last (step << 8 | code) of lane 0
+// Instrumentation exists only in the kTrace instantiation of the kernel (WRNN_RS_TRACE / WRNN_RS_DEBUG select it at launch):
+// in the production instantiation every hook below compiles to nothing -- a disabled hook still cost 6-8 issue slots.
+// dbg: checkpoints into mapped host memory (WRNN_RS_DEBUG=1): [CTA][32 warps] last (step << 8 | code) of lane 0
+template <bool kTrace>
 __device__ __forceinline__ void dbg(const RsParams& p, int t, int code) {
-    if (p.dbg && (threadIdx.x & 31) == 0) {
-        *reinterpret_cast<volatile int*>(p.dbg + blockIdx.x * 32 + (threadIdx.x >> 5)) = (t << 8) | code;
+    if constexpr (kTrace) {
+        if (p.dbg && (threadIdx.x & 31) == 0) *reinterpret_cast<volatile int*>(p.dbg + blockIdx.x * 32 + (threadIdx.x >> 5)) = (t << 8) | code;
     }
 }
-
-// optional timeline (WRNN_RS_TRACE=path): %globaltimer (ns, common to all SMs) of steps [kTraceStep0, +kTraceSteps) per CTA,
-// written by lane 0 of warp 0 (events 0..8) and of the MMA warp (9..12): [CTA][step][16]
+// timeline (WRNN_RS_TRACE=path): %globaltimer (ns, common to all SMs) of steps [kTraceStep0, +kTraceSteps) per CTA, written by
+// lane 0 of warp 0 (events 0..8) and of the MMA warp (9..12): [CTA][step][48]
 constexpr int kTraceStep0 = 96, kTraceSteps = 8;
+template <bool kTrace>
 __device__ __forceinline__ void trace(const RsParams& p, int t, int ev) {
-    if (p.trace && (threadIdx.x == 0 || threadIdx.x == NW * 32) && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + ev] = ns;
+    if constexpr (kTrace) {
+        if (p.trace && (threadIdx.x == 0 || threadIdx.x == NW * 32) && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + ev] = ns;
+        }
     }
 }
-
-// SM-clock stamps of warp 0 / lane 0 inside an epilogue (slots 32 + k): the globaltimer ticks too coarsely (32-256 ns) for these
+// SM-clock stamps of warp 0 / lane 0 (slots 32 + k): the globaltimer ticks too coarsely (32-256 ns) for the inside of an epilogue
+template <bool kTrace>
 __device__ __forceinline__ void ctrace(const RsParams& p, int t, int k) {
-    if (p.trace && threadIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
-        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 32 + k] = (unsigned long long)clock64();
+    if constexpr (kTrace) {
+        if (p.trace && threadIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps)
+            p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 32 + k] = (unsigned long long)clock64();
+    }
 }
-
-// per-K-quarter events of the first ingest of a step: lane 0 of warps (q = 0, cs): slots 16 + 4 cs + {0 canaries, 1 loaded, 2 in TMEM}
-__device__ __forceinline__ void trace_kq(const RsParams& p, int t, int ev0, int cs, int k) {
-    if (p.trace && ev0 == 1 && (threadIdx.x & 127) == 0 && threadIdx.x < NW * 32 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 16 + 4 * cs + k] = ns;
+// per-K-quarter events of the first ingest of a step (warp 0, lane 0): slot 16 + kq = quarter kq of my rows is in TMEM
+template <bool kTrace>
+__device__ __forceinline__ void trace_kq(const RsParams& p, int t, int ev0, int kq) {
+    if constexpr (kTrace) {
+        if (p.trace && ev0 == 1 && threadIdx.x == 0 && t >= kTraceStep0 && t < kTraceStep0 + kTraceSteps) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            p.trace[((size_t)blockIdx.x * kTraceSteps + (t - kTraceStep0)) * 48 + 16 + kq] = ns;
+        }
     }
 }
 
@@ -132,8 +158,20 @@ __device__ __forceinline__ uint4 ld_chunk(const uint4* p) {
 __device__ __forceinline__ void st_chunk(uint4* p, uint4 v) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ bool tags_ok(uint4 v, uint32_t tb, uint32_t want) {
-    return ((((v.x ^ want) | (v.y ^ want) | (v.z ^ want) | (v.w ^ want)) & tb) == 0u);
+// generation bits of a chunk / of four chunks: nonzero = not (all) of this generation yet.  gen1 is warp-uniform, so each side
+// is a tree of three-input logic operations (8 for 16 words) instead of one XOR-OR per word
+__device__ __forceinline__ uint32_t bad1(const uint4& v, uint32_t tb, bool gen1) {
+    return gen1 ? (~(v.x & v.y & v.z & v.w) & tb) : ((v.x | v.y | v.z | v.w) & tb);
+}
+__device__ __forceinline__ uint32_t bad4(const uint4* v, uint32_t tb, bool gen1) {
+    if (gen1) {
+        const uint32_t a = (v[0].x & v[0].y & v[0].z) & (v[0].w & v[1].x & v[1].y) & (v[1].z & v[1].w & v[2].x) & (v[2].y & v[2].z & v[2].w) &
+                           (v[3].x & v[3].y & v[3].z) & v[3].w;
+        return ~a & tb;
+    }
+    const uint32_t o = (v[0].x | v[0].y | v[0].z) | (v[0].w | v[1].x | v[1].y) | (v[1].z | v[1].w | v[2].x) | (v[2].y | v[2].z | v[2].w) |
+                       (v[3].x | v[3].y | v[3].z) | v[3].w;
+    return o & tb;
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     asm volatile(
@@ -153,32 +191,45 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         : "memory");
 }
 
-template <bool kAcc>
-__device__ __forceinline__ void umma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
-    if (kAcc)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-                     "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-                     "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
-}
-
 // exp / reciprocal as ONE special-function instruction each (ex2.approx.ftz / rcp.approx.ftz): __expf and __fdividef wrap
-// the same MUFU operations in three more instructions of denormal handling, and the GRU epilogues are instruction-bound
-// (24 exp + 24 reciprocals per thread and step).  Results differ from __expf only below 1e-38, where a sigmoid is 0 or 1.
+// the same MUFU operations in three more instructions of denormal handling.
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)), 1.0f); }
-// per-unit constants live in shared memory: read them with ld.shared (the generic pointer would cost a generic LD each)
-__device__ __forceinline__ float4 lds4(const float* p) {
+// per-unit constants live in shared memory: read them with ld.shared at a 32-bit address
+__device__ __forceinline__ float4 lds4(uint32_t a) {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void lds8(const float* p, float* out) {
-    const float4 a = lds4(p), b = lds4(p + 4);
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+__device__ __forceinline__ void lds8(uint32_t a, float* out) {
+    const float4 x = lds4(a), y = lds4(a + 16);
+    out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+}
+__device__ __forceinline__ float lds1(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+// The GRU cell of 8 units: pr / pz = complete pre-activations of the reset / update gates, pn = the input side of the candidate,
+// bn = W_hn h + b_hn (what the reset gate multiplies).  The epilogues are bound by the special-function unit (16 results per
+// clock and SM: 6 per unit in the textbook form = 1536 clocks per step for 512 threads x 8 units), so reciprocals are SHARED:
+// 1/a and 1/b from one rcp(a b) -- the reset gates of a pair of units, and the update gate with the candidate's tanh of one
+// unit: 4.5 special-function results per unit.  The exponents are capped at 2^30 so that no product overflows: a sigmoid then
+// saturates at 9.3e-10 instead of 0, far below the fp32 resolution of the state it multiplies.
+constexpr float kL2E = 1.4426950408889634f;
+__device__ __forceinline__ void gru8(const float* pr, const float* pz, const float* pn, const float* bn, float* h) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const float d0 = 1.0f + ex2_ftz(fminf(-kL2E * pr[i], 30.f)), d1 = 1.0f + ex2_ftz(fminf(-kL2E * pr[i + 1], 30.f));
+        const float rr = rcp_ftz(d0 * d1);
+        const float r[2] = {d1 * rr, d0 * rr};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float dz = 1.0f + ex2_ftz(fminf(-kL2E * pz[i + j], 30.f));
+            const float dn = 1.0f + ex2_ftz(fminf((2.0f * kL2E) * fmaf(r[j], bn[i + j], pn[i + j]), 30.f));
+            const float rc = rcp_ftz(dz * dn);
+            const float z = dn * rc, n = fmaf(-2.0f * dz, rc, 1.0f);
+            h[i + j] = fmaf(z, h[i + j] - n, n);
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -192,105 +243,128 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
 
 // Exchange-side view of a thread: fold lane and the step-independent addresses.
 struct Lane {
-    int q, cs, lane, row;         // lane quadrant, column slice / K quarter, lane, fold row inside the group
-    bool live;
+    int q, cs, lane, row;         // lane quadrant, column slice, lane, fold row inside the group
+    int row_ld;                   // the row this lane READS: its own, or the group's last fold for a padding lane of a live warp
+                                  // (same bytes as a neighbour: free, and the warp needs no divergent paths)
+    bool live, wlive;             // my row is a fold / my warp has at least one fold
     uint32_t tlane;               // TMEM address of my lane quadrant, column 0
 };
 
-// Receive one activation matrix (this step's buffer) into the A operand in TMEM: warp (q, kq) takes the 16 chunks
-// [16 kq, 16 kq + 16) of its 32 folds.  `extra` (optional): one more chunk of my row, returned to the caller (T2: my own
-// units of h1).  Lanes 0..15 first poll one canary chunk each (chunk 16 kq + lane of row 32 q + lane), then every lane
-// loads its 16 chunks once and re-polls the ones whose generation bits do not match yet.
+// Receive one activation matrix (this step's buffer) into the A operand in TMEM, K QUARTER BY K QUARTER: warp (q, cs) takes
+// the four chunks 16 kq + 4 cs + {0..3} of every quarter kq of its 32 folds, so a quarter is complete -- and its eight MMAs can
+// run -- while the other quarters are still travelling or being checked.
+// `extra` (optional): one more chunk of my row, returned to the caller (T2: my own units of h1).  Lanes 0..15 first poll one
+// canary chunk each (one per producer CTA), then every lane requests two quarters; quarter kq + 2 is requested when quarter kq
+// has arrived (64 KB per CTA in flight: more than the L2 latency x bandwidth product), so the requests of ALL warps for the
+// early quarters are ahead of anybody's late ones and the quarters complete in K order across the CTA.  Per quarter: one
+// logic tree over the generation bits, re-poll until they match, strip them, one 16-column store into TMEM whose completion is
+// awaited behind the checks of the next quarter, arrive.
+// Lean on purpose: the SM issues ~1 instruction per clock and scheduler, 4 of these warps share a scheduler, so every
+// instruction here costs ~4 clocks of the step.
 // (inlined on purpose: as a real call the ABI spills around it cost more than the code size saves -- 25.8 vs 19.2 us per step)
 struct IngestOut { uint4 extra; float x; };
-__device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, const Lane& L, const uint4* mat, uint32_t tb, uint32_t want,
+template <bool kTrace>
+__device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, uint32_t ctl_s, const Lane& L, const uint4* mat, uint32_t tb, bool gen1,
                                          int extra_chunk, int dbg_t, int ev0, const unsigned long long* xw, uint32_t xtag) {
-    uint4 extra;
-    float xval = 0.f;
-    const uint4* base = mat + (size_t)(L.cs * 16) * 128 + L.row;
-    dbg(p, dbg_t, 0x10);
-    {   // phase 1: one canary chunk per lane (chunk 16 kq + (lane & 15) of my own row) until the first producer of this K
-        // quarter shows this step's generation (p.canary_all: until all do) -- one light load per lane and pass while the data
-        // is still far away; the full passes of phase 2 then overlap the arrival of the remaining producers
-        const uint4* cp = mat + (size_t)(L.cs * 16 + (L.lane & 15)) * 128 + L.row;
-        long long t0 = 0;
-        int spins = 0;
-        const bool any_live = __any_sync(0xffffffffu, L.live);
-        bool ok = !L.live;
-        while (any_live) {
-            if (!ok || !p.canary_all) ok = L.live ? tags_ok(ld_chunk(cp), tb, want) : p.canary_all != 0;
-            if (p.canary_all ? __all_sync(0xffffffffu, ok) : __any_sync(0xffffffffu, ok)) break;
-            const bool quit = ((++spins) & 255) == 0 && spin_check(p, ctl, t0);     // (spins is warp-uniform)
-            if (__any_sync(0xffffffffu, quit)) break;
+    IngestOut o;
+    o.extra = make_uint4(0u, 0u, 0u, 0u);
+    o.x = 0.f;
+    dbg<kTrace>(p, dbg_t, 0x10);
+    if (!L.wlive) {            // a quadrant of padding rows keeps whatever it holds: its accumulator rows are never read
+        if (L.lane == 0) {
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) mbar_arrive_s(ctl_s + kBarA + 8u * kq);
         }
+        return o;
     }
-    dbg(p, dbg_t, 0x11);
-    trace(p, dbg_t, ev0);
-    trace_kq(p, dbg_t, ev0, L.cs, 0);
-    if (ev0 == 1) ctrace(p, dbg_t, 8);
-    unsigned long long xword = 0ull;
-    if (xw) xword = ll_load(xw);            // the sample word was published before this matrix: its load rides along with phase 2
-    // phase 2: full passes (16 loads at immediate offsets, one OR-reduction of the generation bits) until everything matches.
-    // Lean on purpose: at 16 warps per SM every instruction of this path costs ~4 clocks of the step.
-    uint4 v[16];
-    const uint4* xp = mat + (size_t)(extra_chunk >= 0 ? extra_chunk : 0) * 128 + L.row;
-    extra = make_uint4(0u, 0u, 0u, 0u);
-    int passes = 0;
-    {
+    const uint4* base = mat + (size_t)(L.cs * 4) * 128 + L.row_ld;         // + (16 kq + i) * 128
+    {   // phase 1: one canary chunk per lane (chunk 4 (lane & 15) + cs of my row: 16 different producers) until the first
+        // producer shows this step's generation (p.canary_all: until all do) -- one light load per lane and pass while the data
+        // is still far away; the loads of phase 2 then overlap the arrival of the remaining producers
+        const uint4* cp = mat + (size_t)(4 * (L.lane & 15) + L.cs) * 128 + L.row_ld;
         long long t0 = 0;
         int spins = 0;
-        uint32_t bad;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
-        do {
-            ++passes;
-            if (L.live) {          // (padding rows are not fetched: the pass is bound by the SM's ~90 B/clk from L2)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = ld_chunk(base + i * 128);
-                if (extra_chunk >= 0) extra = ld_chunk(xp);
+        bool ok = false;
+        while (true) {
+            if (!ok) ok = bad1(ld_chunk(cp), tb, gen1) == 0u;
+            if (p.canary_all ? __all_sync(FULL, ok) : __any_sync(FULL, ok)) break;
+            if (((++spins) & 255) == 0) {               // (spins is warp-uniform)
+                if (t0 == 0) t0 = clock64();
+                if (__any_sync(FULL, spin_check(p, ctl, t0))) break;
             }
-            bad = (extra_chunk >= 0) ? ((extra.x ^ want) | (extra.y ^ want) | (extra.z ^ want) | (extra.w ^ want)) : 0u;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) bad |= (v[i].x ^ want) | (v[i].y ^ want) | (v[i].z ^ want) | (v[i].w ^ want);
-            bad = L.live ? (bad & tb) : 0u;
-        } while (bad != 0u && !(((++spins) & 255) == 0 && spin_check(p, ctl, t0)));
-    }
-    __syncwarp();
-    dbg(p, dbg_t, 0x12);
-    trace(p, dbg_t, ev0 + 1);
-    trace_kq(p, dbg_t, ev0, L.cs, 1);
-    if (ev0 == 1) ctrace(p, dbg_t, 9);
-    if (p.trace && threadIdx.x == 0 && dbg_t >= kTraceStep0 && dbg_t < kTraceStep0 + kTraceSteps)
-        p.trace[((size_t)blockIdx.x * kTraceSteps + (dbg_t - kTraceStep0)) * 48 + (ev0 == 1 ? 13 : 14)] = (unsigned long long)passes;
-    if (xw) {
-        long long t0 = 0;
-        int spins = 0;
-        while (L.live && ll_tag(xword) != xtag) {
-            xword = ll_load(xw);
-            if (((++spins) & 255) == 0 && spin_check(p, ctl, t0)) break;
         }
-        xval = L.live ? ll_val(xword) : 0.f;
     }
-    if (ev0 == 1) ctrace(p, dbg_t, 10);
-    if (want != 0u) {          // generation 1: the bit is set in every half; take it out (generation 0 needs nothing)
+    dbg<kTrace>(p, dbg_t, 0x11);
+    trace<kTrace>(p, dbg_t, ev0);
+    if (ev0 == 1) ctrace<kTrace>(p, dbg_t, 8);
+    uint4 v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i].x ^= tb; v[i].y ^= tb; v[i].z ^= tb; v[i].w ^= tb; }
-        extra.x ^= tb; extra.y ^= tb; extra.z ^= tb; extra.w ^= tb;
-    }
-    if (__any_sync(0xffffffffu, L.live)) {       // (a quadrant of padding rows keeps whatever it holds: its accumulator rows are never read)
+    for (int i = 0; i < 8; ++i) v[i] = ld_chunk(base + ((i >> 2) * 16 + (i & 3)) * 128);
+    const uint4* xp = mat + (size_t)(extra_chunk >= 0 ? extra_chunk : 0) * 128 + L.row_ld;
+    if (extra_chunk >= 0) o.extra = ld_chunk(xp);
+    unsigned long long xword = 0ull;
+    if (xw) xword = ll_load(xw);            // the sample word was published before this matrix: its load rides along
+    int passes = 1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tmem_st16(L.tlane + kColA + (uint32_t)(L.cs * 64 + j * 16), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int kq = 0; kq < 4; ++kq) {
+        uint32_t bad = bad4(&v[4 * kq], tb, gen1);
+        asm volatile("" ::"r"(bad) : "memory");          // (pins the next requests behind the arrival of this quarter: volatile asm keeps its order)
+        if (kq < 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[4 * (kq + 2) + i] = ld_chunk(base + ((kq + 2) * 16 + i) * 128);
+        }
+        if (bad != 0u) {                                   // rare: a producer of this quarter is late
+            long long t0 = 0;
+            int spins = 0;
+            do {
+                ++passes;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * kq + i] = ld_chunk(base + (kq * 16 + i) * 128);
+                bad = bad4(&v[4 * kq], tb, gen1);
+            } while (bad != 0u && !RS_SPIN_CHECK(255));
+        }
+        if (gen1) {      // generation 1: the bit is set in every half; take it out (generation 0 needs nothing)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[4 * kq + i].x ^= tb; v[4 * kq + i].y ^= tb; v[4 * kq + i].z ^= tb; v[4 * kq + i].w ^= tb; }
+        }
+        __syncwarp();
+        if (kq > 0) {              // the previous quarter's store has had the checks above to complete
+            tmem_st_wait();
+            tcgen05_fence_before();
+            if (L.lane == 0) mbar_arrive_s(ctl_s + kBarA + 8u * (kq - 1));
+            trace_kq<kTrace>(p, dbg_t, ev0, kq - 1);
+        }
+        tmem_st16(L.tlane + kColA + (uint32_t)(kq * 64 + L.cs * 16), v[4 * kq], v[4 * kq + 1], v[4 * kq + 2], v[4 * kq + 3]);
     }
     tmem_st_wait();
     tcgen05_fence_before();
-    __syncwarp();
-    if (L.lane == 0) mbar_arrive(&ctl->abar[L.cs]);
-    dbg(p, dbg_t, 0x13);
-    trace(p, dbg_t, ev0 + 2);
-    trace_kq(p, dbg_t, ev0, L.cs, 2);
-    if (ev0 == 1) ctrace(p, dbg_t, 11);
-    IngestOut o;
-    o.extra = extra; o.x = xval;
+    if (L.lane == 0) mbar_arrive_s(ctl_s + kBarA + 24u);
+    trace_kq<kTrace>(p, dbg_t, ev0, 3);
+    dbg<kTrace>(p, dbg_t, 0x12);
+    trace<kTrace>(p, dbg_t, ev0 + 2);
+    if (ev0 == 1) ctrace<kTrace>(p, dbg_t, 11);
+    if constexpr (kTrace) {
+        if (p.trace && threadIdx.x == 0 && dbg_t >= kTraceStep0 && dbg_t < kTraceStep0 + kTraceSteps)
+            p.trace[((size_t)blockIdx.x * kTraceSteps + (dbg_t - kTraceStep0)) * 48 + (ev0 == 1 ? 13 : 14)] = (unsigned long long)passes;
+    }
+    if (extra_chunk >= 0) {
+        long long t0 = 0;
+        int spins = 0;
+        while (bad1(o.extra, tb, gen1) != 0u) {
+            o.extra = ld_chunk(xp);
+            if (RS_SPIN_CHECK(255)) break;
+        }
+        if (gen1) { o.extra.x ^= tb; o.extra.y ^= tb; o.extra.z ^= tb; o.extra.w ^= tb; }
+    }
+    if (xw) {
+        long long t0 = 0;
+        int spins = 0;
+        while (ll_tag(xword) != xtag) {
+            xword = ll_load(xw);
+            if (RS_SPIN_CHECK(255)) break;
+        }
+        o.x = ll_val(xword);
+    }
     return o;
 }
 
@@ -302,72 +376,72 @@ __device__ __forceinline__ void publish8(uint4* mat, int chunk, int row, const f
     st_chunk(mat + (size_t)chunk * 128 + row, w);
 }
 
-// the MOL draw of one fold from its 30 outputs (vocoder/distribution.py:104-140; same arithmetic as loop_tc.cu), in two
-// halves: the noise depends on (step, fold) only and is drawn while the step's activations are still travelling
-struct MolNoise { float gum[10]; float lnoise; };
-__device__ __forceinline__ void mol_noise(MolNoise& nz, uint32_t t, uint32_t fold, uint32_t utt, uint2 key) {
+// The MOL draw of one fold from its 30 outputs (vocoder/distribution.py:104-140; same arithmetic as loop_tc.cu) in two halves.
+// mol_noise: the noise depends on (step, fold) only and is drawn while the step's activations are still travelling; it waits
+// in shared memory ([12][512 threads]: 10 Gumbel terms with the mixture-logit biases already added, the logistic noise) so
+// that it does not hold 11 registers across the ingest.
+__device__ __forceinline__ void mol_noise(uint32_t nz_s, uint32_t sbias_s, uint32_t t, uint32_t fold, uint32_t utt, uint2 key) {
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const uint4 r = philox4x32_10(make_uint4(t, fold, utt, (uint32_t)b), key);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int i = 4 * b + w;
-            if (i < 10) nz.gum[i] = -__logf(-__logf(1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f)));
+            if (i < 10) sts1(nz_s + 2048u * i, lds1(sbias_s + 4u * i) - __logf(-__logf(1e-5f + u01(word_of(r, w)) * (1.0f - 2e-5f))));
         }
         if (b == 2) {
             const float ul = 1e-5f + u01(r.z) * (1.0f - 2e-5f);
-            nz.lnoise = __logf(ul) - __logf(1.0f - ul);
+            sts1(nz_s + 2048u * 10, __logf(ul) - __logf(1.0f - ul));
         }
     }
 }
-__device__ __forceinline__ float mol_draw(const float* lg, const float* sbias, const MolNoise& nz) {
-    float best = -INFINITY;
+__device__ __forceinline__ float mol_draw(const float* lg, uint32_t nz_s, uint32_t sbias_s) {
+    float best = lg[0] + lds1(nz_s), mean = lg[10], lsc = lg[20];
     int kbest = 0;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const float sc = lg[i] + sbias[i] + nz.gum[i];
-        if (sc > best) { best = sc; kbest = i; }
+    for (int i = 1; i < 10; ++i) {
+        const float sc = lg[i] + lds1(nz_s + 2048u * i);
+        const bool up = sc > best;
+        best = up ? sc : best; mean = up ? lg[10 + i] : mean; lsc = up ? lg[20 + i] : lsc; kbest = up ? i : kbest;
     }
-    float mean = 0.f, lsc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i)
-        if (i == kbest) { mean = lg[10 + i] + sbias[10 + i]; lsc = lg[20 + i] + sbias[20 + i]; }
-    lsc = fmaxf(lsc, -32.23619130191664f);
-    const float xs = mean + __expf(lsc) * nz.lnoise;
+    mean += lds1(sbias_s + 40u + 4u * kbest);
+    lsc = fmaxf(lsc + lds1(sbias_s + 80u + 4u * kbest), -32.23619130191664f);
+    const float xs = fmaf(ex2_ftz(kL2E * lsc), lds1(nz_s + 2048u * 10), mean);
     return fminf(fmaxf(xs, -1.0f), 1.0f);
 }
 
 // One MMA job: D[128 folds x N] = A (TMEM, 512 fp16 per lane) x W^T (shared memory tile [k-block][N][64]); issued K quarter by K
 // quarter as the ingest warps deliver them.  Whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one); a K
-// step is one add on the descriptor and one UTCHMMA.  One rolled copy of the code for every job of every role.
-__device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t w_smem, uint32_t N, uint32_t d, uint32_t a0, uint32_t a_par,
-                                     uint64_t* done, bool wait_e, uint32_t e_par, int tt, int ev) {
+// step is one add on the descriptor and one UTCHMMA.
+template <bool kTrace>
+__device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t ctl_s, uint32_t w_smem, uint32_t N, uint32_t d, uint32_t a0, uint32_t a_par,
+                                     uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev) {
     const uint32_t idesc = umma_idesc_f16(128, (int)N);
     const uint64_t bd0 = umma_desc_sw128(w_smem);
     const uint32_t kb_step = N * 8u;                      // one k-block of the tile, in descriptor units of 16 bytes
-    // The four K quarters reach TMEM within ~0.3 us of each other, and one wait + fence + elect round costs as much as
-    // eight MMAs: wait for all four, then issue the 32 K steps in one go.
-#pragma unroll
-    for (int kq = 0; kq < 4; ++kq) wait_mbar(p, ctl, &ctl->abar[kq], a_par);
-    if (wait_e) wait_mbar(p, ctl, &ctl->ebar, e_par);
-    tcgen05_fence_after();
-    trace(p, tt, ev);
-    if (elect_one()) {
-        uint64_t bd = bd0;
-        uint32_t a = a0;
 #pragma unroll 1
-        for (int kb = 0; kb < 8; ++kb) {
+    for (int kq = 0; kq < 4; ++kq) {
+        wait_mbar(p, ctl, ctl_s + kBarA + 8u * kq, a_par);
+        if (kq == 0 && wait_e) wait_mbar(p, ctl, ctl_s + kBarE, e_par);
+        tcgen05_fence_after();
+        if (kq == 0) trace<kTrace>(p, tt, ev);
+        if (elect_one()) {
+            uint64_t bd = bd0 + (uint64_t)(2u * (uint32_t)kq * kb_step);
+            uint32_t a = a0 + 64u * (uint32_t)kq;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                umma_ts(d, a, bd + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                a += 8u;
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_ts(d, a, bd + 2u * k, idesc, (kq | kb | k) != 0 ? 1u : 0u);
+                    a += 8u;
+                }
+                bd += kb_step;
             }
-            bd += kb_step;
+            if (kq == 3) umma_commit_s(done_bar);
         }
-        umma_commit(done);
+        __syncwarp();
     }
-    __syncwarp();
-    trace(p, tt, ev + 1);
+    trace<kTrace>(p, tt, ev + 1);
 }
 
 // Per-sample conditioning records of the role-specialised loop: CS[group][step % cs_steps][fold][8][512] fp32
@@ -428,11 +502,14 @@ __device__ __forceinline__ void expand_item_rs(const float4* __restrict__ TA1, c
 
 }  // namespace
 
+template <bool kTrace>
 __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_constant__ RsParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (no static shared memory in this kernel: the dynamic window starts 1024-byte aligned, which SWIZZLE_128B tiles need;
+    //  checked below instead of rounded up -- the round-up was recomputed at every use of a shared address)
+    extern __shared__ __align__(1024) uint8_t smem[];
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + kCtlOfs);
     float* cst = reinterpret_cast<float*>(smem + kConstOfs);
+    const uint32_t smem_s = smem_u32(smem), ctl_s = smem_s + kCtlOfs, cst_s = smem_s + kConstOfs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = (int)blockIdx.x / kRsCtas, rc = (int)blockIdx.x % kRsCtas;
     const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : 3));
@@ -441,6 +518,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     const int S = p.S;
     const bool expander = (int)blockIdx.x >= p.G * kRsCtas;        // CTAs past the groups produce the conditioning records
     const unsigned int consumers = (unsigned int)(p.G * kRsCtas * NW);   // warps that read every record chunk
+    if ((smem_s & 1023u) != 0u) {          // never on this toolchain; a misaligned tile would compute garbage silently
+        if (tid == 0) atomicExch(p.abort_flag, 1);
+        return;
+    }
 
     if (expander) {
         // =================================== conditioning expander ==========================================================
@@ -468,7 +549,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cs_consumed + (c - ring_chunks)) : "memory");
                             if (v >= consumers) break;
                             __nanosleep(200);
-                            if (((++spins) & 63) == 0 && spin_check(p, ctl, t0)) break;
+                            if (RS_SPIN_CHECK(63)) break;
                         }
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
@@ -483,7 +564,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     }
 
     // ---- one-time setup: weight tiles, constants, barriers, TMEM ------------------------------------------------------
-    if ((int)blockIdx.x < p.G * kRsCtas) {
+    {
         const unsigned char* img = role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
                                  : role == 1 ? p.w2 + (size_t)cta * kWEnd
                                  : role == 2 ? p.w3 + (size_t)cta * (64 * 128 * 8) : p.w4 + (size_t)cta * (64 * 128 * 8);
@@ -502,68 +583,68 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         if (tid < 64) cst[tid] = p.v3[64 * cta + tid];
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], 4);
+        for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], NW);
         mbar_init(&ctl->dbar[0], 1); mbar_init(&ctl->dbar[1], 1);
         mbar_init(&ctl->ebar, NW);
         ctl->abort_local = 0;
         mbar_fence_init();
     }
-    if (warp == 0 && (int)blockIdx.x < p.G * kRsCtas) tmem_alloc(&ctl->tmem, 512);
+    if (warp == 0) tmem_alloc(&ctl->tmem, 512);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = ctl->tmem;
-    dbg(p, 0, 1);
-    // (register hand-over, first statement of each role's branch below: the service warpgroup gives its registers to the
-    //  16 ingest / epilogue warps, so nothing on the chain spills)
+    dbg<kTrace>(p, 0, 1);
+    // (register hand-over, first statement of each branch below: the service warpgroup gives its registers to the
+    //  16 ingest / epilogue warps)
 
     uint4* const X = p.X + (size_t)g * kMats * kRsBufs * kMatChunks;
-#define MAT(m, t) (X + ((size_t)(m) * kRsBufs + ((t) % kRsBufs)) * kMatChunks)
+#define MAT(m, t) (X + ((size_t)(m) * kRsBufs + ((t) & (kRsBufs - 1))) * kMatChunks)
 #define GEN(t) ((((t) / kRsBufs) & 1) != 0)
+    static_assert(kRsBufs == 2, "MAT / GEN assume two buffers");
 
     if (warp >= NW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsSvc));     // (one instruction for the whole warpgroup)
-        dbg(p, 0, 2);
+        dbg<kTrace>(p, 0, 2);
         if (warp == NW) {
         // =================================== MMA issuer ====================================================================
-        // whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one).  A job = 32 K-steps over the A operand
-        // in TMEM, issued K quarter by K quarter as the ingest warps deliver them.
         uint32_t n_ingest = 0;
-        auto job = [&](uint32_t N, uint32_t dcol, uint32_t wofs, uint64_t* done, bool wait_e, uint32_t e_par, int tt, int ev) {
-            mma_job(p, ctl, smem_u32(smem + wofs), N, tmem + dcol, tmem + kColA, n_ingest & 1u, done, wait_e, e_par, tt, ev);
+        auto job = [&](uint32_t N, uint32_t dcol, uint32_t wofs, uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev) {
+            mma_job<kTrace>(p, ctl, ctl_s, smem_s + wofs, N, tmem + dcol, tmem + kColA, n_ingest & 1u, done_bar, wait_e, e_par, tt, ev);
             ++n_ingest;
         };
         if (role == 0) {
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
-                if (t > 0) job(32u, kColD1, kW1, &ctl->dbar[0], false, 0, t, 9);                       // fc3 f2(t-1)
-                if (t < S) job(96u, kColD0, kW0, &ctl->dbar[1], true, (uint32_t)t & 1u, t, 11);         // W_hh1 h1(t)
+                if (t > 0) job(32u, kColD1, kW1, ctl_s + kBarD, false, 0, t, 9);                       // fc3 f2(t-1)
+                if (t < S) job(96u, kColD0, kW0, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);    // W_hh1 h1(t)
             }
         } else if (role == 1) {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                job(96u, kColD0, kW0, &ctl->dbar[0], false, 0, t, 9);                             // W_ih2a h1(t)
-                job(96u, kColD1, kW1, &ctl->dbar[1], true, (uint32_t)t & 1u, t, 11);                    // W_hh2 h2(t)
+                job(96u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);                                  // W_ih2a h1(t)
+                job(96u, kColD1, kW1, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);               // W_hh2 h2(t)
             }
         } else {
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(64u, kColD0, kW0, &ctl->dbar[0], false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(64u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
         }
         }
     } else {
         // =================================== ingest + epilogue warps ========================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-        dbg(p, 0, 3);
+        dbg<kTrace>(p, 0, 3);
         Lane L;
         L.q = warp & 3; L.cs = warp >> 2; L.lane = lane; L.row = 32 * L.q + lane; L.live = L.row < nrows;
+        L.wlive = 32 * L.q < nrows;               // a warp whose 32 rows are all padding skips loads and arithmetic (frees issue slots)
+        L.row_ld = L.live ? L.row : max(nrows - 1, 0);
         L.tlane = tmem + ((uint32_t)(32 * L.q) << 16);
-        const bool warp_live = 32 * L.q < nrows;       // a warp whose 32 rows are all padding skips the arithmetic (frees issue slots)
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        const FoldDesc fd = p.folds[L.live ? fold0 + L.row : 0];
-        const size_t srow = (size_t)(fold0 + L.row) * S;                     // my fold's row of samples / forced
-        unsigned long long* const xw = p.bX + (size_t)g * 128 + L.row;
-        const float* const csrow = p.CS + ((size_t)g * p.cs_steps * p.Ng + L.row) * 4096;   // + (t % cs_steps) * Ng * 4096
+        const FoldDesc fd = p.folds[fold0 + L.row_ld];
+        const size_t srow = (size_t)(fold0 + L.row_ld) * S;                  // my fold's row of samples / forced
+        unsigned long long* const xw = p.bX + (size_t)g * 128 + L.row_ld;
+        const float* const csrow = p.CS + ((size_t)g * p.cs_steps * p.Ng + L.row_ld) * 4096;   // + (t % cs_steps) * Ng * 4096
         const size_t cs_step = (size_t)p.Ng * 4096;
         // the expanders run a few chunks ahead: before the first step of a chunk, lane 0 acquires its counter
         auto cs_wait = [&](int t) {
-            if (p.cs_done && (t % kRsChunk) == 0) {
+            if (p.cs_done && (t & (kRsChunk - 1)) == 0) {
                 if (lane == 0) {
                     long long t0 = 0;
                     int spins = 0;
@@ -571,7 +652,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                         unsigned int v;
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cs_done + t / kRsChunk) : "memory");
                         if (v >= (unsigned int)p.B) break;
-                        if (((++spins) & 63) == 0 && spin_check(p, ctl, t0)) break;
+                        if (RS_SPIN_CHECK(63)) break;
                     }
                 }
                 __syncwarp();
@@ -579,9 +660,18 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         };
         // ... and after the last step of a chunk (its records are in registers and used) the warp hands the ring slot back
         auto cs_release = [&](int t) {
-            if (p.cs_done && ((t % kRsChunk) == kRsChunk - 1 || t == S - 1)) {
+            if (p.cs_done && ((t & (kRsChunk - 1)) == kRsChunk - 1 || t == S - 1)) {
                 __syncwarp();
                 if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cs_consumed + t / kRsChunk) : "memory");
+            }
+        };
+        // three gate planes of my 8 units from a conditioning record: a[0..7] r, a[8..15] z, a[16..23] n
+        auto load_rec24 = [&](const float* c, float* a) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 lo = __ldcg(reinterpret_cast<const float4*>(c + k * 512)), hi = __ldcg(reinterpret_cast<const float4*>(c + k * 512) + 1);
+                a[8 * k + 0] = lo.x; a[8 * k + 1] = lo.y; a[8 * k + 2] = lo.z; a[8 * k + 3] = lo.w;
+                a[8 * k + 4] = hi.x; a[8 * k + 5] = hi.y; a[8 * k + 6] = hi.z; a[8 * k + 7] = hi.w;
             }
         };
         if (role == 0) {
@@ -589,88 +679,87 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             float h1[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) h1[i] = 0.f;
-            const float* v1 = cst + L.cs * 8;                    // [a][32]: + 32 a
-            const float* sbias = cst + 128;
+            const uint32_t v1_s = cst_s + 32u * L.cs;            // [a][32 units]: + 128 a bytes
+            const uint32_t sbias_s = cst_s + 512u;
+            const uint32_t nz_s = smem_s + kNoiseOfs + 4u * tid;
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
-                trace(p, t, 0);
-                float c1[24];
+                trace<kTrace>(p, t, 0);
+                // everything that does not need f2(t-1) happens BEFORE the wait for it: the conditioning record, the mixture
+                // noise, and the recurrent accumulator W_hh1 h1(t-1) (complete since the off-path job of the previous step)
+                // folded into the record: a[] = (c_r + gh_r, c_z + gh_z, c_n), bn[] = gh_n + b_hn
+                float a[24], bn[8];
                 if (t < S) cs_wait(t);
-                if (t < S && L.live) {
-                    const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs;
+                if (t < S && L.wlive) load_rec24(csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs, a);
+                if (t > 0 && L.wlive) mol_noise(nz_s, sbias_s, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
+                if (t > 0) {
+                    wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(t - 1) & 1u);      // recurrent job of step t-1: D0 complete, A free
+                    tcgen05_fence_after();
+                }
+                if (t < S) {
+                    if (L.wlive) {
+                        lds8(v1_s + 384u, bn);
+                        if (t > 0) {
+                            float gh[24];
+                            tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, gh + 8);
+                            tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, gh + 16);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float4 lo = __ldcg(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcg(reinterpret_cast<const float4*>(c + a * 512) + 1);
-                        c1[8 * a + 0] = lo.x; c1[8 * a + 1] = lo.y; c1[8 * a + 2] = lo.z; c1[8 * a + 3] = lo.w;
-                        c1[8 * a + 4] = hi.x; c1[8 * a + 5] = hi.y; c1[8 * a + 6] = hi.z; c1[8 * a + 7] = hi.w;
+                            for (int i = 0; i < 8; ++i) { a[i] += gh[i]; a[8 + i] += gh[8 + i]; bn[i] += gh[16 + i]; }
+                        }
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 24; ++i) c1[i] = 0.f;
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_s(ctl_s + kBarE);
                 }
                 float x = 0.f;
                 if (t > 0) {
-                    MolNoise nz;
-                    if (warp_live) mol_noise(nz, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
-                    // the A buffer is free once the recurrent job of step t-1 has completed
-                    wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
+                    ingest<kTrace>(p, ctl, ctl_s, L, MAT(MF2, t - 1), kTagS, GEN(t - 1), -1, t, 1, nullptr, 0u);
+                    ctrace<kTrace>(p, t, 0);
+                    wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
-                    ingest(p, ctl, L, MAT(MF2, t - 1), kTagS, GEN(t - 1) ? kTagS : 0u, -1, t, 1, nullptr, 0u);
-                    ctrace(p, t, 0);
-                    wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)(t - 1) & 1u);
-                    tcgen05_fence_after();
-                    trace(p, t, 4);
-                    ctrace(p, t, 1);
-                    float lg[32];
-                    tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
-                    tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
-                    tmem_ld_wait();
-                    ctrace(p, t, 2);
-                    const float xs = warp_live ? mol_draw(lg, sbias, nz) : 0.f;
-                    x = xs;
-                    if (L.live) {
+                    trace<kTrace>(p, t, 4);
+                    ctrace<kTrace>(p, t, 1);
+                    if (L.wlive) {
+                        float lg[32];
+                        tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
+                        tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
+                        tmem_ld_wait();
+                        ctrace<kTrace>(p, t, 2);
+                        const float xs = mol_draw(lg, nz_s, sbias_s);
+                        x = xs;
                         if (p.forced) x = p.forced[srow + t - 1];
-                        if (cta == 0 && L.cs == 0) {
+                        if (cta == 0 && L.cs == 0 && L.live) {
                             p.samples[srow + t - 1] = xs;
                             ll_store(xw, x, (uint32_t)t);
                             if (p.logits_out)
-                                for (int i = 0; i < 30; ++i) p.logits_out[(srow + t - 1) * 30 + i] = lg[i] + sbias[i];
+                                for (int i = 0; i < 30; ++i) p.logits_out[(srow + t - 1) * 30 + i] = lg[i] + lds1(sbias_s + 4u * i);
                         }
                     }
+                    tcgen05_fence_before();
                 }
                 if (t == S) break;
-                ctrace(p, t, 3);
-                float gh[24];
-                if (t > 0) {
-                    tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, gh + 8);
-                    tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, gh + 16);
-                    tmem_ld_wait();
-                } else {
+                ctrace<kTrace>(p, t, 3);
+                if (L.wlive) {
+                    float kr[8];
+                    lds8(v1_s, kr);
 #pragma unroll
-                    for (int i = 0; i < 24; ++i) gh[i] = 0.f;
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->ebar);
-                ctrace(p, t, 4);
-                if (warp_live) {
-                float kr[8], kz[8], kn[8], kb[8];
-                lds8(v1, kr); lds8(v1 + 32, kz); lds8(v1 + 64, kn); lds8(v1 + 96, kb);
+                    for (int i = 0; i < 8; ++i) a[i] = fmaf(kr[i], x, a[i]);
+                    lds8(v1_s + 128u, kr);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float r = sigmoid_fast(fmaf(kr[i], x, c1[i]) + gh[i]);
-                    const float z = sigmoid_fast(fmaf(kz[i], x, c1[8 + i]) + gh[8 + i]);
-                    const float n = tanh_fast(fmaf(kn[i], x, c1[16 + i]) + r * (gh[16 + i] + kb[i]));
-                    h1[i] = fmaf(z, h1[i] - n, n);
+                    for (int i = 0; i < 8; ++i) a[8 + i] = fmaf(kr[i], x, a[8 + i]);
+                    lds8(v1_s + 256u, kr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[16 + i] = fmaf(kr[i], x, a[16 + i]);
+                    gru8(a, a + 8, a + 16, bn, h1);
+                    ctrace<kTrace>(p, t, 5);
+                    if (L.live) publish8(MAT(MH1, t), 4 * cta + L.cs, L.row, h1, kTagE, GEN(t) ? kTagE : 0u);
                 }
-                ctrace(p, t, 5);
-                if (L.live) publish8(MAT(MH1, t), 4 * cta + L.cs, L.row, h1, kTagE, GEN(t) ? kTagE : 0u);
-                }
-                trace(p, t, 5);
-                ctrace(p, t, 6);
+                trace<kTrace>(p, t, 5);
+                ctrace<kTrace>(p, t, 6);
                 // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited).
                 // Off the critical path: wait until the T2 CTAs have read the same lines for the on-path product.
                 __nanosleep(p.offpath_delay_ns);
-                ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
+                ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH1, t), kTagE, GEN(t), -1, t, 6, nullptr, 0u);
                 cs_release(t);
                 if (cta == 0 && g == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
                     *reinterpret_cast<volatile int*>(p.progress) = t;
@@ -682,111 +771,120 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             float h2[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) h2[i] = 0.f;
-            const float* v2 = cst + L.cs * 8;
+            const uint32_t v2_s = cst_s + 32u * L.cs;
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                trace(p, t, 0);
-                float c2[24];
+                trace<kTrace>(p, t, 0);
+                // before the wait for h1(t): the record and the recurrent accumulator W_hh2 h2(t-1), folded together (see T1)
+                float a[24], bn[8];
                 cs_wait(t);
-                if (L.live) {
-                    const float* c = csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float4 lo = __ldcg(reinterpret_cast<const float4*>(c + a * 512)), hi = __ldcg(reinterpret_cast<const float4*>(c + a * 512) + 1);
-                        c2[8 * a + 0] = lo.x; c2[8 * a + 1] = lo.y; c2[8 * a + 2] = lo.z; c2[8 * a + 3] = lo.w;
-                        c2[8 * a + 4] = hi.x; c2[8 * a + 5] = hi.y; c2[8 * a + 6] = hi.z; c2[8 * a + 7] = hi.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 24; ++i) c2[i] = 0.f;
-                }
+                if (L.wlive) load_rec24(csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs, a);
                 if (t > 0) {
-                    wait_mbar(p, ctl, &ctl->dbar[1], (uint32_t)(t - 1) & 1u);
+                    wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
                 }
-                const IngestOut io = ingest(p, ctl, L, MAT(MH1, t), kTagE, GEN(t) ? kTagE : 0u, 4 * cta + L.cs, t, 1, t > 0 ? xw : nullptr, (uint32_t)t);
-                const float x = io.x;
-                const uint4 extra = io.extra;
-                dbg(p, t, 0x30);
-                ctrace(p, t, 0);
-                wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
-                tcgen05_fence_after();
-                dbg(p, t, 0x31);
-                trace(p, t, 4);
-                ctrace(p, t, 1);
-                float pb[24], gh[24];
-                tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, pb); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, pb + 8);
-                tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, pb + 16);
-                if (t > 0) {
-                    tmem_ld8(L.tlane + kColD1 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD1 + 32 + 8 * L.cs, gh + 8);
-                    tmem_ld8(L.tlane + kColD1 + 64 + 8 * L.cs, gh + 16);
-                } else {
+                if (L.wlive) {
+                    lds8(v2_s + 384u, bn);
+                    if (t > 0) {
+                        float gh[24];
+                        tmem_ld8(L.tlane + kColD1 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD1 + 32 + 8 * L.cs, gh + 8);
+                        tmem_ld8(L.tlane + kColD1 + 64 + 8 * L.cs, gh + 16);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 24; ++i) gh[i] = 0.f;
+                        for (int i = 0; i < 8; ++i) { a[i] += gh[i]; a[8 + i] += gh[8 + i]; bn[i] += gh[16 + i]; }
+                    }
                 }
-                tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->ebar);
-                ctrace(p, t, 4);
-                float s2[8];
-                const float2 e0 = unpack2(extra.x), e1 = unpack2(extra.y), e2 = unpack2(extra.z), e3 = unpack2(extra.w);
-                const float h1o[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
-                if (warp_live) {
-                float kr[8], kz[8], kn[8], kb[8];
-                lds8(v2, kr); lds8(v2 + 32, kz); lds8(v2 + 64, kn); lds8(v2 + 96, kb);
+                if (lane == 0) mbar_arrive_s(ctl_s + kBarE);
+                const IngestOut io = ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH1, t), kTagE, GEN(t), 4 * cta + L.cs, t, 1, t > 0 ? xw : nullptr, (uint32_t)t);
+                const float x = io.x;
+                dbg<kTrace>(p, t, 0x30);
+                ctrace<kTrace>(p, t, 0);
+                if (L.wlive) {              // the sample's rank-1 term while the last MMAs run
+                    float kr[8];
+                    lds8(v2_s, kr);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float r = sigmoid_fast(pb[i] + fmaf(kr[i], x, c2[i]) + gh[i]);
-                    const float z = sigmoid_fast(pb[8 + i] + fmaf(kz[i], x, c2[8 + i]) + gh[8 + i]);
-                    const float n = tanh_fast(pb[16 + i] + fmaf(kn[i], x, c2[16 + i]) + r * (gh[16 + i] + kb[i]));
-                    h2[i] = fmaf(z, h2[i] - n, n);
-                    s2[i] = fminf(fmaxf(h1o[i] + h2[i], -1.9990234375f), 1.9990234375f);
+                    for (int i = 0; i < 8; ++i) a[i] = fmaf(kr[i], x, a[i]);
+                    lds8(v2_s + 128u, kr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[8 + i] = fmaf(kr[i], x, a[8 + i]);
+                    lds8(v2_s + 256u, kr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[16 + i] = fmaf(kr[i], x, a[16 + i]);
                 }
-                ctrace(p, t, 5);
-                if (L.live) {
-                    publish8(MAT(MS2, t), 4 * cta + L.cs, L.row, s2, kTagE, GEN(t) ? kTagE : 0u);
-                    publish8(MAT(MH2, t), 4 * cta + L.cs, L.row, h2, kTagE, GEN(t) ? kTagE : 0u);
+                wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
+                tcgen05_fence_after();
+                dbg<kTrace>(p, t, 0x31);
+                trace<kTrace>(p, t, 4);
+                ctrace<kTrace>(p, t, 1);
+                if (L.wlive) {
+                    float pb[24];
+                    tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, pb); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, pb + 8);
+                    tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, pb + 16);
+                    tmem_ld_wait();
+                    tcgen05_fence_before();
+                    ctrace<kTrace>(p, t, 4);
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) a[i] += pb[i];
+                    gru8(a, a + 8, a + 16, bn, h2);
+                    const float2 e0 = unpack2(io.extra.x), e1 = unpack2(io.extra.y), e2 = unpack2(io.extra.z), e3 = unpack2(io.extra.w);
+                    const float h1o[8] = {e0.x, e0.y, e1.x, e1.y, e2.x, e2.y, e3.x, e3.y};
+                    float s2[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s2[i] = fminf(fmaxf(h1o[i] + h2[i], -1.9990234375f), 1.9990234375f);
+                    ctrace<kTrace>(p, t, 5);
+                    if (L.live) {
+                        publish8(MAT(MS2, t), 4 * cta + L.cs, L.row, s2, kTagE, GEN(t) ? kTagE : 0u);
+                        publish8(MAT(MH2, t), 4 * cta + L.cs, L.row, h2, kTagE, GEN(t) ? kTagE : 0u);
+                    }
                 }
-                }
-                trace(p, t, 5);
-                ctrace(p, t, 6);
-                ingest(p, ctl, L, MAT(MH2, t), kTagE, GEN(t) ? kTagE : 0u, -1, t, 6, nullptr, 0u);
+                trace<kTrace>(p, t, 5);
+                ctrace<kTrace>(p, t, 6);
+                ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH2, t), kTagE, GEN(t), -1, t, 6, nullptr, 0u);
                 cs_release(t);
             }
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
             const bool fc1 = role == 2;
-            const float* v3 = cst + L.cs * 16;
+            const uint32_t v3_s = cst_s + 64u * L.cs;
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                trace(p, t, 0);
+                trace<kTrace>(p, t, 0);
                 float cc[16];
                 cs_wait(t);
-                if (L.live) {
+                if (L.wlive) {
                     const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + 64 * cta + 16 * L.cs);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { const float4 q4 = __ldcg(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) cc[i] = 0.f;
                 }
-                const float x = ingest(p, ctl, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t) ? (fc1 ? kTagE : kTagS) : 0u, -1, t, 1,
-                                       (fc1 && t > 0) ? xw : nullptr, (uint32_t)t).x;
-                wait_mbar<true>(p, ctl, &ctl->dbar[0], (uint32_t)t & 1u);
+                const float x = ingest<kTrace>(p, ctl, ctl_s, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t), -1, t, 1,
+                                               (fc1 && t > 0) ? xw : nullptr, (uint32_t)t).x;
+                if (fc1 && L.wlive) {
+                    float kv[8];
+                    lds8(v3_s, kv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cc[i] = fmaf(kv[i], x, cc[i]);
+                    lds8(v3_s + 32u, kv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cc[8 + i] = fmaf(kv[i], x, cc[8 + i]);
+                }
+                wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
                 tcgen05_fence_after();
-                trace(p, t, 4);
-                float d[16];
-                tmem_ld8(L.tlane + kColD0 + 16 * L.cs, d); tmem_ld8(L.tlane + kColD0 + 16 * L.cs + 8, d + 8);
-                tmem_ld_wait();
-                tcgen05_fence_before();
+                trace<kTrace>(p, t, 4);
+                if (L.wlive) {
+                    float d[16];
+                    tmem_ld8(L.tlane + kColD0 + 16 * L.cs, d); tmem_ld8(L.tlane + kColD0 + 16 * L.cs + 8, d + 8);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i] + (fc1 ? fmaf(v3[i], x, cc[i]) : cc[i]), 0.f);
-                if (L.live) {
-                    uint4* m = MAT(fc1 ? MF1 : MF2, t);
-                    const uint32_t want = GEN(t) ? kTagS : 0u;
-                    publish8(m, 8 * cta + 2 * L.cs, L.row, d, kTagS, want);
-                    publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
+                    for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i] + cc[i], 0.f);
+                    if (L.live) {
+                        uint4* m = MAT(fc1 ? MF1 : MF2, t);
+                        const uint32_t want = GEN(t) ? kTagS : 0u;
+                        publish8(m, 8 * cta + 2 * L.cs, L.row, d, kTagS, want);
+                        publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
+                    }
                 }
-                trace(p, t, 5);
+                tcgen05_fence_before();
+                trace<kTrace>(p, t, 5);
                 cs_release(t);
             }
         }
@@ -794,7 +892,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
 #undef MAT
 #undef GEN
     // ---- teardown ---------------------------------------------------------------------------------------------------
-    dbg(p, 0, 0xFF);
+    dbg<kTrace>(p, 0, 0xFF);
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -825,12 +923,14 @@ cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const fl
 }
 
 cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream) {
-    cudaError_t err = cudaFuncSetAttribute(wrnn_loop_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024);
+    // the instrumented instantiation only when a timeline or checkpoints were asked for
+    const void* fn = (p.trace || p.dbg) ? (const void*)wrnn_loop_rs_kernel<true> : (const void*)wrnn_loop_rs_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
     RsParams pp = p;
     void* args[] = {&pp};
     const int grid = p.G * kRsCtas + (p.cs_done ? p.n_expanders : 0);
-    return cudaLaunchCooperativeKernel((const void*)wrnn_loop_rs_kernel, dim3(grid), dim3(NT), args, kSmemBytes + 1024, stream);
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, kSmemBytes, stream);
 }
 
 }  // namespace wrnn

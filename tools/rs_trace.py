@@ -50,11 +50,10 @@ for g in range(min(G, 1)):
             order = [8, 9, 10, 11, 0, 1, 2, 3, 4, 5, 6]
             base = cl[8]
             line += "\n        warp-0 clocks since its canaries: " + " | ".join("%s %.0f" % (nm[j], cl[j] - base) for j in order if not np.isnan(cl[j]))
+            line += "\n        K quarters in TMEM (warp 0):"
             for q in range(4):
-                line += "\n        K quarter %d:" % q
-                for j, nm in enumerate(["canaries", "loaded", "in TMEM"]):
-                    v = ev[cs, k, 16 + 4 * q + j] - origin
-                    line += " %s %.2f..%.2f" % (nm, np.nanmin(v) / 1e3, np.nanmax(v) / 1e3)
+                v = ev[cs, k, 16 + q] - origin
+                line += " %d: %.2f..%.2f" % (q, np.nanmin(v) / 1e3, np.nanmax(v) / 1e3)
         print(line)
         if k >= 2:
             break
