@@ -247,14 +247,15 @@ struct Lane {
     int row_ld;                   // the row this lane READS: its own, or the group's last fold for a padding lane of a live warp
                                   // (same bytes as a neighbour: free, and the warp needs no divergent paths)
     bool live, wlive;             // my row is a fold / my warp has at least one fold
+    int nlive_threads;            // threads of the CTA's live ingest warps (the named barrier behind the canary poll)
     uint32_t tlane;               // TMEM address of my lane quadrant, column 0
 };
 
 // Receive one activation matrix (this step's buffer) into the A operand in TMEM, K QUARTER BY K QUARTER: warp (q, cs) takes
 // the four chunks 16 kq + 4 cs + {0..3} of every quarter kq of its 32 folds, so a quarter is complete -- and its eight MMAs can
 // run -- while the other quarters are still travelling or being checked.
-// `extra` (optional): one more chunk of my row, returned to the caller (T2: my own units of h1).  Lanes 0..15 first poll one
-// canary chunk each (one per producer CTA), then every lane requests two quarters; quarter kq + 2 is requested when quarter kq
+// `extra` (optional): one more chunk of my row, returned to the caller (T2: my own units of h1).  Warp 0 first polls canary
+// chunks (one per lane and producer warp), then every lane requests two quarters; quarter kq + 2 is requested when quarter kq
 // has arrived (64 KB per CTA in flight: more than the L2 latency x bandwidth product), so the requests of ALL warps for the
 // early quarters are ahead of anybody's late ones and the quarters complete in K order across the CTA.  Per quarter: one
 // logic tree over the generation bits, re-poll until they match, strip them, one 16-column store into TMEM whose completion is
@@ -278,21 +279,25 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, uint32_
         return o;
     }
     const uint4* base = mat + (size_t)(L.cs * 4) * 128 + L.row_ld;         // + (16 kq + i) * 128
-    {   // phase 1: one canary chunk per lane (chunk 4 (lane & 15) + cs of my row: 16 different producers) until the first
-        // producer shows this step's generation (p.canary_all: until all do) -- one light load per lane and pass while the data
-        // is still far away; the loads of phase 2 then overlap the arrival of the remaining producers
-        const uint4* cp = mat + (size_t)(4 * (L.lane & 15) + L.cs) * 128 + L.row_ld;
-        long long t0 = 0;
-        int spins = 0;
-        bool ok = false;
-        while (true) {
-            if (!ok) ok = bad1(ld_chunk(cp), tb, gen1) == 0u;
-            if (p.canary_all ? __all_sync(FULL, ok) : __any_sync(FULL, ok)) break;
-            if (((++spins) & 255) == 0) {               // (spins is warp-uniform)
-                if (t0 == 0) t0 = clock64();
-                if (__any_sync(FULL, spin_check(p, ctl, t0))) break;
+    {   // phase 1, ONE warp per CTA: lane l polls the canary chunk 2 l of the group's first fold (32 different producer warps:
+        // every CTA of the producing role) until the first of them shows this step's generation (p.canary_all: until all
+        // do); the other live warps sleep on a named barrier.  (All 16 warps polling cost 16 KB of L2 traffic per CTA and
+        // round trip, with ~100 CTAs waiting at any time: 13.1 -> 12.75 us per step at 213 folds.)
+        if (L.q == 0 && L.cs == 0) {
+            const uint4* cp = mat + (size_t)(2 * L.lane) * 128;
+            long long t0 = 0;
+            int spins = 0;
+            bool ok = false;
+            while (true) {
+                if (!ok) ok = bad1(ld_chunk(cp), tb, gen1) == 0u;
+                if (p.canary_all ? __all_sync(FULL, ok) : __any_sync(FULL, ok)) break;
+                if (((++spins) & 255) == 0) {               // (spins is warp-uniform)
+                    if (t0 == 0) t0 = clock64();
+                    if (__any_sync(FULL, spin_check(p, ctl, t0))) break;
+                }
             }
         }
+        asm volatile("bar.sync 2, %0;" ::"r"(L.nlive_threads) : "memory");
     }
     dbg<kTrace>(p, dbg_t, 0x11);
     trace<kTrace>(p, dbg_t, ev0);
@@ -396,16 +401,26 @@ __device__ __forceinline__ void mol_noise(uint32_t nz_s, uint32_t sbias_s, uint3
     }
 }
 __device__ __forceinline__ float mol_draw(const float* lg, uint32_t nz_s, uint32_t sbias_s) {
-    float best = lg[0] + lds1(nz_s), mean = lg[10], lsc = lg[20];
-    int kbest = 0;
+    // argmax over the 10 perturbed mixture logits as a TREE (depth 4 instead of a chain of 9 dependent compare-selects: the
+    // draw sits on the critical path of every step); ties keep the lower index, as the sequential scan does
+    float sc[10], mu[10], ls[10];
+    int kx[10];
 #pragma unroll
-    for (int i = 1; i < 10; ++i) {
-        const float sc = lg[i] + lds1(nz_s + 2048u * i);
-        const bool up = sc > best;
-        best = up ? sc : best; mean = up ? lg[10 + i] : mean; lsc = up ? lg[20 + i] : lsc; kbest = up ? i : kbest;
-    }
-    mean += lds1(sbias_s + 40u + 4u * kbest);
-    lsc = fmaxf(lsc + lds1(sbias_s + 80u + 4u * kbest), -32.23619130191664f);
+    for (int i = 0; i < 10; ++i) { sc[i] = lg[i] + lds1(nz_s + 2048u * i); mu[i] = lg[10 + i]; ls[i] = lg[20 + i]; kx[i] = i; }
+    auto pick = [&](int l, int r) {
+        const bool up = sc[r] > sc[l];
+        sc[l] = up ? sc[r] : sc[l]; mu[l] = up ? mu[r] : mu[l]; ls[l] = up ? ls[r] : ls[l]; kx[l] = up ? kx[r] : kx[l];
+    };
+#ifdef RS_DRAW_CHAIN
+    for (int i = 1; i < 10; ++i) pick(0, i);
+#else
+    pick(0, 1); pick(2, 3); pick(4, 5); pick(6, 7); pick(8, 9);
+    pick(0, 2); pick(4, 6);
+    pick(0, 4);
+    pick(0, 8);
+#endif
+    const float mean = mu[0] + lds1(sbias_s + 40u + 4u * kx[0]);
+    const float lsc = fmaxf(ls[0] + lds1(sbias_s + 80u + 4u * kx[0]), -32.23619130191664f);
     const float xs = fmaf(ex2_ftz(kL2E * lsc), lds1(nz_s + 2048u * 10), mean);
     return fminf(fmaxf(xs, -1.0f), 1.0f);
 }
@@ -635,6 +650,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         L.q = warp & 3; L.cs = warp >> 2; L.lane = lane; L.row = 32 * L.q + lane; L.live = L.row < nrows;
         L.wlive = 32 * L.q < nrows;               // a warp whose 32 rows are all padding skips loads and arithmetic (frees issue slots)
         L.row_ld = L.live ? L.row : max(nrows - 1, 0);
+        L.nlive_threads = 4 * 32 * ((nrows + 31) / 32);
         L.tlane = tmem + ((uint32_t)(32 * L.q) << 16);
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         const FoldDesc fd = p.folds[fold0 + L.row_ld];
