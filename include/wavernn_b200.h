@@ -51,6 +51,13 @@ typedef void (*wrnn_progress_fn)(int64_t i, int64_t seq_len, int64_t b_size, dou
  * upsample (5,5,8), hop 200, pad 2, feat 80); `bits` 8..10 for RAW (the reference trains 9 and 10); MOL has 30 outputs; anything else: WRNN_ERR_INVALID. */
 int wrnn_create(int device, int bits, int mode, wrnn_engine** out);
 int wrnn_destroy(wrnn_engine* e);
+/* base.init_voc_model(MODEL_TYPE_RUNTIMERACER, ...) -- vocoder/models/base.py:82-104, the model type vocoder/inference.py:43
+ * hard-codes for the reference's C++ path: four GRU-256 cells on a residual chain and five FC layers
+ * (vocoder/models/runtimeracer_version.py:119-132), the fatchord front end (config/hparams.py:355-366).  Call between
+ * wrnn_create and the first wrnn_set_tensor; the state_dict names are the reference's (I, rnn1..rnn4, fc1..fc5, upsample.*).
+ * This topology runs WRNN_PREC_F32 only (wrnn_loop_rr_kernel).                                                             */
+enum { WRNN_TOPO_FATCHORD = 0, WRNN_TOPO_RUNTIMERACER = 1 };
+int wrnn_set_topology(wrnn_engine* e, int topology);
 const char* wrnn_last_error(const wrnn_engine* e);
 
 /* model.load_state_dict(checkpoint["model_state"]) -- vocoder/inference.py:35.  One call per entry of
@@ -107,7 +114,7 @@ typedef struct {
     int32_t n_folds, n_steps, n_launches;
     int32_t loop_kernel;        /* which loop ran the last wave: WRNN_LOOP_F32 / _TC / _RS / _SPARSE / _TC2     */
 } wrnn_request;
-enum { WRNN_LOOP_F32 = 0, WRNN_LOOP_TC = 1, WRNN_LOOP_RS = 2, WRNN_LOOP_SPARSE = 3, WRNN_LOOP_TC2 = 4 };
+enum { WRNN_LOOP_F32 = 0, WRNN_LOOP_TC = 1, WRNN_LOOP_RS = 2, WRNN_LOOP_SPARSE = 3, WRNN_LOOP_TC2 = 4, WRNN_LOOP_RR = 5 };
 
 /* WaveRNN.generate(mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback)
  * -- fatchord_version.py:155-259 -- for one or many utterances, end to end on the GPU:

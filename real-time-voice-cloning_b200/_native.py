@@ -6,9 +6,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WRNN_B200_LIB") or os.path.join(HERE, "libwavernn_b200.so")   # override: A/B timing of kernel variants
 
-LOOP_KERNELS = {0: "wrnn_loop_f32_kernel", 1: "wrnn_loop_tc_kernel", 2: "wrnn_loop_rs_kernel", 3: "wrnn_loop_sparse_kernel", 4: "wrnn_loop_tc2_kernel"}
+LOOP_KERNELS = {0: "wrnn_loop_f32_kernel", 1: "wrnn_loop_tc_kernel", 2: "wrnn_loop_rs_kernel", 3: "wrnn_loop_sparse_kernel", 4: "wrnn_loop_tc2_kernel", 5: "wrnn_loop_rr_kernel"}
 OK, ERR_INVALID, ERR_NOT_LOADED, ERR_CUDA, ERR_TIMEOUT, ERR_SHAPE, ERR_TOO_SHORT = 0, -1, -2, -3, -4, -5, -6
 MODE_RAW, MODE_MOL = 0, 1
+TOPO_FATCHORD, TOPO_RUNTIMERACER = 0, 1
 PREC_F32, PREC_F16, PREC_SPARSE_F32 = 0, 1, 2
 PREC_AUTO = -1        # host-side only: resolved per call by vocoder/models/fatchord_version.py:resolve_precision
 
@@ -46,7 +47,7 @@ class Request(C.Structure):
     ]
 
 
-EXPORTS = ["wrnn_create", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
+EXPORTS = ["wrnn_create", "wrnn_set_topology", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
            "wrnn_finalize", "wrnn_sparsity", "wrnn_sparse_available", "wrnn_fold_plan", "wrnn_generate", "wrnn_condition", "wrnn_condition_tc", "wrnn_postprocess",
            "wrnn_xfade_unfold", "wrnn_barrier_floor", "wrnn_cluster_floor", "wrnn_debug_umma_rate", "wrnn_debug_tc_gemm", "wrnn_debug_tc_gemm2", "wrnn_launch_count"]
 
@@ -64,6 +65,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.wrnn_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.wrnn_set_topology.argtypes = [vp, C.c_int]
     lib.wrnn_destroy.argtypes = [vp]
     lib.wrnn_last_error.argtypes = [vp]
     lib.wrnn_last_error.restype = C.c_char_p

@@ -150,6 +150,38 @@ cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream);
 cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                   const FoldDesc* folds, int B, int S, int Ng, int cs_steps, float* CS, cudaStream_t stream);
 
+// ---- runtimeracer-wavernn topology (loop_rr.cu): four GRU-256 + five FC layers, fp32 ---------------------------------
+constexpr int kRrH = 256;            // rnn_dims = fc_dims (config/hparams.py:363-364)
+constexpr int kRrCtas = 128;         // 2 hidden units of every layer per CTA
+constexpr int kRrMaxFolds = 32;      // folds per launch (longer batches run in waves)
+struct RrLoopParams {
+    const float* Whh[4];         // rnn1..4 weight_hh [768][256]
+    const float* Wih[3];         // rnn2, rnn3[:, :256], rnn4 weight_ih [768][256] (rnn1's is folded into the tables)
+    const float *M12, *M34;      // fc2 fc1[:, :256], fc4 fc3[:, :256]  [256][256] (no activation between the pairs)
+    const float* Wfc5;           // [C][256]
+    const float* u;              // [13][256] coefficients of the previous sample: GRU1..4 (r, z, n) and the M12 station
+    const float* bhn;            // [4][256] b_hn of the four GRUs
+    const float* bfc5;           // [C]
+    // per-frame tables, 4 float4 per hidden unit: {c1 r,z,n, c5} {c2 r,z,n, c6} {c3 r,z,n, 0} {c4 r,z,n, 0}
+    // TA[frame row][256][4] from the aux channels (+ biases), TQ[padded frame row][256][4] from the padded mel frames
+    const float4 *TA, *TQ;
+    const float* coef;           // [200][kTaps] interpolation weights of the upsampling stack
+    const FoldDesc* folds;
+    int B, S, C, Cpad, CR, mode;
+    unsigned long long seed;
+    unsigned long long* bH[4];   // exchange words {value, tag}: [B][256] each
+    unsigned long long *bY2, *bY4, *bLG, *bX;
+    float* samples;
+    float* logits_out;
+    const float* forced;
+    int* progress;
+    int* abort_flag;
+};
+using RrParams = RrLoopParams;
+size_t loop_rr_smem_bytes(int B, int CR);
+cudaError_t set_rr_deadline(long long cycles);
+cudaError_t launch_loop_rr(const RrLoopParams& p, cudaStream_t stream);
+
 // ---- cluster-local tensor-core loop, MOL (loop_tc2.cu) --------------------------------------------------------------
 struct Tc2Params {
     const unsigned char* wimg;   // [16][loop_tc2_image_bytes()] per-CTA streams of pre-swizzled weight tiles

@@ -45,12 +45,15 @@ def _raise(lib, handle, rc):
 
 
 class WaveRNN(object):
+    _FIXED_DIMS = _FIXED                      # the topology this class is built for (subclasses: runtimeracer_version.py)
+    _TOPOLOGY = _native.TOPO_FATCHORD
+
     def __init__(self, rnn_dims, fc_dims, bits, pad, upsample_factors, feat_dims, compute_dims, res_out_dims,
                  res_blocks, hop_length, sample_rate, mode='RAW', pruning=False, device=0):
         given = dict(rnn_dims=rnn_dims, fc_dims=fc_dims, pad=pad, upsample_factors=tuple(upsample_factors),
                      feat_dims=feat_dims, compute_dims=compute_dims, res_out_dims=res_out_dims,
                      res_blocks=res_blocks, hop_length=hop_length)
-        for k, v in _FIXED.items():
+        for k, v in self._FIXED_DIMS.items():
             if given[k] != v:
                 raise NotImplementedError("the B200 engine is built for %s=%r (got %r)" % (k, v, given[k]))
         self.mode = mode
@@ -79,6 +82,8 @@ class WaveRNN(object):
             raise ValueError("wrnn_create: unsupported bits=%r / mode=%r (RAW takes 8..10 bits)" % (bits, mode))
         if rc != _native.OK:
             raise RuntimeError("wrnn_create failed (%d): no usable CUDA device %d" % (rc, self.device_index))
+        if self._TOPOLOGY != _native.TOPO_FATCHORD and self._lib.wrnn_set_topology(self._h, self._TOPOLOGY) != _native.OK:
+            raise RuntimeError("wrnn_set_topology(%d) failed" % self._TOPOLOGY)
         self._lock = threading.Lock()        # a handle is not re-entrant (include/wavernn_b200.h): calls on it are serialised here
 
     def __del__(self):
@@ -189,7 +194,9 @@ class WaveRNN(object):
         rq.mu_law = 1 if mu_law else 0
         rq.apply_preemphasis = 1 if apply_preemphasis else 0
         prec = int(extra.get("precision", self.precision))
-        if prec == _native.PREC_AUTO:
+        if self._TOPOLOGY != _native.TOPO_FATCHORD:
+            prec = _native.PREC_F32              # (the other topologies have the fp32 loop only)
+        elif prec == _native.PREC_AUTO:
             prec = resolve_precision(self.n_classes, self.sparsity, self._count_folds(arrs, batched, target, overlap),
                                      self.sparse_available)
         rq.precision = prec
