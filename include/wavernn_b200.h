@@ -55,8 +55,12 @@ int wrnn_destroy(wrnn_engine* e);
  * hard-codes for the reference's C++ path: four GRU-256 cells on a residual chain and five FC layers
  * (vocoder/models/runtimeracer_version.py:119-132), the fatchord front end (config/hparams.py:355-366).  Call between
  * wrnn_create and the first wrnn_set_tensor; the state_dict names are the reference's (I, rnn1..rnn4, fc1..fc5, upsample.*).
- * This topology runs WRNN_PREC_F32 only (wrnn_loop_rr_kernel).                                                             */
-enum { WRNN_TOPO_FATCHORD = 0, WRNN_TOPO_RUNTIMERACER = 1 };
+ * This topology runs WRNN_PREC_F32 only (wrnn_loop_rr_kernel).
+ * WRNN_TOPO_GENEING: base.init_voc_model(MODEL_TYPE_GENEING, ...) -- base.py:57-80: one GRU-256, fc1 (288 -> 128, ReLU), fc3
+ * (vocoder/models/geneing_version.py:107-113), its own front end (64 channels, 3 residual blocks, upsampling 4 x 5 x 10:
+ * config/hparams.py:288-300); mode 'BITS' is WRNN_MODE_RAW (softmax over 2**bits classes), 'MOL' WRNN_MODE_MOL; the
+ * beta-distribution mode is not supported.  wrnn_loop_gn_kernel, WRNN_PREC_F32 only.                                      */
+enum { WRNN_TOPO_FATCHORD = 0, WRNN_TOPO_RUNTIMERACER = 1, WRNN_TOPO_GENEING = 2 };
 int wrnn_set_topology(wrnn_engine* e, int topology);
 const char* wrnn_last_error(const wrnn_engine* e);
 
@@ -114,7 +118,7 @@ typedef struct {
     int32_t n_folds, n_steps, n_launches;
     int32_t loop_kernel;        /* which loop ran the last wave: WRNN_LOOP_F32 / _TC / _RS / _SPARSE / _TC2     */
 } wrnn_request;
-enum { WRNN_LOOP_F32 = 0, WRNN_LOOP_TC = 1, WRNN_LOOP_RS = 2, WRNN_LOOP_SPARSE = 3, WRNN_LOOP_TC2 = 4, WRNN_LOOP_RR = 5 };
+enum { WRNN_LOOP_F32 = 0, WRNN_LOOP_TC = 1, WRNN_LOOP_RS = 2, WRNN_LOOP_SPARSE = 3, WRNN_LOOP_TC2 = 4, WRNN_LOOP_RR = 5, WRNN_LOOP_GN = 6 };
 
 /* WaveRNN.generate(mels, batched, target, overlap, mu_law, apply_preemphasis, progress_callback)
  * -- fatchord_version.py:155-259 -- for one or many utterances, end to end on the GPU:

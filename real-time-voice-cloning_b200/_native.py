@@ -6,10 +6,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WRNN_B200_LIB") or os.path.join(HERE, "libwavernn_b200.so")   # override: A/B timing of kernel variants
 
-LOOP_KERNELS = {0: "wrnn_loop_f32_kernel", 1: "wrnn_loop_tc_kernel", 2: "wrnn_loop_rs_kernel", 3: "wrnn_loop_sparse_kernel", 4: "wrnn_loop_tc2_kernel", 5: "wrnn_loop_rr_kernel"}
+LOOP_KERNELS = {0: "wrnn_loop_f32_kernel", 1: "wrnn_loop_tc_kernel", 2: "wrnn_loop_rs_kernel", 3: "wrnn_loop_sparse_kernel", 4: "wrnn_loop_tc2_kernel", 5: "wrnn_loop_rr_kernel", 6: "wrnn_loop_gn_kernel"}
 OK, ERR_INVALID, ERR_NOT_LOADED, ERR_CUDA, ERR_TIMEOUT, ERR_SHAPE, ERR_TOO_SHORT = 0, -1, -2, -3, -4, -5, -6
 MODE_RAW, MODE_MOL = 0, 1
-TOPO_FATCHORD, TOPO_RUNTIMERACER = 0, 1
+TOPO_FATCHORD, TOPO_RUNTIMERACER, TOPO_GENEING = 0, 1, 2
 PREC_F32, PREC_F16, PREC_SPARSE_F32 = 0, 1, 2
 PREC_AUTO = -1        # host-side only: resolved per call by vocoder/models/fatchord_version.py:resolve_precision
 

@@ -36,10 +36,18 @@ wavernn_fatchord = HParams(
     gen_batched=True, gen_target=3000, gen_overlap=1500,
 )
 
-# RuntimeRacer's WaveRNN (config/hparams.py:355-383); training-only fields omitted
+# RuntimeRacer's WaveRNN (config/hparams.py:355-421); training-only fields omitted
 wavernn_runtimeracer = HParams(
     mode="RAW", bits=10, mu_law=True, upsample_factors=(5, 5, 8),
     rnn_dims=256, fc_dims=256, compute_dims=128, res_out_dims=64 * 2, res_blocks=10, pad=2,
+    use_sparsification=False, sparsity_target=0.90, sparse_group=4,
+    gen_batched=True, gen_target=6000, gen_overlap=1000,
+)
+
+# geneing's WaveRNN (config/hparams.py:288-352); training-only fields omitted
+wavernn_geneing = HParams(
+    mode="BITS", bits=10, mu_law=False, upsample_factors=(4, 5, 10),
+    rnn_dims=256, fc_dims=128, compute_dims=64, res_out_dims=32 * 2, res_blocks=3, pad=2,
     use_sparsification=False, sparsity_target=0.90, sparse_group=4,
     gen_batched=True, gen_target=3000, gen_overlap=1500,
 )

@@ -64,7 +64,7 @@ __global__ void im2col_kernel(const float* __restrict__ mel, const UttDesc* __re
 
 __global__ void zero_rows_kernel(float* __restrict__ aux, const UttDesc* __restrict__ utts, int n_utts) {
     const int u = blockIdx.x;
-    if (u < n_utts) aux[(size_t)(utts[u].ta_row0 + utts[u].T) * 128 + threadIdx.x] = 0.f;
+    if (u < n_utts) aux[(size_t)(utts[u].ta_row0 + utts[u].T) * blockDim.x + threadIdx.x] = 0.f;     // (blockDim.x = channels per row)
 }
 
 // 64x64 tile, BK=16, 256 threads, 4x4 outputs per thread.
@@ -212,8 +212,8 @@ cudaError_t launch_gemm_f32(const float* A, const float* W, const float* bias, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream) {
-    zero_rows_kernel<<<n_utts, 128, 0, stream>>>(aux, utts, n_utts);
+cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream, int channels) {
+    zero_rows_kernel<<<n_utts, channels, 0, stream>>>(aux, utts, n_utts);
     return cudaGetLastError();
 }
 

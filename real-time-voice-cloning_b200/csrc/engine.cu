@@ -44,6 +44,13 @@ struct HostTensor {
 constexpr int kResBlocks = 10;
 constexpr int kCondLayers = 2 + 2 * kResBlocks;   // conv_in, 20 1x1, conv_out
 
+// device pointers of the geneing topology (engine_gn.inc)
+struct GnDev {
+    float *Whh = nullptr, *Wfc1a = nullptr, *Wfc3 = nullptr, *u1 = nullptr, *u2 = nullptr, *bhn = nullptr, *bfc3 = nullptr, *coef = nullptr;
+    float* CW[2 + 2 * kGnResBlocks] = {};      // front end (64 channels, 3 residual blocks): conv_in, 6 1x1, conv_out
+    float* CB[2 + 2 * kGnResBlocks] = {};
+    float *MA = nullptr, *bA = nullptr, *MQ = nullptr;      // table projections [1024][64], [1024], [1024][80]
+};
 // device pointers of the runtimeracer topology (engine_rr.inc)
 struct RrDev {
     float *Whh[4] = {}, *Wih[3] = {}, *M12 = nullptr, *M34 = nullptr, *Wfc5 = nullptr, *u = nullptr, *bhn = nullptr, *bfc5 = nullptr, *coef = nullptr;
@@ -56,6 +63,7 @@ struct wrnn_engine {
     int device = 0, bits = 9, mode = 0, C = 512, Cpad = 512, CR = 4;
     int topology = 0;            // WRNN_TOPO_FATCHORD / WRNN_TOPO_RUNTIMERACER (wrnn_set_topology, before wrnn_finalize)
     RrDev rr;
+    GnDev gn;
     std::string err;
     std::map<std::string, HostTensor> tensors;
     int64_t step = 0;
@@ -130,8 +138,8 @@ void np_linspace(double start, double stop, int num, std::vector<double>& out) {
 
 // composite interpolation weights of the three Stretch2d+Conv2d layers (fatchord_version.py:66-75,82-84):
 // coef[phase][d] multiplies padded mel frame (n/200 + d) for output sample n with n%200 == phase.
-void build_coef(const float* w5a, const float* w5b, const float* w8, std::vector<float>& coef) {
-    const int L = 8, scales[3] = {5, 5, 8};
+void build_coef(const float* w5a, const float* w5b, const float* w8, std::vector<float>& coef, int s0 = 5, int s1 = 5, int s2 = 8) {
+    const int L = 8, scales[3] = {s0, s1, s2};       // (geneing: 4, 5, 10 -- the same hop of 200 and the same reach of +-2 frames)
     const float* ws[3] = {w5a, w5b, w8};
     std::vector<double> x(L, 0.0);
     x[3] = 1.0;
@@ -157,6 +165,7 @@ void build_coef(const float* w5a, const float* w5b, const float* w8, std::vector
 int python_floordiv(int64_t a, int64_t b) { int64_t q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return (int)q; }
 
 #include "engine_rr.inc"
+#include "engine_gn.inc"
 
 }  // namespace
 
@@ -212,6 +221,8 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
         if (err == cudaSuccess) err = set_rs_deadline((long long)(atof(dl) * 1.9e6));
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
         if (err == cudaSuccess) err = set_rr_deadline((long long)(atof(dl) * 1.9e6));
+    if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
+        if (err == cudaSuccess) err = set_gn_deadline((long long)(atof(dl) * 1.9e6));
     if (err != cudaSuccess) { delete e; return WRNN_ERR_CUDA; }
     *out = e;
     return WRNN_OK;
@@ -253,7 +264,8 @@ int wrnn_sparse_available(const wrnn_engine* e) { return (e && (e->spStride[0] |
 int64_t wrnn_launch_count(const wrnn_engine* e) { return e ? e->launches : 0; }
 
 int wrnn_set_topology(wrnn_engine* e, int topology) {
-    if (!e || (topology != WRNN_TOPO_FATCHORD && topology != WRNN_TOPO_RUNTIMERACER)) return fail(e, WRNN_ERR_INVALID, "unknown topology");
+    if (!e || (topology != WRNN_TOPO_FATCHORD && topology != WRNN_TOPO_RUNTIMERACER && topology != WRNN_TOPO_GENEING))
+        return fail(e, WRNN_ERR_INVALID, "unknown topology");
     e->topology = topology;
     e->finalized = false;
     return WRNN_OK;
@@ -262,6 +274,7 @@ int wrnn_set_topology(wrnn_engine* e, int topology) {
 int wrnn_finalize(wrnn_engine* e) {
     if (!e) return WRNN_ERR_INVALID;
     if (e->topology == WRNN_TOPO_RUNTIMERACER) return finalize_rr(e, e->rr);
+    if (e->topology == WRNN_TOPO_GENEING) return finalize_gn(e, e->gn);
     CU(cudaSetDevice(e->device));
     const int H = kRnn, C = e->C;
 #define GET(var, name, ...)                                   \
@@ -826,8 +839,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     if (use_sparse && !e->spStride[0] && !e->spStride[1])
         return fail(e, WRNN_ERR_INVALID, "block-sparse loop needs a pruned checkpoint (>= 50 % zero 1x4 groups that fit one cluster)");
     const bool use_tc = rq->precision == WRNN_PREC_F16;
-    const bool is_rr = e->topology == WRNN_TOPO_RUNTIMERACER;
-    if (is_rr && rq->precision != WRNN_PREC_F32) return fail(e, WRNN_ERR_INVALID, "the runtimeracer topology runs the fp32 loop only");
+    const bool is_rr = e->topology == WRNN_TOPO_RUNTIMERACER, is_gn = e->topology == WRNN_TOPO_GENEING;
+    if ((is_rr || is_gn) && rq->precision != WRNN_PREC_F32)
+        return fail(e, WRNN_ERR_INVALID, "the runtimeracer / geneing topologies run the fp32 loop only");
     if (use_tc && !e->wTc.p) return fail(e, WRNN_ERR_INVALID, "tensor-core loop supports RAW 9/10-bit and MOL only");
     CU(cudaSetDevice(e->device));
     const int n_utts = rq->n_utts;
@@ -858,6 +872,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     CU(cudaEventRecord(e->ev[1], st));
     CU(cudaMemsetAsync(e->dAbort, 0, 2 * sizeof(int), st));
     rc = is_rr ? run_conditioning_rr(e, e->rr, n_utts, ta_rows, tq_rows)
+       : is_gn ? run_conditioning_gn(e, e->gn, n_utts, ta_rows, tq_rows)
                : (use_tc ? run_conditioning_tc(e, n_utts, ta_rows) : run_conditioning(e, n_utts, ta_rows, tq_rows));
     if (rc) return rc;
     CU(cudaEventRecord(e->ev[2], st));
@@ -926,7 +941,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
     float ms_expand = 0.f;
-    const int wave = is_rr ? kRrMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
+    const int wave = is_rr ? kRrMaxFolds : is_gn ? kGnMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
     // role-specialised loop: as many 48-CTA groups as the device holds; WRNN_RS=0 keeps loop_tc.cu for every fold count
     const int rs_groups_max = std::max(0, e->n_sms / kRsCtas);
     const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
@@ -935,7 +950,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
         bool expanded = false;
         if (is_rr) {
-            // ---- runtimeracer topology: fp32 weight-stationary loop (loop_rr.cu), <= 32 folds per launch ------------------------
+            // ---- runtimeracer topology: fp32 weight-stationary loop (loop_rr.cu), <= 64 folds per launch ------------------------
             const size_t words = (size_t)B * (6 * kRrH + e->Cpad + 2);
             CU(e->bExch.ensure(words * sizeof(unsigned long long)));
             CU(cudaMemsetAsync(e->bExch.p, 0, words * sizeof(unsigned long long), st));
@@ -959,6 +974,28 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             if (loop_rr_smem_bytes(B, e->CR) > e->smem_limit) return fail(e, WRNN_ERR_INVALID, "shared memory budget exceeded");
             CU(launch_loop_rr(p, st));
             rq->loop_kernel = WRNN_LOOP_RR;
+            e->launches += 1;
+        } else if (is_gn) {
+            // ---- geneing topology: fp32 weight-stationary loop (loop_gn.cu) ----------------------------------------------------
+            const size_t words = (size_t)B * (kGnH + kGnFc + e->Cpad + 2);
+            CU(e->bExch.ensure(words * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(e->bExch.p, 0, words * sizeof(unsigned long long), st));
+            GnLoopParams p;
+            memset(&p, 0, sizeof(p));
+            p.Whh = e->gn.Whh; p.Wfc1a = e->gn.Wfc1a; p.Wfc3 = e->gn.Wfc3; p.u1 = e->gn.u1; p.u2 = e->gn.u2; p.bhn = e->gn.bhn; p.bfc3 = e->gn.bfc3;
+            p.TA = e->bTA1.as<float4>(); p.TQ = e->bTQ1.as<float4>(); p.coef = e->gn.coef;
+            p.folds = e->bFolds.as<FoldDesc>() + w0;
+            p.B = B; p.S = S; p.C = e->C; p.Cpad = e->Cpad; p.CR = e->CR; p.mode = e->mode; p.seed = rq->seed;
+            unsigned long long* x = e->bExch.as<unsigned long long>();
+            p.bH = x; x += (size_t)B * kGnH; p.bF = x; x += (size_t)B * kGnFc; p.bLG = x; x += (size_t)B * e->Cpad; p.bX = x;
+            p.samples = e->bSamples.as<float>() + (size_t)w0 * S;
+            p.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            p.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
+            p.progress = e->dProgress;
+            p.abort_flag = e->dAbort;
+            if (loop_gn_smem_bytes(B, e->CR) > e->smem_limit) return fail(e, WRNN_ERR_INVALID, "shared memory budget exceeded");
+            CU(launch_loop_gn(p, st));
+            rq->loop_kernel = WRNN_LOOP_GN;
             e->launches += 1;
         } else if (use_sparse) {
             // ---- block-sparse cluster loop: folds partitioned over independent 16-CTA (or 8-CTA) clusters ------------------

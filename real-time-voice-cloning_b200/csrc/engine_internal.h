@@ -153,7 +153,7 @@ cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const fl
 // ---- runtimeracer-wavernn topology (loop_rr.cu): four GRU-256 + five FC layers, fp32 ---------------------------------
 constexpr int kRrH = 256;            // rnn_dims = fc_dims (config/hparams.py:363-364)
 constexpr int kRrCtas = 128;         // 2 hidden units of every layer per CTA
-constexpr int kRrMaxFolds = 32;      // folds per launch (longer batches run in waves)
+constexpr int kRrMaxFolds = 64;      // folds per launch (longer batches run in waves): activations + running sums = 2 KB of shared memory per fold
 struct RrLoopParams {
     const float* Whh[4];         // rnn1..4 weight_hh [768][256]
     const float* Wih[3];         // rnn2, rnn3[:, :256], rnn4 weight_ih [768][256] (rnn1's is folded into the tables)
@@ -181,6 +181,37 @@ using RrParams = RrLoopParams;
 size_t loop_rr_smem_bytes(int B, int CR);
 cudaError_t set_rr_deadline(long long cycles);
 cudaError_t launch_loop_rr(const RrLoopParams& p, cudaStream_t stream);
+
+// ---- geneing-wavernn topology (loop_gn.cu): one GRU-256, fc1 (-> 128, ReLU), fc3 (-> classes), fp32 -------------------------
+constexpr int kGnH = 256;            // rnn_dims (config/hparams.py:295)
+constexpr int kGnFc = 128;           // fc_dims (:296)
+constexpr int kGnAux = 32;           // res_out_dims / 2 (:298, geneing_version.py:103)
+constexpr int kGnCh = 64;            // compute_dims = res_out_dims (:297-298)
+constexpr int kGnResBlocks = 3;      // :299
+constexpr int kGnCtas = 128;         // 2 GRU units + 1 fc1 unit per CTA
+constexpr int kGnMaxFolds = 96;      // folds per launch
+struct GnLoopParams {
+    const float* Whh;            // rnn1 weight_hh [768][256]
+    const float* Wfc1a;          // fc1[:, :256] [128][256]
+    const float* Wfc3;           // [C][128]
+    const float *u1, *u2;        // coefficients of the previous sample: GRU1 gates [3][256], fc1 [128]
+    const float *bhn, *bfc3;     // [256], [C]
+    // per-frame tables, one float4 per GRU unit j: {c1 r, z, n of unit j, c2 of fc1 unit j/2 (even j; 0 for odd j)}
+    const float4 *TA, *TQ;       // [frame row][256], [padded frame row][256]
+    const float* coef;
+    const FoldDesc* folds;
+    int B, S, C, Cpad, CR, mode;
+    unsigned long long seed;
+    unsigned long long *bH, *bF, *bLG, *bX;   // exchange words: [B][256], [B][128], [B][Cpad], [B]
+    float* samples;
+    float* logits_out;
+    const float* forced;
+    int* progress;
+    int* abort_flag;
+};
+size_t loop_gn_smem_bytes(int B, int CR);
+cudaError_t set_gn_deadline(long long cycles);
+cudaError_t launch_loop_gn(const GnLoopParams& p, cudaStream_t stream);
 
 // ---- cluster-local tensor-core loop, MOL (loop_tc2.cu) --------------------------------------------------------------
 struct Tc2Params {
@@ -237,7 +268,7 @@ cudaError_t launch_im2col(const float* mel, const UttDesc* utts, int n_utts, int
 // C[M][N] = act(A[M][K] W[N][K]^T + bias) (+ R)   ; fp32 ; K % 16 == 0 ; N % 64 == 0
 cudaError_t launch_gemm_f32(const float* A, const float* W, const float* bias, const float* R, float* C,
                             int M, int N, int K, int relu, cudaStream_t stream);
-cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream);
+cudaError_t launch_zero_rows(float* aux, const UttDesc* utts, int n_utts, cudaStream_t stream, int channels = 128);
 
 // ---- conditioning contractions on tensor cores (cond_tc.cu) ------------------------------------------------
 struct GemmTcArgs {

@@ -14,17 +14,18 @@
 //    product (for the next step) and the running sum the next layer reads;
 //  * sampling (softmax + inverse CDF, or mixture of logistics) fused, Philox noise as in loop_f32.cu (sampling.cuh);
 //  * every spin has a deadline; a miss raises the abort flag and all CTAs leave.
-// One launch serves <= kRrMaxFolds folds (the engine runs longer batches in waves).
+// One launch serves <= kRrMaxFolds (64) folds (the engine runs longer batches in waves).
 #include "engine_internal.h"
 #include "sampling.cuh"
+#include "chain_f32.cuh"
 
 namespace wrnn {
 
 namespace {
 
 constexpr int H = kRrH;           // 256
-constexpr int NT = 512;
-constexpr int NW = NT / 32;
+using chain::NT;
+using chain::NW;
 constexpr int U = kRrH / kRrCtas; // hidden units per CTA (2)
 constexpr int G = 3 * U;          // gate rows per CTA and GRU matrix (6)
 __device__ long long g_rr_deadline = 1500000000LL;
@@ -76,61 +77,6 @@ __device__ __forceinline__ Smem carve(float* base, int B, int CR) {
     s.b5 = p;  p += (CR + 3) & ~3;
     s.coef = p; p += kHop * kTaps;
     return s;
-}
-
-// Spin until every {value, tag} word of `nb` rows of `buf` carries `tag`; values into act[nb][H] and, per `mode`, into the running
-// sum (0: none, 1: sum = act, 2: sum += act).  Returns nonzero (CTA-uniform) if the deadline passed or another CTA aborted.
-__device__ __noinline__ int gather(const unsigned long long* __restrict__ buf, int nb, float* __restrict__ act, float* __restrict__ sum,
-                                   int mode, uint32_t tag, int* abort_flag) {
-    const int tid = threadIdx.x;
-    const int npairs = nb * (H / 2);
-    int failed = 0;
-    for (int i = tid; i < npairs && !failed; i += NT) {
-        unsigned long long a, b;
-        long long t0 = 0;
-        int spins = 0;
-        while (true) {
-            ll_load2(buf + 2 * (size_t)i, a, b);
-            if (ll_tag(a) == tag && ll_tag(b) == tag) break;
-            if (((++spins) & 63) == 0) {
-                if (t0 == 0) t0 = clock64();
-                if (clock64() - t0 > g_rr_deadline || ld_volatile_i32(abort_flag) != 0) { failed = 1; break; }
-            }
-        }
-        const float2 v = make_float2(ll_val(a), ll_val(b));
-        *reinterpret_cast<float2*>(act + 2 * (size_t)i) = v;
-        if (mode == 1) *reinterpret_cast<float2*>(sum + 2 * (size_t)i) = v;
-        else if (mode == 2) {
-            float2 s2 = *reinterpret_cast<float2*>(sum + 2 * (size_t)i);
-            s2.x += v.x; s2.y += v.y;
-            *reinterpret_cast<float2*>(sum + 2 * (size_t)i) = s2;
-        }
-    }
-    return __syncthreads_or(failed);
-}
-
-// out[f][o0 + r] = sum_k W[r][k] * in[f][k] for r < R, f < nb: one warp per (row, fold pair), lanes split K (float4 x 2).
-__device__ __forceinline__ void dots(const float* __restrict__ sW, int R, const float* __restrict__ in, int nb, float* __restrict__ out, int ldo,
-                                     int o0) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nfp = (nb + 1) / 2;
-    for (int task = warp; task < R * nfp; task += NW) {
-        const int r = task % R, f0 = (task / R) * 2, f1 = min(f0 + 1, nb - 1);
-        const float4 w0 = *reinterpret_cast<const float4*>(sW + r * H + lane * 4), w1 = *reinterpret_cast<const float4*>(sW + r * H + 128 + lane * 4);
-        const float4 a0 = *reinterpret_cast<const float4*>(in + f0 * H + lane * 4), a1 = *reinterpret_cast<const float4*>(in + f0 * H + 128 + lane * 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(in + f1 * H + lane * 4), b1 = *reinterpret_cast<const float4*>(in + f1 * H + 128 + lane * 4);
-        float sa = w0.x * a0.x, sb = w0.x * b0.x;
-        sa = fmaf(w0.y, a0.y, sa); sa = fmaf(w0.z, a0.z, sa); sa = fmaf(w0.w, a0.w, sa);
-        sa = fmaf(w1.x, a1.x, sa); sa = fmaf(w1.y, a1.y, sa); sa = fmaf(w1.z, a1.z, sa); sa = fmaf(w1.w, a1.w, sa);
-        sb = fmaf(w0.y, b0.y, sb); sb = fmaf(w0.z, b0.z, sb); sb = fmaf(w0.w, b0.w, sb);
-        sb = fmaf(w1.x, b1.x, sb); sb = fmaf(w1.y, b1.y, sb); sb = fmaf(w1.z, b1.z, sb); sb = fmaf(w1.w, b1.w, sb);
-        sa = warp_sum(sa);
-        sb = warp_sum(sb);
-        if (lane == 0) {
-            out[f0 * ldo + o0 + r] = sa;
-            if (f1 != f0) out[f1 * ldo + o0 + r] = sb;
-        }
-    }
 }
 
 }  // namespace
@@ -239,32 +185,32 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rr_kernel(RrParams p) {
             gru_station(0, false, 0, p.bH[0], tag);
         }
         // ---- 2: h1 -> [W_hh1 h1 (next step) | W_ih2 h1]; GRU2; publish h2 ---------------------------------------------------
-        if (gather(p.bH[0], B, s.act, s.sum, 1, tag, p.abort_flag)) RR_FAIL();
-        dots(s.W1, 2 * G, s.act, B, s.tmp, LDT, 0);
+        if (chain::gather<H>(p.bH[0], B, s.act, s.sum, 1, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
+        chain::dots<H>(s.W1, 2 * G, s.act, B, s.tmp, LDT, 0);
         __syncthreads();
         gru_station(1, true, G, p.bH[1], tag);
         save_gh(0, 0);
         __syncthreads();
         // ---- 3: h2 -> W_ih3 (h1 + h2), W_hh2 h2; GRU3; publish h3 -----------------------------------------------------------
-        if (gather(p.bH[1], B, s.act, s.sum, 2, tag, p.abort_flag)) RR_FAIL();
-        dots(s.W2h, G, s.act, B, s.tmp, LDT, 0);
-        dots(s.W2s, G, s.sum, B, s.tmp, LDT, G);
+        if (chain::gather<H>(p.bH[1], B, s.act, s.sum, 2, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
+        chain::dots<H>(s.W2h, G, s.act, B, s.tmp, LDT, 0);
+        chain::dots<H>(s.W2s, G, s.sum, B, s.tmp, LDT, G);
         __syncthreads();
         gru_station(2, true, G, p.bH[2], tag);
         save_gh(1, 0);
         __syncthreads();
         // ---- 4: h3 -> W_ih4 (h1 + h2 + h3), W_hh3 h3; GRU4; publish h4 ------------------------------------------------------
-        if (gather(p.bH[2], B, s.act, s.sum, 2, tag, p.abort_flag)) RR_FAIL();
-        dots(s.W3h, G, s.act, B, s.tmp, LDT, 0);
-        dots(s.W3s, G, s.sum, B, s.tmp, LDT, G);
+        if (chain::gather<H>(p.bH[2], B, s.act, s.sum, 2, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
+        chain::dots<H>(s.W3h, G, s.act, B, s.tmp, LDT, 0);
+        chain::dots<H>(s.W3s, G, s.sum, B, s.tmp, LDT, G);
         __syncthreads();
         gru_station(3, true, G, p.bH[3], tag);
         save_gh(2, 0);
         __syncthreads();
         // ---- 5: h4 -> y2 = relu(M12 (h1 + .. + h4) + u5 x + c5), W_hh4 h4; publish y2 ----------------------------------------
-        if (gather(p.bH[3], B, s.act, s.sum, 2, tag, p.abort_flag)) RR_FAIL();
-        dots(s.W4h, G, s.act, B, s.tmp, LDT, 0);
-        dots(s.W4s, U, s.sum, B, s.tmp, LDT, G);
+        if (chain::gather<H>(p.bH[3], B, s.act, s.sum, 2, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
+        chain::dots<H>(s.W4h, G, s.act, B, s.tmp, LDT, 0);
+        chain::dots<H>(s.W4s, U, s.sum, B, s.tmp, LDT, G);
         __syncthreads();
         for (int e = tid; e < B * U; e += NT) {
             const int b = e / U, uu = e % U;
@@ -274,8 +220,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rr_kernel(RrParams p) {
         save_gh(3, 0);
         __syncthreads();
         // ---- 6: y4 = relu(M34 y2 + c6); publish ---------------------------------------------------------------------------------
-        if (gather(p.bY2, B, s.act, s.sum, 0, tag, p.abort_flag)) RR_FAIL();
-        dots(s.W5, U, s.act, B, s.tmp, LDT, 0);
+        if (chain::gather<H>(p.bY2, B, s.act, s.sum, 0, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
+        chain::dots<H>(s.W5, U, s.act, B, s.tmp, LDT, 0);
         __syncthreads();
         for (int e = tid; e < B * U; e += NT) {
             const int b = e / U, uu = e % U;
@@ -283,9 +229,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rr_kernel(RrParams p) {
         }
         __syncthreads();
         // ---- 7: my classes of logits = fc5 y4 + b; publish ------------------------------------------------------------------
-        if (gather(p.bY4, B, s.act, s.sum, 0, tag, p.abort_flag)) RR_FAIL();
+        if (chain::gather<H>(p.bY4, B, s.act, s.sum, 0, tag, p.abort_flag, g_rr_deadline)) RR_FAIL();
         if (cta * CR < C) {
-            dots(s.W6, CR, s.act, B, s.tmp, LDT, 0);
+            chain::dots<H>(s.W6, CR, s.act, B, s.tmp, LDT, 0);
             __syncthreads();
             for (int e = tid; e < B * CR; e += NT) {
                 const int b = e / CR, r = e % CR, cls = cta * CR + r;

@@ -5,7 +5,7 @@ exported `.bin` (libwavernn_bin.py) onto the same engine."""
 import numpy as np
 
 from .. import _native
-from ..config.hparams import sp, wavernn_fatchord, wavernn_runtimeracer
+from ..config.hparams import sp, wavernn_fatchord, wavernn_geneing, wavernn_runtimeracer
 from .models import base
 
 _model = None        # list of per-GPU WaveRNN objects once loaded
@@ -21,13 +21,13 @@ def _devices(devices):
 
 
 def load_state(state_dict, model_type=base.MODEL_TYPE_FATCHORD, devices=None, override_hp_fatchord=None, verbose=False,
-               override_hp_runtimeracer=None):
+               override_hp_runtimeracer=None, override_hp_geneing=None):
     """Builds the engine(s) from an in-memory state_dict (what load_model does after torch.load)."""
     global _model, _model_type
     models = []
     for d in _devices(devices):
         m, _ = base.init_voc_model(model_type, d, override_hp_fatchord=override_hp_fatchord,
-                                   override_hp_runtimeracer=override_hp_runtimeracer)
+                                   override_hp_runtimeracer=override_hp_runtimeracer, override_hp_geneing=override_hp_geneing)
         m.eval()
         m.load_state_dict(state_dict)
         m.precision = _native.PREC_AUTO       # facade default: the fastest loop for the call (fatchord_version.resolve_precision)
@@ -114,6 +114,8 @@ def _hp():
         return wavernn_fatchord
     if _model_type == base.MODEL_TYPE_RUNTIMERACER:               # inference.py:69-70
         return wavernn_runtimeracer
+    if _model_type == base.MODEL_TYPE_GENEING:                    # inference.py:67-68
+        return wavernn_geneing
     raise NotImplementedError("Invalid model of type '%s' provided. Aborting..." % _model_type)
 
 

@@ -1,7 +1,8 @@
 """Model factory and type constants (reference: vocoder/models/base.py:9-15 constants, :18-109
 init_voc_model, :112-120 get_model_type)."""
-from ...config.hparams import sp, wavernn_fatchord, wavernn_runtimeracer
+from ...config.hparams import sp, wavernn_fatchord, wavernn_geneing, wavernn_runtimeracer
 from .fatchord_version import WaveRNN as WaveRNNFatchord
+from .geneing_version import WaveRNN as WaveRNNGeneing
 from .runtimeracer_version import WaveRNN as WaveRNNRuntimeRacer
 
 # Vocoder types (base.py:9-10) plus the backend this package adds next to them
@@ -25,8 +26,10 @@ def init_voc_model(model_type, device, override_hp_fatchord=None, override_hp_ge
     elif model_type == MODEL_TYPE_FATCHORD:
         hparams = override_hp_fatchord if override_hp_fatchord is not None else wavernn_fatchord
         cls = WaveRNNFatchord
+    elif model_type == MODEL_TYPE_GENEING:                        # base.py:57-80
+        hparams = override_hp_geneing if override_hp_geneing is not None else wavernn_geneing
+        cls = WaveRNNGeneing
     else:
-        # the geneing topology is SURVEY.md section 8(f) "next"
         raise NotImplementedError("Invalid model of type '%s' provided. Aborting..." % model_type)
     prod = 1
     for f in hparams.upsample_factors:
@@ -43,6 +46,8 @@ def init_voc_model(model_type, device, override_hp_fatchord=None, override_hp_ge
 def get_model_type(model):
     if isinstance(model, WaveRNNRuntimeRacer):
         return MODEL_TYPE_RUNTIMERACER
+    if isinstance(model, WaveRNNGeneing):
+        return MODEL_TYPE_GENEING
     if isinstance(model, WaveRNNFatchord):
         return MODEL_TYPE_FATCHORD
     raise NotImplementedError("Provided object is not a valid vocoder model.")

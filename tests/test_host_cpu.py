@@ -59,12 +59,26 @@ def test_drop_in_surface():
         raise AssertionError("expected the not-loaded exception")
     except Exception as e:
         assert str(e) == "Please load Wave-RNN in memory before using it"
-    for bad in ("geneing-wavernn", "nope"):
+    for bad in ("nope", "wavernn"):
         try:
             base.init_voc_model(bad, 0)
             raise AssertionError
         except NotImplementedError:
             pass
+    # all three model types of the reference (base.py:13-15) have a class; the topologies reject other sizes before touching a GPU
+    from rtvc_b200.vocoder.models import geneing_version, runtimeracer_version
+    from rtvc_b200.config import hparams
+    assert (base.MODEL_TYPE_GENEING, base.MODEL_TYPE_RUNTIMERACER) == ("geneing-wavernn", "runtimeracer-wavernn")
+    for cls, hp in ((runtimeracer_version.WaveRNN, hparams.wavernn_fatchord), (geneing_version.WaveRNN, hparams.wavernn_runtimeracer)):
+        try:
+            cls(rnn_dims=hp.rnn_dims, fc_dims=hp.fc_dims, bits=9, pad=2, upsample_factors=hp.upsample_factors, feat_dims=80,
+                compute_dims=hp.compute_dims, res_out_dims=hp.res_out_dims, res_blocks=hp.res_blocks, hop_length=200, sample_rate=16000,
+                mode="MOL")
+            raise AssertionError
+        except NotImplementedError:
+            pass
+    assert (hparams.wavernn_runtimeracer.gen_target, hparams.wavernn_runtimeracer.gen_overlap) == (6000, 1000)      # config/hparams.py:419-420
+    assert (hparams.wavernn_geneing.gen_target, hparams.wavernn_geneing.gen_overlap, hparams.wavernn_geneing.mu_law) == (3000, 1500, False)
 
 
 def test_product_does_not_import_oracle():
