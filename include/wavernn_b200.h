@@ -62,6 +62,11 @@ int wrnn_destroy(wrnn_engine* e);
  * beta-distribution mode is not supported.  wrnn_loop_gn_kernel, WRNN_PREC_F32 only.                                      */
 enum { WRNN_TOPO_FATCHORD = 0, WRNN_TOPO_RUNTIMERACER = 1, WRNN_TOPO_GENEING = 2 };
 int wrnn_set_topology(wrnn_engine* e, int topology);
+/* WaveRNNVocoder::loadWeights(path) -- vocoder/libwavernn/fatchord_version/src/WaveRNNVocoder.cpp:22-31: create + load + finalize an
+ * engine from a libwavernn `.bin` export (vocoder/libwavernn/convert.py; fatchord topology, usually pruned).  Mode and bits
+ * follow from fc3's row count.  On failure *out is NULL and `err` (optional, err_len bytes) holds the message -- a file that
+ * cannot be opened gives the reference's "Cannot open file.".                                                              */
+int wrnn_create_from_bin(const char* path, int device, wrnn_engine** out, char* err, int err_len);
 const char* wrnn_last_error(const wrnn_engine* e);
 
 /* model.load_state_dict(checkpoint["model_state"]) -- vocoder/inference.py:35.  One call per entry of

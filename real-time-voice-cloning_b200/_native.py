@@ -47,7 +47,7 @@ class Request(C.Structure):
     ]
 
 
-EXPORTS = ["wrnn_create", "wrnn_set_topology", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
+EXPORTS = ["wrnn_create", "wrnn_create_from_bin", "wrnn_set_topology", "wrnn_destroy", "wrnn_last_error", "wrnn_set_tensor", "wrnn_set_step", "wrnn_get_step",
            "wrnn_finalize", "wrnn_sparsity", "wrnn_sparse_available", "wrnn_fold_plan", "wrnn_generate", "wrnn_condition", "wrnn_condition_tc", "wrnn_postprocess",
            "wrnn_xfade_unfold", "wrnn_barrier_floor", "wrnn_cluster_floor", "wrnn_debug_umma_rate", "wrnn_debug_tc_gemm", "wrnn_debug_tc_gemm2", "wrnn_launch_count"]
 
@@ -66,6 +66,7 @@ def load():
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.wrnn_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     lib.wrnn_set_topology.argtypes = [vp, C.c_int]
+    lib.wrnn_create_from_bin.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]
     lib.wrnn_destroy.argtypes = [vp]
     lib.wrnn_last_error.argtypes = [vp]
     lib.wrnn_last_error.restype = C.c_char_p

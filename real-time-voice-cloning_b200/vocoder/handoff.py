@@ -34,9 +34,22 @@ def peak_normalize(wav, peak=0.97):
     return wav / np.abs(wav).max() * peak
 
 
-def vocode_specs(specs, normalize_peak=True, **infer_kwargs):
-    """One text -> one spectrogram each; returns the float64 waveform the toolbox would play."""
-    spec, breaks = concat_specs(specs)
-    wav = inference.infer_waveform(spec, **infer_kwargs)
-    wav = add_breaks(wav, breaks)
+def join_with_gaps(wavs, break_seconds=0.15, sample_rate=None):
+    """Pieces that were vocoded separately, each followed by the toolbox's gap (toolbox.py:312-314)."""
+    sample_rate = sp.sample_rate if sample_rate is None else sample_rate
+    gap = np.zeros(int(break_seconds * sample_rate))
+    return np.concatenate([i for w in wavs for i in (np.asarray(w, np.float64), gap)])
+
+
+def vocode_specs(specs, normalize_peak=True, pooled=False, **infer_kwargs):
+    """One text -> one spectrogram each; returns the float64 waveform the toolbox would play.
+    pooled=False: the reference's way -- concatenate, vocode once, cut at the breaks (the recurrent state runs across the texts and
+    the last piece is one hop short).  pooled=True: every text is its own utterance in ONE engine call (`infer_waveforms`: all
+    folds of all texts share the persistent-loop launches, BASELINE config 5), so no text hears its neighbour; piece i has
+    (T_i - 1) * hop samples."""
+    if pooled:
+        wav = join_with_gaps(inference.infer_waveforms(list(specs), **infer_kwargs))
+    else:
+        spec, breaks = concat_specs(specs)
+        wav = add_breaks(inference.infer_waveform(spec, **infer_kwargs), breaks)
     return peak_normalize(wav) if normalize_peak else wav

@@ -77,3 +77,66 @@ def test_load_model_libwavernn_matches_state_dict(tmp_path):
     b = inference.infer_waveform(mel, target=1200, overlap=200)
     assert a.shape == b.shape == ((40 - 1) * 200,) and a.dtype == np.float64
     np.testing.assert_array_equal(a, b)
+
+
+def _c_loader(path, device=0):
+    import ctypes as C
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    lib = _native.load()
+    h = C.c_void_p()
+    err = C.create_string_buffer(256)
+    rc = lib.wrnn_create_from_bin(str(path).encode(), device, C.byref(h), err, 256)
+    return lib, rc, h, err.value.decode()
+
+
+def test_c_level_bin_loader_errors(tmp_path):
+    """wrnn_create_from_bin (the C ABI's WaveRNNVocoder::loadWeights): errors are decided before any GPU is touched."""
+    from rtvc_b200 import _native
+    lib, rc, h, msg = _c_loader("/nonexistent/model.bin")
+    assert rc == _native.ERR_INVALID and not h.value and msg == "Cannot open file."        # WaveRNNVocoder.cpp:24-26
+    sd = weights.make_state_dict(seed=3, bits=9, mode="RAW")
+    path = tmp_path / "m.bin"
+    libwavernn_io.write_bin(path, sd)
+    raw = path.read_bytes()
+    (tmp_path / "short.bin").write_bytes(raw[: len(raw) // 2])
+    lib, rc, h, msg = _c_loader(tmp_path / "short.bin")
+    assert rc == _native.ERR_SHAPE and not h.value and "truncated" in msg
+    (tmp_path / "long.bin").write_bytes(raw + b"\0" * 8)
+    lib, rc, h, msg = _c_loader(tmp_path / "long.bin")
+    assert rc == _native.ERR_SHAPE and "trailing" in msg
+    bad = bytearray(raw)
+    bad[16] = 9
+    (tmp_path / "bad.bin").write_bytes(bytes(bad))
+    lib, rc, h, msg = _c_loader(tmp_path / "bad.bin")
+    assert rc == _native.ERR_SHAPE and "layer type" in msg
+
+
+@pytest.mark.gpu
+def test_c_level_bin_loader_matches_python_reader(tmp_path):
+    """An engine created by wrnn_create_from_bin generates the same samples as one loaded through the Python reader."""
+    import ctypes as C
+    from tests.util import norm_mel
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200 import _native
+    from rtvc_b200.vocoder import inference
+    sd = weights.prune_state_dict(weights.make_state_dict(seed=3, bits=9, mode="RAW"), z=0.9)
+    path = tmp_path / "m.bin"
+    libwavernn_io.write_bin(path, sd)
+    lib, rc, h, msg = _c_loader(path)
+    assert rc == _native.OK and h.value, msg
+    try:
+        inference.load_model(str(path), voc_type="libwavernn", verbose=False)
+        m = inference._model[0]
+        assert abs(lib.wrnn_sparsity(h) - m.sparsity) < 1e-12 and m.sparsity > 0.8
+        mel = norm_mel(30, 2)
+        a = m.generate_debug(mel, True, 400, 100, seed=3, max_steps=64, precision=_native.PREC_F32)["samples"]
+        keep, m._h = m._h, h                       # run the same request on the C-loaded engine
+        try:
+            b = m.generate_debug(mel, True, 400, 100, seed=3, max_steps=64, precision=_native.PREC_F32)["samples"]
+        finally:
+            m._h = keep
+        assert np.array_equal(a, b)
+    finally:
+        inference.unload()
+        lib.wrnn_destroy(h)
