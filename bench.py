@@ -42,9 +42,33 @@ WORKLOADS = {
     "cfg4": ("RAW", 9, 10, True, 8000, 800),
     # cfg5: 256 utterances of 5..20 s (numpy default_rng(2)), all folds pooled, sharded by utterance over the ranks
     "cfg5": ("RAW", 9, 0, True, 6000, 1000),
+    # the other two topologies of the reference at the cfg1 shape; fp32 loops
+    "rr1": ("RAW", 9, 10, True, 8000, 800),       # runtimeracer-wavernn: 4 x GRU-256 + 5 FC (wrnn_loop_rr_kernel)
+    "gn1": ("RAW", 9, 10, True, 8000, 800),       # geneing-wavernn, mode BITS: GRU-256 + 2 FC (wrnn_loop_gn_kernel)
 }
 PRUNED = {"cfg4"}
 MULTI = {"cfg5"}
+TOPO = {"rr1": "runtimeracer-wavernn", "gn1": "geneing-wavernn"}       # default: fatchord-wavernn
+
+
+def topo_state_dict(weights, wl, bits, mode):
+    """Synthetic weights of the workload's topology (rtvc_b200/synth.py)."""
+    t = TOPO.get(wl)
+    if t == "runtimeracer-wavernn":
+        return weights.make_state_dict_rr(seed=0, bits=bits, mode=mode)
+    if t == "geneing-wavernn":
+        return weights.make_state_dict_gn(seed=0, bits=bits)
+    return weights.make_state_dict(seed=0, bits=bits, mode=mode)
+
+
+def topo_macs(wl, C):
+    """Algorithmic MACs of the REFERENCE's step per fold for the workload's topology."""
+    t = TOPO.get(wl)
+    if t == "runtimeracer-wavernn":      # runtimeracer_version.py:119-131: I, rnn1..4 (rnn3 takes 288), fc1 / fc3 (288 -> 256), fc2 / fc4, fc5
+        return 112 * 256 + 3 * 256 * (256 * 3 + 288 + 4 * 256) + 2 * 288 * 256 + 2 * 256 * 256 + 256 * C
+    if t == "geneing-wavernn":           # geneing_version.py:107-113: I, rnn1, fc1 (288 -> 128), fc3
+        return 112 * 256 + 3 * 256 * 2 * 256 + 288 * 128 + 128 * C
+    return macs_per_row_step(C)
 
 
 def workload_mels(wl, rank, world):
@@ -140,7 +164,8 @@ def cpu_baseline(wl, sd, mode, bits, mel_norm, batched, target, overlap, seconds
     from oracle import ref_bench
     out = None
     if ref_bench.available():
-        r = ref_bench.time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=os.cpu_count(), budget_s=seconds)
+        topo = TOPO.get(wl, "fatchord-wavernn")
+        r = ref_bench.time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=os.cpu_count(), budget_s=seconds, model_type=topo)
         out = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "reference",
                "extrapolated": r["extrapolated"], "measured_fraction": r["measured_fraction"], "us_per_step": r["us_per_step"],
                "sample": "UNMODIFIED reference base.init_voc_model(...).generate() from baseline/_ref on %d torch threads: conditioning + fold "
@@ -148,7 +173,7 @@ def cpu_baseline(wl, sd, mode, bits, mel_norm, batched, target, overlap, seconds
                          "extrapolated at the measured %.0f us per step" % (r["threads"], r["seconds_before_loop"], r["steps_measured"],
                                                                            r["steps_total"], r["folds"], r["us_per_step"])}
         if extras:
-            r1 = ref_bench.time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=1, budget_s=max(2.0, seconds / 4))
+            r1 = ref_bench.time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=1, budget_s=max(2.0, seconds / 4), model_type=topo)
             out["one_thread"] = {"value": r1["value"], "us_per_step": r1["us_per_step"], "cores": 1, "measured_fraction": r1["measured_fraction"]}
     else:
         from oracle.torch_port import time_generate
@@ -157,7 +182,7 @@ def cpu_baseline(wl, sd, mode, bits, mel_norm, batched, target, overlap, seconds
                "extrapolated": True, "measured_fraction": r["steps_done"] / max(1, r["steps_total"]),
                "sample": "%d of %d loop steps x %d folds (torch CPU port of the reference loop: baseline/_ref is absent), conditioning in "
                          "full; extrapolated linearly" % (r["steps_done"], r["steps_total"], r["folds"])}
-    if extras or wl in PRUNED:
+    if (extras and wl not in TOPO) or wl in PRUNED:       # (the libwavernn port restates the fatchord engine only)
         try:
             lw = libwavernn_port_baseline(sd, mel_norm, max(2.0, seconds / 3))
             if wl in PRUNED:
@@ -178,7 +203,7 @@ def reference_arm(args, wl):
     import rtvc_b200  # noqa: F401
     from rtvc_b200 import synth as weights
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
-    sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
+    sd = topo_state_dict(weights, wl, bits, mode)
     if wl in PRUNED:
         sd = weights.prune_state_dict(sd, z=0.9)
     mel = workload_mels(wl, 0, 1)[0][0] / np.float32(4.0)
@@ -201,11 +226,13 @@ def reference_arm(args, wl):
 
 def workload_config(wl):
     mode, bits, seconds, batched, target, overlap = WORKLOADS[wl]
-    return {"workload": "%s: WaveRNN fatchord %s%s, %s synthetic 80-mel @16 kHz, %s" % (
-        wl, mode, (" %d-bit" % bits) if mode == "RAW" else "",
+    topo = TOPO.get(wl, "fatchord-wavernn").split("-")[0]
+    dims = {"fatchord": "rnn_dims=512 fc_dims=512", "runtimeracer": "rnn_dims=256 fc_dims=256 (4 GRU, 5 FC)", "geneing": "rnn_dims=256 fc_dims=128 (1 GRU, 2 FC)"}[topo]
+    return {"workload": "%s: WaveRNN %s %s%s, %s synthetic 80-mel @16 kHz, %s" % (
+        wl, topo, ("BITS" if topo == "geneing" else mode), (" %d-bit" % bits) if mode == "RAW" else "",
         "256 utterances of 5-20 s" if wl in MULTI else "%d s" % seconds,
         ("batched target=%d overlap=%d" % (target, overlap)) if batched else "unbatched (single fold)"),
-        "weights": "random-init rnn_dims=512 fc_dims=512 hop=200", "cache": "L2 flushed (256 MiB write) between timed steps"}
+        "weights": "random-init %s hop=200" % dims, "cache": "L2 flushed (256 MiB write) between timed steps"}
 
 
 _REAL_STDOUT = None
@@ -249,7 +276,7 @@ def main():
     _guard_stdout()
     if args.precision is None:      # defaults = what the facade's PREC_AUTO picks (fatchord_version.resolve_precision): pruned model ->
         # block-sparse cluster loop; fewer than 24 folds in the call (cfg1: 19, cfg2: 1) -> fp32 loop; else the tensor-core loops
-        args.precision = "sparse" if wl in PRUNED else ("f32" if (not WORKLOADS[wl][3] or wl == "cfg1") else "f16")
+        args.precision = "sparse" if wl in PRUNED else ("f32" if (not WORKLOADS[wl][3] or wl == "cfg1" or wl in TOPO) else "f16")
 
     import torch
     import torch.distributed as dist
@@ -283,13 +310,16 @@ def main():
 
     def setup(wl_, precision):
         mode, bits, seconds, batched, target, overlap = WORKLOADS[wl_]
-        hp = copy.deepcopy(hparams.wavernn_fatchord)
-        hp.bits, hp.mode = bits, mode
-        hparams.wavernn_fatchord.bits, hparams.wavernn_fatchord.mode = bits, mode   # infer_waveform reads the globals
-        sd = weights.make_state_dict(seed=0, bits=bits, mode=mode)
+        topo = TOPO.get(wl_, "fatchord-wavernn")
+        ghp = {"fatchord-wavernn": hparams.wavernn_fatchord, "runtimeracer-wavernn": hparams.wavernn_runtimeracer, "geneing-wavernn": hparams.wavernn_geneing}[topo]
+        hmode = "BITS" if topo == "geneing-wavernn" else mode
+        hp = copy.deepcopy(ghp)
+        hp.bits, hp.mode = bits, hmode
+        ghp.bits, ghp.mode = bits, hmode                                            # infer_waveform reads the globals
+        sd = topo_state_dict(weights, wl_, bits, mode)
         if wl_ in PRUNED:
             sd = weights.prune_state_dict(sd, z=0.9)
-        model = inference.load_state(sd, devices=[local_rank], override_hp_fatchord=hp)
+        model = inference.load_state(sd, topo, devices=[local_rank], override_hp_fatchord=hp, override_hp_runtimeracer=hp, override_hp_geneing=hp)
         model.precision = PREC[precision]
         mels_raw, utt_idx = workload_mels(wl_, rank, world)                      # synthesizer range [-4, 4]
         mels_host = [torch.from_numpy(m).pin_memory() for m in mels_raw]
@@ -378,7 +408,7 @@ def main():
     def loop_block(mres, precision):
         lt = mres["last_t"]
         kern = lt.get("loop_kernel", "?")
-        n_exch = 4 if kern == "wrnn_loop_rs_kernel" else (5 if (lt.get("precision") == _native.PREC_SPARSE_F32 or ctx["plan"][0] == "MOL") else 6)
+        n_exch = 8 if kern == "wrnn_loop_rr_kernel" else 4 if kern in ("wrnn_loop_rs_kernel", "wrnn_loop_gn_kernel") else (5 if (lt.get("precision") == _native.PREC_SPARSE_F32 or ctx["plan"][0] == "MOL") else 6)
         us = mres["loop_s"] * 1e6 / (lt["n_steps"] * max(1, lt["n_launches"]))
         fl = {"f32": floor["ll_us"], "f16": floor["counter_us"], "sparse": floor["cluster_us"]}[precision]
         return {"kernel": kern, "us_per_step": us, "folds": lt["n_folds"], "loop_steps": lt["n_steps"], "exchanges_per_step": n_exch,
@@ -436,6 +466,7 @@ def main():
                 hp = ctx["hp"]
                 inference.load_state(ctx["sd"], devices=list(range(world)), override_hp_fatchord=hp)
                 mel_h = ctx["mels_host"][0].numpy()
+                keep_min, inference.SHARD_MIN_FOLDS = inference.SHARD_MIN_FOLDS, 0       # force the split (the facade itself keeps 213 folds on one GPU)
                 inference.infer_waveform(mel_h, target=target, overlap=overlap)
                 ts = []
                 for _ in range(3):
@@ -445,7 +476,10 @@ def main():
                 sharded["cfg3ref_fold_sharded"] = {"n_gpus": world, "x_realtime": (w.shape[0] / float(np.mean(ts))) / 16000.0,
                                                    "ms_per_call": float(np.mean(ts)) * 1e3,
                                                    "what": "one 60 s utterance, 213 folds split into %d contiguous ranges, one engine + host thread per "
-                                                           "GPU, host gather + crossfade on GPU 0 inside the timed region (inference._infer_sharded)" % world}
+                                                           "GPU, host gather + crossfade on GPU 0 inside the timed region (inference._infer_sharded, "
+                                                           "forced: at <= 256 folds a step is a latency chain that does not shorten with fewer "
+                                                           "folds, so the facade keeps such an utterance on one GPU)" % world}
+                inference.SHARD_MIN_FOLDS = keep_min
             except Exception as e:
                 sharded["cfg3ref_fold_sharded"] = {"error": str(e)[:300]}
         if world > 1:
@@ -469,14 +503,14 @@ def main():
         pass
     if batched:
         # tensor bound: algorithmic FLOPs of the REFERENCE's step over the loop kernel's time
-        flops = 2.0 * macs_per_row_step(C) * F * S
+        flops = 2.0 * topo_macs(wl, C) * F * S
         achieved = flops / loop_s / 1e12
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": pk_kind + " bf16_tflops_sustained", "algorithmic_flops_per_launch": flops}
     else:
         # weight-streaming bound: every step touches the fp32 loop weights once; they live on-chip here
-        wbytes = 4.0 * macs_per_row_step(C)
+        wbytes = 4.0 * topo_macs(wl, C)
         if wl in PRUNED:
             wbytes = 4.0 * 0.41e6 * 1.25            # ~0.41 M MAC per fold-step at 90 % sparsity: value + one index byte per 1x4 group
         achieved = wbytes * S * max(1, F if wl in PRUNED else 1) / loop_s / 1e9

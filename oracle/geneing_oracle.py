@@ -16,43 +16,7 @@ GN = dict(rnn_dims=256, fc_dims=128, compute_dims=64, res_out_dims=64, res_block
 HOP = 200
 
 
-def make_state_dict_gn(seed=0, bits=9, mode="BITS"):
-    rng = np.random.default_rng(seed)
-
-    def U(shape, fan):
-        b = 1.0 / np.sqrt(fan)
-        return rng.uniform(-b, b, size=shape).astype(F32)
-
-    cd, ro, aux = GN["compute_dims"], GN["res_out_dims"], GN["res_out_dims"] // 2
-    sd = {"step": np.zeros((1,), np.int64)}
-
-    def bn(p):
-        sd[p + ".weight"] = rng.uniform(0.5, 1.5, cd).astype(F32)
-        sd[p + ".bias"] = (0.2 * rng.standard_normal(cd)).astype(F32)
-        sd[p + ".running_mean"] = (0.3 * rng.standard_normal(cd)).astype(F32)
-        sd[p + ".running_var"] = rng.uniform(0.5, 1.5, cd).astype(F32)
-        sd[p + ".num_batches_tracked"] = np.zeros((), np.int64)
-
-    k = 2 * GN["pad"] + 1
-    sd["upsample.resnet.conv_in.weight"] = U((cd, GN["feat"], k), GN["feat"] * k)
-    bn("upsample.resnet.batch_norm")
-    for i in range(GN["res_blocks"]):
-        p = "upsample.resnet.layers.%d" % i
-        sd[p + ".conv1.weight"], sd[p + ".conv2.weight"] = U((cd, cd, 1), cd), U((cd, cd, 1), cd)
-        bn(p + ".batch_norm1"); bn(p + ".batch_norm2")
-    sd["upsample.resnet.conv_out.weight"], sd["upsample.resnet.conv_out.bias"] = U((ro, cd, 1), cd), U((ro,), cd)
-    for idx, s in zip((1, 3, 5), GN["upsample"]):
-        w = np.full((1, 1, 1, 2 * s + 1), 1.0 / (2 * s + 1), np.float64) + 0.02 * rng.standard_normal((1, 1, 1, 2 * s + 1))
-        sd["upsample.up_layers.%d.weight" % idx] = w.astype(F32)
-    C = 30 if mode == "MOL" else 2 ** bits
-    n_in = GN["feat"] + aux - 1 + 1
-    R, Fc = GN["rnn_dims"], GN["fc_dims"]
-    sd["I.weight"], sd["I.bias"] = U((R, n_in), n_in), U((R,), n_in)
-    sd["rnn1.weight_ih_l0"], sd["rnn1.weight_hh_l0"] = U((3 * R, R), R), U((3 * R, R), R)
-    sd["rnn1.bias_ih_l0"], sd["rnn1.bias_hh_l0"] = U((3 * R,), R), U((3 * R,), R)
-    sd["fc1.weight"], sd["fc1.bias"] = U((Fc, R + aux), R + aux), U((Fc,), R + aux)
-    sd["fc3.weight"], sd["fc3.bias"] = U((C, Fc), Fc), U((C,), Fc)
-    return sd
+from .weights import make_state_dict_gn  # noqa: E402,F401  (rtvc_b200/synth.py)
 
 
 def upsample_network_generic(mel, sd, pad=2):

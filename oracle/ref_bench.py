@@ -24,16 +24,17 @@ def available():
     return ref_import.find_reference_root() is not None
 
 
-def time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=None, budget_s=10.0):
+def time_reference(sd, mode, bits, mel_norm, batched, target, overlap, threads=None, budget_s=10.0, model_type="fatchord-wavernn"):
     """sd: numpy state dict (oracle/weights.py); mel_norm: (80, T) float32 already divided by max_abs_value."""
     assert os.environ.get("CUDA_VISIBLE_DEVICES", None) == "", "hide the GPUs before importing torch"
     import torch
     from . import ref_import
     base, fv, hpm, _ = ref_import.import_reference()
     torch.set_num_threads(int(threads or os.cpu_count()))
-    hp = copy.deepcopy(hpm.wavernn_fatchord)
-    hp.bits, hp.mode = bits, mode
-    model, _ = base.init_voc_model(base.MODEL_TYPE_FATCHORD, torch.device("cpu"), override_hp_fatchord=hp)
+    hp = copy.deepcopy({"fatchord-wavernn": hpm.wavernn_fatchord, "runtimeracer-wavernn": hpm.wavernn_runtimeracer,
+                        "geneing-wavernn": hpm.wavernn_geneing}[model_type])
+    hp.bits, hp.mode = bits, ("BITS" if model_type == "geneing-wavernn" else mode)
+    model, _ = base.init_voc_model(model_type, torch.device("cpu"), override_hp_fatchord=hp, override_hp_runtimeracer=hp, override_hp_geneing=hp)
     state = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
     model.load_state_dict(state, strict=False)
     model.eval()

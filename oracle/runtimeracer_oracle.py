@@ -18,28 +18,7 @@ RR_RNN = 256      # config/hparams.py:363
 RR_FC = 256       # :364
 
 
-def make_state_dict_rr(seed=0, bits=9, mode="RAW"):
-    """Deterministic weights of the runtimeracer layout: the front end of oracle/weights.py (same UpsampleNetwork, res_out_dims
-    128) plus I, rnn1..rnn4, fc1..fc5 of runtimeracer_version.py:119-131."""
-    base = make_state_dict(seed=seed, bits=bits, mode=mode)
-    sd = {k: v for k, v in base.items() if k.startswith("upsample.") or k == "step"}
-    rng = np.random.default_rng(seed + 7919)
-
-    def U(shape, fan):
-        b = 1.0 / np.sqrt(fan)
-        return rng.uniform(-b, b, size=shape).astype(F32)
-
-    n_in = FEAT_DIMS + AUX_DIMS - 1 + 1
-    sd["I.weight"], sd["I.bias"] = U((RR_RNN, n_in), n_in), U((RR_RNN,), n_in)
-    for name, n_inp in (("rnn1", RR_RNN), ("rnn2", RR_RNN), ("rnn3", RR_RNN + AUX_DIMS), ("rnn4", RR_RNN)):
-        sd[name + ".weight_ih_l0"] = U((3 * RR_RNN, n_inp), RR_RNN)
-        sd[name + ".weight_hh_l0"] = U((3 * RR_RNN, RR_RNN), RR_RNN)
-        sd[name + ".bias_ih_l0"] = U((3 * RR_RNN,), RR_RNN)
-        sd[name + ".bias_hh_l0"] = U((3 * RR_RNN,), RR_RNN)
-    for name, n_inp, n_out in (("fc1", RR_RNN + AUX_DIMS, RR_FC), ("fc2", RR_FC, RR_FC), ("fc3", RR_RNN + AUX_DIMS, RR_FC),
-                               ("fc4", RR_FC, RR_FC), ("fc5", RR_FC, n_classes(bits, mode))):
-        sd[name + ".weight"], sd[name + ".bias"] = U((n_out, n_inp), n_inp), U((n_out,), n_inp)
-    return sd
+from .weights import make_state_dict_rr  # noqa: E402,F401  (the generator lives with the other input generators: rtvc_b200/synth.py)
 
 
 def _gru(x, h, sd, name):

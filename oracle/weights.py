@@ -9,4 +9,5 @@ if _ROOT not in sys.path:
 import rtvc_b200  # noqa: E402,F401
 from rtvc_b200.synth import *  # noqa: E402,F401,F403
 from rtvc_b200.synth import (AUX_DIMS, COMPUTE_DIMS, FC_DIMS, FEAT_DIMS, HOP, PAD, RES_BLOCKS, RES_OUT_DIMS, RNN_DIMS,  # noqa: E402,F401
-                             UPSAMPLE, make_state_dict, n_classes, prune_state_dict, synthetic_mel)
+                             UPSAMPLE, make_state_dict, make_state_dict_gn, make_state_dict_rr, n_classes, prune_state_dict,
+                             synthetic_mel)

@@ -8,6 +8,8 @@ from .. import _native
 from ..config.hparams import sp, wavernn_fatchord, wavernn_geneing, wavernn_runtimeracer
 from .models import base
 
+SHARD_MIN_FOLDS = 256    # infer_waveform splits one utterance over the loaded engines only above this many folds
+
 _model = None        # list of per-GPU WaveRNN objects once loaded
 _model_type = None
 _seed = 0
@@ -135,7 +137,17 @@ def infer_waveform(mel, normalize=True, batched=True, target=None, overlap=None,
         mel = mel / sp.max_abs_value
     mel = np.ascontiguousarray(mel, dtype=np.float32)
     seed = _next_seed()
-    if len(_model) == 1 or not batched:
+    shard = len(_model) > 1 and batched
+    if shard:
+        # Splitting ONE utterance pays only where the loop's time grows with the fold count.  Below ~256 folds a step is a latency
+        # chain whose length does not depend on the work (10.6 us at 18 folds, 12.7 us at 213), so two GPUs
+        # with half the folds each finish no earlier and the host gather is pure loss (measured on 2 B200s, cfg3ref: 263 ms sharded
+        # vs 77 ms on one GPU).
+        try:
+            shard = _native.fold_plan(mel.shape[1] * sp.hop_size, int(target), int(overlap))[0] > SHARD_MIN_FOLDS
+        except Exception:
+            shard = False
+    if not shard:
         return _model[0].generate(mel[None, ...], batched, target, overlap, hp_wavernn.mu_law, sp.preemphasize, progress_callback,
                                   seed=seed)
     return _infer_sharded(mel, target, overlap, hp_wavernn.mu_law, sp.preemphasize, seed, progress_callback)

@@ -7,7 +7,7 @@ from tests.util import norm_mel
 pytestmark = pytest.mark.gpu
 
 
-def test_two_engines_match_one():
+def test_two_engines_match_one(monkeypatch):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -26,8 +26,12 @@ def test_two_engines_match_one():
     one = inference.infer_waveform(mel, target=800, overlap=100)
     inference.load_state(sd, devices=[0, 1], override_hp_fatchord=hp)
     inference.set_seed(5)
-    two = inference.infer_waveform(mel, target=800, overlap=100)
+    two = inference.infer_waveform(mel, target=800, overlap=100)       # 13 folds: the facade keeps one GPU (SHARD_MIN_FOLDS)
     assert np.array_equal(one, two)
+    monkeypatch.setattr(inference, "SHARD_MIN_FOLDS", 0)               # force the fold-range split over both engines
+    inference.set_seed(5)
+    split = inference.infer_waveform(mel, target=800, overlap=100)
+    assert np.array_equal(one, split)
     inference.set_seed(5)
     many = inference.infer_waveforms([mel, mel[:, :40], mel[:, :33]], target=800, overlap=100)
     assert [len(w) for w in many] == [59 * 200, 39 * 200, 32 * 200]
