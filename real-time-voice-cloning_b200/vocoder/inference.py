@@ -141,8 +141,8 @@ def infer_waveform(mel, normalize=True, batched=True, target=None, overlap=None,
     if shard:
         # Splitting ONE utterance pays only where the loop's time grows with the fold count.  Below ~256 folds a step is a latency
         # chain whose length does not depend on the work (10.6 us at 18 folds, 12.7 us at 213), so two GPUs
-        # with half the folds each finish no earlier and the host gather is pure loss (measured on 2 B200s, cfg3ref: 263 ms sharded
-        # vs 77 ms on one GPU).
+        # with half the folds each finish hardly earlier and the host gather eats the rest (measured on 2 B200s, cfg3ref: 73 ms
+        # sharded vs 77 ms on one GPU).
         try:
             shard = _native.fold_plan(mel.shape[1] * sp.hop_size, int(target), int(overlap))[0] > SHARD_MIN_FOLDS
         except Exception:
