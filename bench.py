@@ -501,7 +501,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s:%s" % (wl, kern))
     except Exception:
         pass
-    if batched:
+    if batched and args.precision == "f16":
         # tensor bound: algorithmic FLOPs of the REFERENCE's step over the loop kernel's time
         flops = 2.0 * topo_macs(wl, C) * F * S
         achieved = flops / loop_s / 1e12
@@ -509,11 +509,12 @@ def main():
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": pk_kind + " bf16_tflops_sustained", "algorithmic_flops_per_launch": flops}
     else:
-        # weight-streaming bound: every step touches the fp32 loop weights once; they live on-chip here
+        # weight-streaming bound of the fp32 loops (CUDA-core FMAs, no tensor pipe): every step touches the fp32 loop
+        # weights once, whatever the number of folds; they live on-chip here
         wbytes = 4.0 * topo_macs(wl, C)
         if wl in PRUNED:
             wbytes = 4.0 * 0.41e6 * 1.25            # ~0.41 M MAC per fold-step at 90 % sparsity: value + one index byte per 1x4 group
-        achieved = wbytes * S * max(1, F if wl in PRUNED else 1) / loop_s / 1e9
+        achieved = wbytes * S * max(1, last_t["n_launches"]) * max(1, F if wl in PRUNED else 1) / loop_s / 1e9
         peak = float(pk.get("hbm_gbs"))
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": pk_kind + " hbm_gbs", "algorithmic_bytes_per_step": wbytes,

@@ -19,12 +19,31 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+STAMP = os.path.join(HERE, "build_stamp.json")
+
+
+def source_digest():
+    """sha256 over every source the library is built from (names + contents) and the compiler flags: the library is rebuilt when
+    -- and only when -- this changes (mtimes do not survive a snapshot copy; a stale .so next to newer sources must not pass)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc")))
+    deps.append(os.path.join(HERE, "..", "include", "wavernn_b200.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "wavernn_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        import json
+        return json.load(open(STAMP)).get("sources_sha256") != source_digest()
+    except Exception:
+        return True
 
 
 def build(force=False, verbose=False):
@@ -48,6 +67,12 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed")
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write("\n".join(log))
+    import json
+    import time
+    ver = subprocess.run([NVCC, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1:]
+    with open(STAMP, "w") as f:       # travels with the .so: which sources / flags / compiler it was built from, and where
+        json.dump({"sources_sha256": source_digest(), "flags": FLAGS, "nvcc": ver, "built_at": time.strftime("%Y-%m-%dT%H:%M:%S"),
+                   "host": os.uname().nodename, "objects": [os.path.basename(o) for o in objs]}, f, indent=1)
     if verbose:
         print("\n".join(log))
     return LIB

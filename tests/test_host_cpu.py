@@ -28,6 +28,21 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS)
 
 
+def test_library_is_built_from_these_sources():
+    """The shipped .so carries a stamp (build_stamp.json) of the sources and flags it was compiled from; a library that is older than
+    its sources must not pass for the product."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("_rtvc_build", os.path.join(ROOT, "real-time-voice-cloning_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()                                      # no-op when the stamp matches
+    stamp = json.load(open(b.STAMP))
+    assert stamp["sources_sha256"] == b.source_digest()
+    assert "arch=compute_100a,code=sm_100a" in stamp["flags"] and "-lineinfo" in stamp["flags"]
+    assert os.path.getmtime(b.LIB) >= os.path.getmtime(b.STAMP) - 60
+
+
 def test_fold_plan_matches_oracle():
     _native, _ = _lib()
     rng = np.random.default_rng(0)
