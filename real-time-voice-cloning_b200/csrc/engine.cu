@@ -469,7 +469,8 @@ int wrnn_finalize(wrnn_engine* e) {
                     if (role == 0)
                         for (int k = 0; k < 30; ++k) put_tile(t1, 32, k, f3w->data.data() + (size_t)k * H);
                 } else {
-                    for (int u = 0; u < 64; ++u) put_tile(t0, 64, u, (role == 2 ? Wfc1a : Wfc2a) + (size_t)(64 * c + u) * H);
+                    const int FU = H / kRsT3;
+                    for (int u = 0; u < FU; ++u) put_tile(t0, FU, u, (role == 2 ? Wfc1a : Wfc2a) + (size_t)(FU * c + u) * H);
                 }
             }
             CU(e->wRs[role].ensure(hw.size()));

@@ -111,7 +111,10 @@ cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float
                                const FoldDesc* folds, int B, int S, int Mg, float4* CS, cudaStream_t stream);
 
 // ---- role-specialised tensor-core loop, MOL, <= 128 folds per group (loop_rs.cu) ------------------------------------
-constexpr int kRsT1 = 16, kRsT2 = 16, kRsT3 = 8, kRsT4 = 8;     // CTAs per role: GRU1 (+fc3 + draw), GRU2, fc1, fc2
+#ifndef WRNN_RS_FC_CTAS
+#define WRNN_RS_FC_CTAS 8
+#endif
+constexpr int kRsT1 = 16, kRsT2 = 16, kRsT3 = WRNN_RS_FC_CTAS, kRsT4 = WRNN_RS_FC_CTAS;     // CTAs per role: GRU1 (+fc3 + draw), GRU2, fc1, fc2
 constexpr int kRsCtas = kRsT1 + kRsT2 + kRsT3 + kRsT4;          // one group
 constexpr int kRsBufs = 2;                                      // exchange matrices are double-buffered by step parity
 constexpr int kRsMaxFoldsPerGroup = 128;

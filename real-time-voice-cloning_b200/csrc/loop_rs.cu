@@ -53,6 +53,8 @@ constexpr int kW0 = 0;                                   // first tile: T1 W_hh1
 constexpr int kW1 = 96 * 128 * 8;                        // second tile: T1 fc3 (32 rows), T2 W_hh2 (96)
 constexpr int kNoiseOfs = kW1 + 32 * 128 * 8;            // T1 only: the step's mixture noise, [12][512 threads] floats (24 KB behind the fc3 tile)
 constexpr int kWEnd = kW1 + 96 * 128 * 8;                // 196608
+constexpr int kFU = kRnn / kRsT3;                        // units per FC-role CTA: 64 (8 CTAs per role) or 32 (16)
+static_assert(kRsT3 == kRsT4 && (kFU == 128 || kFU == 64 || kFU == 32), "thread <-> unit map of the FC roles");
 constexpr int kConstOfs = kWEnd;                         // per-unit constants, <= 5 x 64 floats
 constexpr int kCtlOfs = kConstOfs + 2048;
 constexpr int kSmemBytes = kCtlOfs + 256;
@@ -582,8 +584,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     {
         const unsigned char* img = role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
                                  : role == 1 ? p.w2 + (size_t)cta * kWEnd
-                                 : role == 2 ? p.w3 + (size_t)cta * (64 * 128 * 8) : p.w4 + (size_t)cta * (64 * 128 * 8);
-        const int bytes = role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : 64 * 128 * 8);
+                                 : role == 2 ? p.w3 + (size_t)cta * (kFU * 128 * 8) : p.w4 + (size_t)cta * (kFU * 128 * 8);
+        const int bytes = role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : kFU * 128 * 8);
         const uint4* src = reinterpret_cast<const uint4*>(img);
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     } else if (role == 1) {     // [v2 r,z,n | b_hn2] x 32 units
         if (tid < 128) { const int a = tid >> 5, u = tid & 31, j = 32 * cta + u; cst[tid] = a < 3 ? p.v2[a * kRnn + j] : p.bhn2[j]; }
     } else if (role == 2) {     // v3 x 64 units
-        if (tid < 64) cst[tid] = p.v3[64 * cta + tid];
+        if (tid < kFU) cst[tid] = p.v3[kFU * cta + tid];
     }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], NW);
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 job(96u, kColD1, kW1, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);               // W_hh2 h2(t)
             }
         } else {
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job(64u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
         }
         }
     } else {
@@ -862,41 +864,42 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
             const bool fc1 = role == 2;
-            const uint32_t v3_s = cst_s + 64u * L.cs;
+            constexpr int kPU = kFU / 4;                       // units per thread: 16 (8 CTAs per FC role) or 8 (16 CTAs)
+            const uint32_t v3_s = cst_s + 4u * kPU * L.cs;
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
                 trace<kTrace>(p, t, 0);
-                float cc[16];
+                float cc[kPU];
                 cs_wait(t);
                 if (L.wlive) {
-                    const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + 64 * cta + 16 * L.cs);
+                    const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + kFU * cta + kPU * L.cs);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 q4 = __ldcg(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
+                    for (int i = 0; i < kPU / 4; ++i) { const float4 q4 = __ldcg(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
                 }
                 const float x = ingest<kTrace>(p, ctl, ctl_s, L, MAT(fc1 ? MS2 : MF1, t), fc1 ? kTagE : kTagS, GEN(t), -1, t, 1,
                                                (fc1 && t > 0) ? xw : nullptr, (uint32_t)t).x;
                 if (fc1 && L.wlive) {
-                    float kv[8];
-                    lds8(v3_s, kv);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) cc[i] = fmaf(kv[i], x, cc[i]);
-                    lds8(v3_s + 32u, kv);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cc[8 + i] = fmaf(kv[i], x, cc[8 + i]);
+                    for (int i = 0; i < kPU / 4; ++i) {
+                        const float4 v = lds4(v3_s + 16u * i);
+                        cc[4 * i] = fmaf(v.x, x, cc[4 * i]); cc[4 * i + 1] = fmaf(v.y, x, cc[4 * i + 1]);
+                        cc[4 * i + 2] = fmaf(v.z, x, cc[4 * i + 2]); cc[4 * i + 3] = fmaf(v.w, x, cc[4 * i + 3]);
+                    }
                 }
                 wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
                 tcgen05_fence_after();
                 trace<kTrace>(p, t, 4);
                 if (L.wlive) {
-                    float d[16];
-                    tmem_ld8(L.tlane + kColD0 + 16 * L.cs, d); tmem_ld8(L.tlane + kColD0 + 16 * L.cs + 8, d + 8);
+                    float d[kPU];
+#pragma unroll
+                    for (int i = 0; i < kPU / 8; ++i) tmem_ld8(L.tlane + kColD0 + kPU * L.cs + 8 * i, d + 8 * i);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) d[i] = fmaxf(d[i] + cc[i], 0.f);
+                    for (int i = 0; i < kPU; ++i) d[i] = fmaxf(d[i] + cc[i], 0.f);
                     if (L.live) {
                         uint4* m = MAT(fc1 ? MF1 : MF2, t);
                         const uint32_t want = GEN(t) ? kTagS : 0u;
-                        publish8(m, 8 * cta + 2 * L.cs, L.row, d, kTagS, want);
-                        publish8(m, 8 * cta + 2 * L.cs + 1, L.row, d + 8, kTagS, want);
+#pragma unroll
+                        for (int i = 0; i < kPU / 8; ++i) publish8(m, (kFU / 8) * cta + (kPU / 8) * L.cs + i, L.row, d + 8 * i, kTagS, want);
                     }
                 }
                 tcgen05_fence_before();
@@ -927,7 +930,7 @@ __global__ void __launch_bounds__(512) expand_cond_rs_kernel(const float4* __res
 }
 
 cudaError_t set_rs_deadline(long long cycles) { return cudaMemcpyToSymbol(g_rs_deadline, &cycles, sizeof(cycles)); }
-size_t loop_rs_image_bytes(int role) { return role == 0 ? (size_t)kW1 + 32 * 128 * 8 : (role == 1 ? (size_t)kWEnd : (size_t)64 * 128 * 8); }
+size_t loop_rs_image_bytes(int role) { return role == 0 ? (size_t)kW1 + 32 * 128 * 8 : (role == 1 ? (size_t)kWEnd : (size_t)kFU * 128 * 8); }
 size_t loop_rs_exchange_bytes(int groups) { return (size_t)groups * kMats * kRsBufs * kMatChunks * 16; }
 
 cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
