@@ -69,9 +69,10 @@ def step_logits_gn(x, m_t, a_t, h1, sd):
     return (v @ sd["fc3.weight"].T + sd["fc3.bias"]).astype(F32), h1                                         # :211
 
 
-def generate_gn(mel_norm, sd, seed, bits=9, batched=True, target=1000, overlap=200, forced=None, max_steps=0):
-    """geneing_version.py:generate in mode 'BITS' (mu_law False, config/hparams.py:292) with the build's Philox noise contract."""
-    C = 2 ** bits
+def generate_gn(mel_norm, sd, seed, bits=9, batched=True, target=1000, overlap=200, forced=None, max_steps=0, mode="BITS"):
+    """geneing_version.py:generate in mode 'BITS' (mu_law False, config/hparams.py:292) or 'MOL' (:217-223, the fatchord rule) with the
+    build's Philox noise contract."""
+    C = 2 ** bits if mode == "BITS" else 30
     T = mel_norm.shape[1]
     mels, aux = upsample_network_generic(mel_norm, sd)
     if batched:
@@ -84,11 +85,17 @@ def generate_gn(mel_norm, sd, seed, bits=9, batched=True, target=1000, overlap=2
     h1 = np.zeros((B, GN["rnn_dims"]), F32)
     x = np.zeros((B, 1), F32)
     logits, samples = np.zeros((B, S, C), F32), np.zeros((B, S), F32)
-    U = philox.raw_uniforms(seed, S, B)
+    if mode == "BITS":
+        U = philox.raw_uniforms(seed, S, B)
+    else:
+        UM, UL = philox.mol_uniforms(seed, S, B)
     for i in range(S):
         lg, h1 = step_logits_gn(x, mels[:, i], aux[:, i], h1, sd)
         logits[:, i] = lg
-        samples[:, i] = orc.label_to_float(orc.sample_raw(lg, U[i]), C)
+        if mode == "BITS":
+            samples[:, i] = orc.label_to_float(orc.sample_raw(lg, U[i]), C)
+        else:
+            samples[:, i] = orc.sample_mol(lg, UM[i], UL[i])[0]
         x = (forced[:, i] if forced is not None else samples[:, i]).reshape(B, 1).astype(F32)
     out = dict(logits=logits, samples=samples, wav=None)
     if not max_steps:

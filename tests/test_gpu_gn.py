@@ -83,3 +83,28 @@ def test_geneing_rejects_beta_mode():
     hp.mode = "RAW"
     with pytest.raises(NotImplementedError):
         base.init_voc_model(base.MODEL_TYPE_GENEING, 0, override_hp_geneing=hp)
+
+
+def test_geneing_mol_vs_oracle():
+    """Mode 'MOL' of this topology (geneing_version.py:217-223: the fatchord mixture rule on fc3's 30 outputs): first 48 steps against
+    the oracle, teacher-forced on the kernel's own samples (no reference-minted vector exists for this mode: the golden is 'BITS')."""
+    import rtvc_b200  # noqa: F401
+    from rtvc_b200.vocoder.models import base
+    from rtvc_b200.config import hparams
+    hp = copy.deepcopy(hparams.wavernn_geneing)
+    hp.mode = "MOL"
+    sd = gn.make_state_dict_gn(seed=9, bits=9, mode="MOL")
+    model, _ = base.init_voc_model(base.MODEL_TYPE_GENEING, 0, override_hp_geneing=hp)
+    model.load_state_dict(sd)
+    assert model.n_classes == 30
+    mel = norm_mel(40, 6)
+    steps, tg, ov = 48, 600, 100
+    o = model.generate_debug(mel, True, tg, ov, want_logits=True, seed=11, max_steps=steps)
+    F = o["samples"].shape[0]
+    forced = np.zeros((F, tg + 2 * ov), np.float32)
+    forced[:, :steps] = o["samples"]
+    t = gn.generate_gn(mel, sd, 11, bits=9, batched=True, target=tg, overlap=ov, forced=forced, max_steps=steps, mode="MOL")
+    err = _rel(o["logits"], t["logits"])
+    agree = float((np.abs(o["samples"] - t["samples"]) < 1e-4).mean())
+    print("geneing MOL, %d folds x %d steps vs oracle: logits rel err %.3e, draw agreement %.5f" % (F, steps, err, agree))
+    assert err < 1e-4 and agree >= 0.999, (err, agree)
