@@ -87,7 +87,7 @@ struct wrnn_engine {
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor, bCsDone;
     DevBuf wTc, wTcS, bTcExch, bCS;
     DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
-    DevBuf wRs[4], bRsExch;     // role-specialised tensor-core loop (MOL): per-role weight images, exchange matrices + sample words
+    DevBuf wRs[5], bRsExch;     // role-specialised tensor-core loop: per-role weight images ([4]: RAW sampler CTAs), exchange matrices + sample words
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
     int spStride[2] = {0, 0};
     DevBuf wCondTc, bCondH;     // tensor-core front end: hi/lo fp16 weights (scaled by 2^8) and activation pairs
@@ -234,7 +234,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2, &e->wRs[0], &e->wRs[1], &e->wRs[2], &e->wRs[3], &e->bRsExch};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2, &e->wRs[0], &e->wRs[1], &e->wRs[2], &e->wRs[3], &e->wRs[4], &e->bRsExch};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -438,10 +438,12 @@ int wrnn_finalize(wrnn_engine* e) {
         }
     }
 
-    // ---- role-specialised tensor-core loop (MOL, loop_rs.cu): one image per CTA and role, K-major SWIZZLE_128B tiles --------
-    //   T1 (GRU1, units 32c..32c+31): [W_hh1 rows gate*32+u (96)] [fc3 rows (30 of 32)]      T2 (GRU2): [W_ih2a (96)] [W_hh2 (96)]
+    // ---- role-specialised tensor-core loop (loop_rs.cu): one image per CTA and role, K-major SWIZZLE_128B tiles ---------------
+    //   T1 (GRU1, units 32c..32c+31): [W_hh1 rows gate*32+u (96)] [MOL: fc3 rows (30 of 32)]  T2 (GRU2): [W_ih2a (96)] [W_hh2 (96)]
     //   T3 (fc1, units 64c..64c+63): [fc1[:, :512] (64)]                                       T4 (fc2): [fc2[:, :512] (64)]
-    if (C == 30) {
+    //   T5 (RAW with 512 / 1024 classes: sampler CTAs): [fc3 rows 128c..128c+127]
+    const bool rs_raw = e->mode == WRNN_MODE_RAW && C % kRsQCols == 0 && C / kRsQCols >= 2 && C / kRsQCols <= kRsMaxSamplers;
+    if (C == 30 || rs_raw) {
         auto put_tile = [&](unsigned char* tile, int nrows, int r, const float* src) {
             for (int kb = 0; kb < 8; ++kb)
                 for (int c = 0; c < 8; ++c) {
@@ -466,7 +468,7 @@ int wrnn_finalize(wrnn_engine* e) {
                             if (role == 0) put_tile(t0, 96, 32 * gt + u, r1hh->data.data() + r);
                             else { put_tile(t0, 96, 32 * gt + u, Wih2a + r); put_tile(t1, 96, 32 * gt + u, r2hh->data.data() + r); }
                         }
-                    if (role == 0)
+                    if (role == 0 && C == 30)
                         for (int k = 0; k < 30; ++k) put_tile(t1, 32, k, f3w->data.data() + (size_t)k * H);
                 } else {
                     const int FU = H / kRsT3;
@@ -475,6 +477,15 @@ int wrnn_finalize(wrnn_engine* e) {
             }
             CU(e->wRs[role].ensure(hw.size()));
             CU(cudaMemcpy(e->wRs[role].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+        }
+        if (rs_raw) {
+            const int nq = C / kRsQCols;
+            const size_t img = (size_t)kRsQCols * 1024;
+            std::vector<unsigned char> hw((size_t)nq * img, 0);
+            for (int c = 0; c < nq; ++c)
+                for (int k = 0; k < kRsQCols; ++k) put_tile(hw.data() + (size_t)c * img, kRsQCols, k, f3w->data.data() + (size_t)(kRsQCols * c + k) * H);
+            CU(e->wRs[4].ensure(hw.size()));
+            CU(cudaMemcpy(e->wRs[4].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
         }
     }
 
@@ -944,7 +955,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     float ms_expand = 0.f;
     const int wave = is_rr ? kRrMaxFolds : is_gn ? kGnMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
     // role-specialised loop: as many 48-CTA groups as the device holds; WRNN_RS=0 keeps loop_tc.cu for every fold count
-    const int rs_groups_max = std::max(0, e->n_sms / kRsCtas);
+    const int rs_samplers = (e->mode == WRNN_MODE_RAW && e->wRs[4].p) ? e->C / kRsQCols : 0;     // RAW: sampler CTAs per group
+    const int rs_ctas = kRsCtas + rs_samplers;
+    const int rs_groups_max = std::max(0, e->n_sms / rs_ctas);
     const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);
@@ -1026,7 +1039,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             if (lerr != cudaSuccess) return fail(e, WRNN_ERR_CUDA, std::string("block-sparse loop launch: ") + cudaGetErrorString(lerr));
             e->launches += 1;
             rq->loop_kernel = WRNN_LOOP_SPARSE;
-        } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wRs[0].p && B <= rs_max_folds) {
+        } else if (use_tc && (e->mode == WRNN_MODE_MOL || rs_samplers > 0) && e->wRs[0].p && B <= rs_max_folds) {
             // ---- role-specialised tensor-core loop (loop_rs.cu): the latency-bound regime, <= 128 folds per 48-CTA group ---------
             // groups: two leave 52 SMs to the expanders (three groups run the loop 4 % faster but starve them)
             int G = std::min(std::min(rs_groups_max, 2), std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
@@ -1037,7 +1050,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             // groups leave free, into a ring sized to stay resident in L2 (WRNN_RS_RING_MB, default 48 MB: three 4-step chunks at 213 folds): produced / consumed
             // counters per chunk of kRsChunk steps order the two sides.  WRNN_RS_EXPAND=0 (or no SM left): the whole table is
             // expanded before the launch.
-            const int n_exp = e->n_sms - G * kRsCtas;
+            const int n_exp = e->n_sms - G * rs_ctas;
             const bool ring = n_exp >= 1 && !(getenv("WRNN_RS_EXPAND") && atoi(getenv("WRNN_RS_EXPAND")) == 0);
             const int nchunks = (S + kRsChunk - 1) / kRsChunk;
             int cs_steps = nchunks * kRsChunk;
@@ -1058,7 +1071,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                                          e->bFolds.as<FoldDesc>() + w0, B, S, Ng, cs_steps, e->bCS.as<float>(), st));
             CU(cudaEventRecord(e->evx[1], st));
             expanded = true;
-            const size_t xbytes = loop_rs_exchange_bytes(G), wbytes = (size_t)G * 128 * sizeof(unsigned long long);
+            // exchange matrices (all bytes 0xFF), then the sample words and (RAW) the soft-max partial words (zero)
+            const size_t xbytes = loop_rs_exchange_bytes(G);
+            const size_t wbytes = (size_t)G * 128 * sizeof(unsigned long long) * (1 + 2 * kRsMaxSamplers * 2);
             CU(e->bRsExch.ensure(xbytes + wbytes));
             CU(cudaMemsetAsync(e->bRsExch.p, 0xFF, xbytes, st));
             CU(cudaMemsetAsync(e->bRsExch.as<unsigned char>() + xbytes, 0, wbytes, st));
@@ -1082,6 +1097,9 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.B = B; rp.S = S; rp.seed = rq->seed;
             rp.X = e->bRsExch.as<uint4>();
             rp.bX = reinterpret_cast<unsigned long long*>(e->bRsExch.as<unsigned char>() + xbytes);
+            rp.bP = rp.bX + (size_t)G * 128;
+            rp.w5 = e->wRs[4].as<unsigned char>();
+            rp.mode = e->mode; rp.C = e->C; rp.n_samplers = rs_samplers; rp.ctas = rs_ctas;
             rp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
             rp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
             rp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
@@ -1089,12 +1107,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.abort_flag = e->dAbort;
             int* hdbg = nullptr;
             if (getenv("WRNN_RS_DEBUG") && atoi(getenv("WRNN_RS_DEBUG"))) {     // checkpoints in mapped host memory: readable while the kernel hangs
-                CU(cudaHostAlloc(&hdbg, (size_t)G * kRsCtas * 32 * sizeof(int), cudaHostAllocMapped));
-                memset(hdbg, 0, (size_t)G * kRsCtas * 32 * sizeof(int));
+                CU(cudaHostAlloc(&hdbg, (size_t)G * rs_ctas * 32 * sizeof(int), cudaHostAllocMapped));
+                memset(hdbg, 0, (size_t)G * rs_ctas * 32 * sizeof(int));
                 CU(cudaHostGetDevicePointer(&rp.dbg, hdbg, 0));
             }
             const char* rs_trace = getenv("WRNN_RS_TRACE");
-            const size_t trace_n = (size_t)G * kRsCtas * 8 * 48;
+            const size_t trace_n = (size_t)G * rs_ctas * 8 * 48;
             if (rs_trace) {
                 CU(e->bFloor.ensure(trace_n * sizeof(unsigned long long)));
                 CU(cudaMemsetAsync(e->bFloor.p, 0, trace_n * sizeof(unsigned long long), st));
@@ -1135,7 +1153,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 CU(cudaMemcpyAsync(tr.data(), e->bFloor.p, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 if (FILE* f = fopen(rs_trace, "w")) {
-                    for (int c = 0; c < G * kRsCtas; ++c)
+                    for (int c = 0; c < G * rs_ctas; ++c)
                         for (int k = 0; k < 8; ++k) {
                             fprintf(f, "%d %d", c, k);
                             for (int j = 0; j < 48; ++j) fprintf(f, " %llu", tr[((size_t)c * 8 + k) * 48 + j]);
@@ -1152,7 +1170,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_dbg).count();
                     if (dt > 3.0 && !dumped) {
                         dumped = true;
-                        for (int c = 0; c < G * kRsCtas; ++c) {
+                        for (int c = 0; c < G * rs_ctas; ++c) {
                             fprintf(stderr, "[rs dbg] cta %3d:", c);
                             for (int w = 0; w < 20; ++w) fprintf(stderr, " %d:%02x", hdbg[c * 32 + w] >> 8, hdbg[c * 32 + w] & 0xFF);
                             fprintf(stderr, "\n");

@@ -528,13 +528,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     float* cst = reinterpret_cast<float*>(smem + kConstOfs);
     const uint32_t smem_s = smem_u32(smem), ctl_s = smem_s + kCtlOfs, cst_s = smem_s + kConstOfs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = (int)blockIdx.x / kRsCtas, rc = (int)blockIdx.x % kRsCtas;
-    const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : 3));
-    const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : rc - kRsT1 - kRsT2 - kRsT3));
+    const int g = (int)blockIdx.x / p.ctas, rc = (int)blockIdx.x % p.ctas;
+    const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : (rc < kRsCtas ? 3 : 4)));      // 4: RAW sampler (T5)
+    const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : (role == 3 ? rc - kRsT1 - kRsT2 - kRsT3 : rc - kRsCtas)));
+    const bool raw = p.mode == 0;                                   // RAW: fc3 + the draw live on the sampler CTAs, T1 only waits for the sample
     const int fold0 = g * p.Ng, nrows = max(0, min(p.Ng, p.B - fold0));
     const int S = p.S;
-    const bool expander = (int)blockIdx.x >= p.G * kRsCtas;        // CTAs past the groups produce the conditioning records
-    const unsigned int consumers = (unsigned int)(p.G * kRsCtas * NW);   // warps that read every record chunk
+    const bool expander = (int)blockIdx.x >= p.G * p.ctas;         // CTAs past the groups produce the conditioning records
+    const unsigned int consumers = (unsigned int)(p.G * kRsCtas * NW);   // warps that read every record chunk (the samplers read none)
     if ((smem_s & 1023u) != 0u) {          // never on this toolchain; a misaligned tile would compute garbage silently
         if (tid == 0) atomicExch(p.abort_flag, 1);
         return;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         __syncthreads();
         if (warp < NW) {
             const float* coef_s = reinterpret_cast<const float*>(smem);
-            const int e_idx = (int)blockIdx.x - p.G * kRsCtas;
+            const int e_idx = (int)blockIdx.x - p.G * p.ctas;
             const int nchunks = (S + kRsChunk - 1) / kRsChunk, ring_chunks = p.cs_steps / kRsChunk;
             const long long nitems = (long long)nchunks * p.B;
             int waited = -1;
@@ -582,10 +583,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
 
     // ---- one-time setup: weight tiles, constants, barriers, TMEM ------------------------------------------------------
     {
-        const unsigned char* img = role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
+        const unsigned char* img = role == 4 ? p.w5 + (size_t)cta * (kRsQCols * 128 * 8)
+                                 : role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
                                  : role == 1 ? p.w2 + (size_t)cta * kWEnd
                                  : role == 2 ? p.w3 + (size_t)cta * (kFU * 128 * 8) : p.w4 + (size_t)cta * (kFU * 128 * 8);
-        const int bytes = role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : kFU * 128 * 8);
+        const int bytes = role == 4 ? kRsQCols * 128 * 8 : role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : kFU * 128 * 8);
         const uint4* src = reinterpret_cast<const uint4*>(img);
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
@@ -598,6 +600,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         if (tid < 128) { const int a = tid >> 5, u = tid & 31, j = 32 * cta + u; cst[tid] = a < 3 ? p.v2[a * kRnn + j] : p.bhn2[j]; }
     } else if (role == 2) {     // v3 x 64 units
         if (tid < kFU) cst[tid] = p.v3[kFU * cta + tid];
+    } else if (role == 4) {     // fc3 bias of my 128 classes
+        if (tid < kRsQCols) cst[tid] = p.bfc3[kRsQCols * cta + tid];
     }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], NW);
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         };
         if (role == 0) {
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
-                if (t > 0) job(32u, kColD1, kW1, ctl_s + kBarD, false, 0, t, 9);                       // fc3 f2(t-1)
+                if (t > 0 && !raw) job(32u, kColD1, kW1, ctl_s + kBarD, false, 0, t, 9);               // fc3 f2(t-1)
                 if (t < S) job(96u, kColD0, kW0, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);    // W_hh1 h1(t)
             }
         } else if (role == 1) {
@@ -640,6 +644,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 job(96u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);                                  // W_ih2a h1(t)
                 job(96u, kColD1, kW1, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);               // W_hh2 h2(t)
             }
+        } else if (role == 4) {
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kRsQCols, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);   // fc3 slice f2(t)
         } else {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
         }
@@ -708,7 +714,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 float a[24], bn[8];
                 if (t < S) cs_wait(t);
                 if (t < S && L.wlive) load_rec24(csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs, a);
-                if (t > 0 && L.wlive) mol_noise(nz_s, sbias_s, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
+                if (raw && t == S) break;           // (RAW: the sampler CTAs draw the last sample; nothing is left to do here)
+                if (t > 0 && L.wlive && !raw) mol_noise(nz_s, sbias_s, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
                 if (t > 0) {
                     wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(t - 1) & 1u);      // recurrent job of step t-1: D0 complete, A free
                     tcgen05_fence_after();
@@ -730,7 +737,20 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     if (lane == 0) mbar_arrive_s(ctl_s + kBarE);
                 }
                 float x = 0.f;
-                if (t > 0) {
+                if (t > 0 && raw) {
+                    // RAW: the sample of step t-1 comes from the group's sampler CTAs as a tagged word (no matrix on this station's path)
+                    if (L.wlive) {
+                        long long t0 = 0;
+                        int spins = 0;
+                        unsigned long long w = ll_load(xw);
+                        while (ll_tag(w) != (uint32_t)t) {
+                            w = ll_load(xw);
+                            if (RS_SPIN_CHECK(255)) break;
+                        }
+                        x = ll_val(w);
+                    }
+                    trace<kTrace>(p, t, 4);
+                } else if (t > 0) {
                     ingest<kTrace>(p, ctl, ctl_s, L, MAT(MF2, t - 1), kTagS, GEN(t - 1), -1, t, 1, nullptr, 0u);
                     ctrace<kTrace>(p, t, 0);
                     wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)(t - 1) & 1u);
@@ -861,6 +881,127 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH2, t), kTagE, GEN(t), -1, t, 6, nullptr, 0u);
                 cs_release(t);
             }
+        } else if (role == 4) {
+            // ---- T5 (RAW): my 128 classes of fc3 on f2(t), the soft-max partials, and -- in the CTA whose classes contain the
+            // threshold -- the inverse-CDF draw (rule: oracle sample_raw; fatchord_version.py:224-230: first k with cdf[k] >= u, one
+            // Philox uniform per (step, fold)).  Thread (q, cs): fold 32 q + lane, classes 32 cs .. 32 cs + 31 of this CTA's 128.
+            // The four slices of a fold meet in shared memory ({max, sum} per slice), the CTAs of the group exchange {max, sum} of
+            // their 128 classes as tagged words (double-buffered by step parity), every CTA forms the same normaliser Z and
+            // threshold u Z, and exactly one thread finds the class.  The sample goes out as the tagged word T1, T2 and T3 wait for.
+            const int nq = p.n_samplers;
+            float* pm = reinterpret_cast<float*>(smem + kNoiseOfs);          // [4 slices][128 folds] max, then sums
+            float* ps = pm + 4 * 128;
+            const uint32_t bias_s = cst_s + 128u * L.cs;
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+                trace<kTrace>(p, t, 0);
+                const uint32_t tag = (uint32_t)t + 1u;
+                ingest<kTrace>(p, ctl, ctl_s, L, MAT(MF2, t), kTagS, GEN(t), -1, t, 1, nullptr, 0u);
+                wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
+                tcgen05_fence_after();
+                trace<kTrace>(p, t, 4);
+                if (L.wlive) {
+                    float l[32];
+                    tmem_ld8(L.tlane + kColD0 + 32 * L.cs, l); tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 8, l + 8);
+                    tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 16, l + 16); tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 24, l + 24);
+                    tmem_ld_wait();
+                    tcgen05_fence_before();
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = lds4(bias_s + 4u * i);
+                        l[i] += b4.x; l[i + 1] += b4.y; l[i + 2] += b4.z; l[i + 3] += b4.w;
+                        m = fmaxf(fmaxf(m, fmaxf(l[i], l[i + 1])), fmaxf(l[i + 2], l[i + 3]));
+                    }
+                    float ssum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ssum += ex2_ftz(kL2E * (l[i] - m));
+                    if (p.logits_out && L.live) {
+                        float* lo = p.logits_out + (srow + t) * p.C + kRsQCols * cta + 32 * L.cs;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) lo[i] = l[i];
+                    }
+                    pm[L.cs * 128 + L.row] = m;
+                    ps[L.cs * 128 + L.row] = ssum;
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + L.q) : "memory");       // the four slice warps of my lane quadrant
+                    float sm[4], ss[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { sm[c] = pm[c * 128 + L.row]; ss[c] = ps[c * 128 + L.row]; }
+                    const float mc = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+                    float sc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sc += ss[c] * ex2_ftz(kL2E * (sm[c] - mc));
+                    unsigned long long* pw = p.bP + ((((size_t)g * 2 + (t & 1)) * 128 + L.row_ld) * kRsMaxSamplers) * 2;
+                    if (L.cs == 0 && L.live) { ll_store(pw + 2 * cta, mc, tag); ll_store(pw + 2 * cta + 1, sc, tag); }
+                    float mq[kRsMaxSamplers], zq[kRsMaxSamplers];
+#pragma unroll
+                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                        mq[q2] = -INFINITY; zq[q2] = 0.f;
+                        if (q2 == cta) { mq[q2] = mc; zq[q2] = sc; }
+                        else if (q2 < nq) {
+                            long long t0 = 0;
+                            int spins = 0;
+                            while (true) {
+                                unsigned long long wa, wb;
+                                ll_load2(pw + 2 * q2, wa, wb);
+                                if (ll_tag(wa) == tag && ll_tag(wb) == tag) { mq[q2] = ll_val(wa); zq[q2] = ll_val(wb); break; }
+                                if (RS_SPIN_CHECK(255)) break;
+                            }
+                        }
+                    }
+                    float M = mq[0];
+#pragma unroll
+                    for (int q2 = 1; q2 < kRsMaxSamplers; ++q2) M = fmaxf(M, mq[q2]);
+                    float before = 0.f, Z = 0.f;                 // mass of the CTAs before mine, total mass (same order in every CTA)
+#pragma unroll
+                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                        if (q2 < nq) {
+                            if (q2 == cta) before = Z;
+                            Z += zq[q2] * ex2_ftz(kL2E * (mq[q2] - M));
+                        }
+                    }
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 0u), key);
+                    const float thr = u01(r.x) * Z;
+                    // owner CTA: the first whose cumulative mass reaches the threshold (the last one if rounding left the total short)
+                    float cum = 0.f;
+                    int qs = nq - 1;
+#pragma unroll
+                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                        if (q2 < nq) {
+                            cum += zq[q2] * ex2_ftz(kL2E * (mq[q2] - M));
+                            if (qs == nq - 1 && thr <= cum && q2 < nq - 1) qs = q2;
+                        }
+                    }
+                    if (qs == cta) {
+                        // owner slice inside the CTA: the first whose cumulative mass reaches the threshold (the last if none)
+                        float base = before;
+                        int cs_own = 3;
+                        float base_own = 0.f;
+                        bool found = false;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float e = ss[c] * ex2_ftz(kL2E * (sm[c] - M));
+                            if (!found && (thr <= base + e || c == 3)) { cs_own = c; base_own = base; found = true; }
+                            base += e;
+                        }
+                        if (cs_own == L.cs && L.live) {
+                            float acc = base_own;
+                            int k = 31;
+                            bool hit = false;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                acc += ex2_ftz(kL2E * (l[i] - M));
+                                if (!hit && acc >= thr) { k = i; hit = true; }
+                            }
+                            const float xs = 2.0f * (float)(kRsQCols * cta + 32 * L.cs + k) / ((float)p.C - 1.0f) - 1.0f;      // fatchord_version.py:228
+                            p.samples[srow + t] = xs;
+                            ll_store(xw, p.forced ? p.forced[srow + t] : xs, tag);
+                        }
+                    }
+                } else {
+                    tcgen05_fence_before();
+                }
+                trace<kTrace>(p, t, 5);
+            }
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
             const bool fc1 = role == 2;
@@ -948,7 +1089,7 @@ cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream) {
     if (err != cudaSuccess) return err;
     RsParams pp = p;
     void* args[] = {&pp};
-    const int grid = p.G * kRsCtas + (p.cs_done ? p.n_expanders : 0);
+    const int grid = p.G * p.ctas + (p.cs_done ? p.n_expanders : 0);
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, kSmemBytes, stream);
 }
 
