@@ -275,8 +275,8 @@ def main():
         return reference_arm(args, wl)
     _guard_stdout()
     if args.precision is None:      # defaults = what the facade's PREC_AUTO picks (fatchord_version.resolve_precision): pruned model ->
-        # block-sparse cluster loop; fewer than 24 folds in the call (cfg1: 19, cfg2: 1) -> fp32 loop; else the tensor-core loops
-        args.precision = "sparse" if wl in PRUNED else ("f32" if (not WORKLOADS[wl][3] or wl == "cfg1" or wl in TOPO) else "f16")
+        # block-sparse cluster loop; fewer than 8 folds in the call (cfg2: 1) and the two small topologies -> fp32 loops; else the tensor-core loops
+        args.precision = "sparse" if wl in PRUNED else ("f32" if (not WORKLOADS[wl][3] or wl in TOPO) else "f16")
 
     import torch
     import torch.distributed as dist
@@ -408,7 +408,7 @@ def main():
     def loop_block(mres, precision):
         lt = mres["last_t"]
         kern = lt.get("loop_kernel", "?")
-        n_exch = 8 if kern == "wrnn_loop_rr_kernel" else 4 if kern in ("wrnn_loop_rs_kernel", "wrnn_loop_gn_kernel") else (5 if (lt.get("precision") == _native.PREC_SPARSE_F32 or ctx["plan"][0] == "MOL") else 6)
+        n_exch = 8 if kern == "wrnn_loop_rr_kernel" else (6 if ctx["plan"][0] == "RAW" else 4) if kern == "wrnn_loop_rs_kernel" else 4 if kern == "wrnn_loop_gn_kernel" else (5 if (lt.get("precision") == _native.PREC_SPARSE_F32 or ctx["plan"][0] == "MOL") else 6)
         us = mres["loop_s"] * 1e6 / (lt["n_steps"] * max(1, lt["n_launches"]))
         fl = {"f32": floor["ll_us"], "f16": floor["counter_us"], "sparse": floor["cluster_us"]}[precision]
         return {"kernel": kern, "us_per_step": us, "folds": lt["n_folds"], "loop_steps": lt["n_steps"], "exchanges_per_step": n_exch,

@@ -403,20 +403,20 @@ class WaveRNN(object):
                                                                        gen_rate), end='', flush=True)
 
 
-AUTO_F16_MIN_FOLDS = 24
-AUTO_F16_MIN_FOLDS_MOL = 12
+AUTO_F16_MIN_FOLDS = 8
+AUTO_F16_MIN_FOLDS_MOL = 4
 AUTO_SPARSE_MIN = 0.8
 
 
 def resolve_precision(n_classes, sparsity, n_folds, sparse_available=True):
     """Which loop `PREC_AUTO` (the default of the `vocoder.inference` facade) runs, from what was measured on B200 (DESIGN.md
-    section 6): a pruned checkpoint whose compressed images fit one cluster -> the block-sparse cluster loop (62.9x vs 38.8x
-    real-time on cfg4; a pruned checkpoint that does NOT fit falls through to the dense loops -- its tensors are dense with
-    zeros, vocoder/pruner.py:55-58); a dense one with at least AUTO_F16_MIN_FOLDS folds in the call -> the fp16 tensor-core
-    loops (MOL up to 384 folds: loop_rs.cu, 18.7 us per step whatever the fold count; else loop_tc.cu); fewer folds -> the
-    fp32 loop, which is then the faster one AND bit-faithful (19 folds: 39.2x vs 36.2x; one fold: the only loop built for
-    it).  Measured crossover (tools/auto_crossover.py, us per step fp32 / fp16): 14 folds 21.2 / 28.7, 19 folds 26.3 / 29.2,
-    23 folds 27.7 / 29.0, 28 folds 30.6 / 29.0, 37 folds 42.7 / 29.8; MOL on loop_rs.cu crosses at ~12 folds.
+    sections 4.5, 6): a pruned checkpoint whose compressed images fit one cluster -> the block-sparse cluster loop (62.9x vs
+    38.8x real-time on cfg4; a pruned checkpoint that does NOT fit falls through to the dense loops -- its tensors are dense
+    with zeros, vocoder/pruner.py:55-58); a dense one with at least AUTO_F16_MIN_FOLDS folds in the call -> the fp16
+    tensor-core loops (up to 256 folds: the role-specialised loop_rs.cu, MOL and RAW; above: loop_tc.cu); fewer folds -> the
+    fp32 loop, which is then as fast AND bit-faithful (one fold: the only loop built for it).  Measured crossover, us per
+    step fp32 loop / loop_rs.cu (tools/auto_crossover_raw.py, RAW 9-bit): 2 folds 14.6 / 14.3, 5 folds 16.1 / 15.5, 9 folds
+    18.6 / 15.7, 13 folds 20.5 / 15.9, 19 folds 26.2 / 16.1; MOL on loop_rs.cu runs 10.6 us per step at 18 folds.
     The tensor-core loops exist for 30 (MOL), 512 and 1024 classes."""
     if sparsity >= AUTO_SPARSE_MIN and sparse_available:
         return _native.PREC_SPARSE_F32

@@ -264,7 +264,7 @@ def test_facade_default_precision_is_auto(mol):
     w = inference.infer_waveform(norm_mel(960, 1) * 4.0)                   # 12 s, the facade's own fold plan (3000 / 1500): 42 folds
     assert w.shape == ((960 - 1) * 200,) and np.isfinite(w).all()
     assert m.last_timings["n_folds"] >= 24 and m.last_timings["precision"] == _native.PREC_F16
-    inference.infer_waveform(norm_mel(160, 1) * 4.0)                       # 2 s: 7 folds
-    assert m.last_timings["n_folds"] < 24 and m.last_timings["precision"] == _native.PREC_F32
+    inference.infer_waveform(norm_mel(60, 1) * 4.0)                        # 0.75 s: 3 folds
+    assert m.last_timings["n_folds"] < 4 and m.last_timings["precision"] == _native.PREC_F32
     inference.infer_waveform(norm_mel(40, 1) * 4.0, batched=False)
     assert m.last_timings["precision"] == _native.PREC_F32

@@ -52,6 +52,37 @@ def test_rs_loop_config3_full_size_vs_oracle(target, overlap, folds):
     assert dict(model.last_timings)["n_folds"] == folds
 
 
+@pytest.mark.parametrize("bits,T,target,overlap,folds,steps", [(9, 800, 8000, 800, 19, 96), (10, 4800, 3000, 1500, 213, 64), (9, 4800, 6000, 1000, 137, 64)])
+def test_rs_loop_raw_vs_oracle(bits, T, target, overlap, folds, steps):
+    """RAW on the role-specialised loop (sampler CTAs: fc3 slices, soft-max partials exchanged between the CTAs, inverse-CDF draw):
+    BASELINE config 1 (9-bit, 10 s, 19 folds) and a 60 s utterance on the two config-3 fold plans (10-bit: the reference's default
+    bits, 8 sampler CTAs per group; 9-bit: 4) against the ORACLE teacher-forced on the kernel's samples."""
+    model, sd = make_model(seed=11, bits=bits, mode="RAW")
+    mel = norm_mel(T, 1)
+    out = _oracle_check(model, sd, "RAW", mel, target, overlap, steps, 9, "loop_rs RAW %d-bit %d/%d" % (bits, target, overlap))
+    assert out["samples"].shape[0] == folds
+    assert dict(model.last_timings)["loop_kernel"] == "wrnn_loop_rs_kernel"
+
+
+def test_rs_loop_raw_deterministic_groups_and_generate(monkeypatch):
+    """RAW: same samples run to run and with one / two groups; the public generate() returns the right length."""
+    model, _ = make_model(seed=11, bits=9, mode="RAW")
+    mel = norm_mel(400, 3)
+    a = model.generate_debug(mel, True, 700, 150, seed=4, max_steps=300, precision=F16)
+    b = model.generate_debug(mel, True, 700, 150, seed=4, max_steps=300, precision=F16)
+    np.testing.assert_array_equal(a["samples"], b["samples"])
+    assert a["samples"].shape[0] == 94
+    monkeypatch.setenv("WRNN_RS_GROUPS", "1")
+    c = model.generate_debug(mel, True, 700, 150, seed=4, max_steps=300, precision=F16)
+    np.testing.assert_array_equal(a["samples"], c["samples"])
+    monkeypatch.delenv("WRNN_RS_GROUPS")
+    model.precision = F16
+    model.seed = 3
+    w = model.generate(mel[None], True, 3000, 1500, True, True)
+    assert w.shape == ((400 - 1) * 200,) and w.dtype == np.float64 and np.isfinite(w).all()
+    assert dict(model.last_timings)["loop_kernel"] == "wrnn_loop_rs_kernel"
+
+
 def test_rs_loop_deterministic_and_ring_invisible(monkeypatch):
     """Same samples (a) run to run, (b) with the records expanded up front instead of through the ring, (c) with a ring so
     small that it wraps every 12 steps, (d) with one, two and three CTA groups."""
