@@ -61,6 +61,7 @@ struct RrDev {
 
 struct wrnn_engine {
     int device = 0, bits = 9, mode = 0, C = 512, Cpad = 512, CR = 4;
+    int rs_samplers = 0;         // RAW on the role-specialised loop: sampler CTAs per group (wrnn_finalize)
     int topology = 0;            // WRNN_TOPO_FATCHORD / WRNN_TOPO_RUNTIMERACER (wrnn_set_topology, before wrnn_finalize)
     RrDev rr;
     GnDev gn;
@@ -442,7 +443,7 @@ int wrnn_finalize(wrnn_engine* e) {
     //   T1 (GRU1, units 32c..32c+31): [W_hh1 rows gate*32+u (96)] [MOL: fc3 rows (30 of 32)]  T2 (GRU2): [W_ih2a (96)] [W_hh2 (96)]
     //   T3 (fc1, units 64c..64c+63): [fc1[:, :512] (64)]                                       T4 (fc2): [fc2[:, :512] (64)]
     //   T5 (RAW with 512 / 1024 classes: sampler CTAs): [fc3 rows 128c..128c+127]
-    const bool rs_raw = e->mode == WRNN_MODE_RAW && C % kRsQCols == 0 && C / kRsQCols >= 2 && C / kRsQCols <= kRsMaxSamplers;
+    const bool rs_raw = e->mode == WRNN_MODE_RAW && (C == 512 || C == 1024);          // 8 sampler CTAs with 64 / 128 classes each
     if (C == 30 || rs_raw) {
         auto put_tile = [&](unsigned char* tile, int nrows, int r, const float* src) {
             for (int kb = 0; kb < 8; ++kb)
@@ -479,11 +480,16 @@ int wrnn_finalize(wrnn_engine* e) {
             CU(cudaMemcpy(e->wRs[role].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
         }
         if (rs_raw) {
-            const int nq = C / kRsQCols;
-            const size_t img = (size_t)kRsQCols * 1024;
+            // sampler CTAs per group: classes / 128 (4 for 9 bits, 8 for 10) -- fewer, fatter samplers exchange fewer partials;
+            // WRNN_RS_QCOLS=64 builds 8 x 64 for 9 bits (measured below)
+            int qc = 128;
+            if (const char* ev = getenv("WRNN_RS_QCOLS")) qc = (atoi(ev) == 64 && C == 512) ? 64 : 128;
+            const int nq = C / qc;
+            e->rs_samplers = nq;
+            const size_t img = (size_t)qc * 1024;
             std::vector<unsigned char> hw((size_t)nq * img, 0);
             for (int c = 0; c < nq; ++c)
-                for (int k = 0; k < kRsQCols; ++k) put_tile(hw.data() + (size_t)c * img, kRsQCols, k, f3w->data.data() + (size_t)(kRsQCols * c + k) * H);
+                for (int k = 0; k < qc; ++k) put_tile(hw.data() + (size_t)c * img, qc, k, f3w->data.data() + (size_t)(qc * c + k) * H);
             CU(e->wRs[4].ensure(hw.size()));
             CU(cudaMemcpy(e->wRs[4].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
         }
@@ -955,7 +961,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     float ms_expand = 0.f;
     const int wave = is_rr ? kRrMaxFolds : is_gn ? kGnMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
     // role-specialised loop: as many 48-CTA groups as the device holds; WRNN_RS=0 keeps loop_tc.cu for every fold count
-    const int rs_samplers = (e->mode == WRNN_MODE_RAW && e->wRs[4].p) ? e->C / kRsQCols : 0;     // RAW: sampler CTAs per group
+    const int rs_samplers = (e->mode == WRNN_MODE_RAW && e->wRs[4].p) ? e->rs_samplers : 0;      // RAW: sampler CTAs per group
     const int rs_ctas = kRsCtas + rs_samplers;
     const int rs_groups_max = std::max(0, e->n_sms / rs_ctas);
     const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
@@ -1099,7 +1105,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.bX = reinterpret_cast<unsigned long long*>(e->bRsExch.as<unsigned char>() + xbytes);
             rp.bP = rp.bX + (size_t)G * 128;
             rp.w5 = e->wRs[4].as<unsigned char>();
-            rp.mode = e->mode; rp.C = e->C; rp.n_samplers = rs_samplers; rp.ctas = rs_ctas;
+            rp.mode = e->mode; rp.C = e->C; rp.n_samplers = rs_samplers; rp.ctas = rs_ctas; rp.qcols = rs_samplers ? e->C / rs_samplers : 0;
             rp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
             rp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
             rp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;

@@ -116,15 +116,15 @@ cudaError_t launch_expand_cond(const float4* TA1, const float4* TA2, const float
 #endif
 constexpr int kRsT1 = 16, kRsT2 = 16, kRsT3 = WRNN_RS_FC_CTAS, kRsT4 = WRNN_RS_FC_CTAS;     // CTAs per role: GRU1 (+fc3 + draw), GRU2, fc1, fc2
 constexpr int kRsCtas = kRsT1 + kRsT2 + kRsT3 + kRsT4;          // one group (MOL); RAW adds n_samplers sampler CTAs (T5) per group
-constexpr int kRsQCols = 128;                                   // classes per RAW sampler CTA (512 classes: 4 CTAs, 1024: 8)
-constexpr int kRsMaxSamplers = 8;
+constexpr int kRsMaxSamplers = 8;                               // RAW: sampler CTAs per group; each holds C / 8 classes of fc3 (64 or 128)
 constexpr int kRsBufs = 2;                                      // exchange matrices are double-buffered by step parity
 constexpr int kRsMaxFoldsPerGroup = 128;
 constexpr int kRsChunk = 4;                                     // steps per chunk of conditioning records (granularity of the ring's counters)
 struct RsParams {
     const unsigned char *w1, *w2, *w3, *w4;   // per-role weight images [CTA][loop_rs_image_bytes(role)], shared-memory layout
     const unsigned char* w5;     // RAW: sampler images [n_samplers][128 classes of fc3 as an N = 128 tile]
-    int mode, C, n_samplers;     // WRNN_MODE_*; classes; RAW: sampler CTAs per group (C / 128), MOL: 0
+    int mode, C, n_samplers;     // WRNN_MODE_*; classes; RAW: sampler CTAs per group (8), MOL: 0
+    int qcols;                   // RAW: classes per sampler CTA = C / n_samplers (64 or 128)
     int ctas;                    // CTAs per group = kRsCtas + n_samplers
     unsigned long long* bP;      // RAW: soft-max partials {max, sum} as tagged words [G][2 (step parity)][128 folds][n_samplers][2]
     const float *v1, *v2, *v3, *bhn1, *bhn2, *bfc3;

@@ -517,6 +517,169 @@ __device__ __forceinline__ void expand_item_rs(const float4* __restrict__ TA1, c
     }
 }
 
+// The RAW sampler role (T5).  Thread (q, cs): fold 32 q + lane, classes kCls cs .. kCls cs + kCls - 1 of this CTA's 4 kCls.
+// The four slices of a fold meet in shared memory ({max, sum} per slice), the CTAs of the group exchange {max, sum} of their
+// classes as tagged words (double-buffered by step parity), every CTA forms the same normaliser Z and threshold u Z, and exactly
+// one thread finds the class: the sample goes out as the tagged word T1, T2 and T3 wait for.  The station is bound by the
+// special-function unit, so every class is exponentiated ONCE (against its slice's maximum; rescaled by one factor per slice
+// afterwards) and the uniform is drawn before the wait.
+template <bool kTrace, int kCls>
+__device__ __forceinline__ void sampler_role(const RsParams& p, Ctl* ctl, uint32_t ctl_s, uint8_t* smem, uint32_t cst_s, const Lane& L, uint4* X, int g,
+                                             int cta, int S, const FoldDesc& fd, size_t srow, unsigned long long* xw, uint2 key) {
+#define MAT(m, t) (X + ((size_t)(m) * kRsBufs + ((t) & (kRsBufs - 1))) * kMatChunks)
+#define GEN(t) ((((t) / kRsBufs) & 1) != 0)
+    constexpr int kQC = 4 * kCls;                                        // classes of this CTA
+    const int nq = p.n_samplers;
+    float* pm = reinterpret_cast<float*>(smem + kNoiseOfs);          // [4 slices][128 folds] max, then sums
+    float* ps = pm + 4 * 128;
+    const uint32_t bias_s = cst_s + 4u * kCls * L.cs;
+    for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
+        trace<kTrace>(p, t, 0);
+        const uint32_t tag = (uint32_t)t + 1u;
+        const float u = u01(philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 0u), key).x);      // (before the wait)
+        ingest<kTrace>(p, ctl, ctl_s, L, MAT(MF2, t), kTagS, GEN(t), -1, t, 1, nullptr, 0u);
+        wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
+        tcgen05_fence_after();
+        trace<kTrace>(p, t, 4);
+        ctrace<kTrace>(p, t, 0);
+        if (L.wlive) {
+            float l[kCls];
+#pragma unroll
+            for (int i = 0; i < kCls; i += 8) tmem_ld8(L.tlane + kColD0 + kCls * L.cs + i, l + i);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            ctrace<kTrace>(p, t, 1);
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kCls; i += 4) {
+                const float4 b4 = lds4(bias_s + 4u * i);
+                l[i] += b4.x; l[i + 1] += b4.y; l[i + 2] += b4.z; l[i + 3] += b4.w;
+                m = fmaxf(fmaxf(m, fmaxf(l[i], l[i + 1])), fmaxf(l[i + 2], l[i + 3]));
+            }
+            if (p.logits_out && L.live) {
+                float* lo = p.logits_out + (srow + t) * p.C + kQC * cta + kCls * L.cs;
+#pragma unroll
+                for (int i = 0; i < kCls; ++i) lo[i] = l[i];
+            }
+            float ssum = 0.f;
+#pragma unroll
+            for (int i = 0; i < kCls; ++i) { l[i] = ex2_ftz(kL2E * (l[i] - m)); ssum += l[i]; }      // l[] = exp(logit - slice max) from here on
+            pm[L.cs * 128 + L.row] = m;
+            ps[L.cs * 128 + L.row] = ssum;
+            ctrace<kTrace>(p, t, 2);
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + L.q) : "memory");       // the four slice warps of my lane quadrant
+            ctrace<kTrace>(p, t, 3);
+            float sm[4], ss[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { sm[c] = pm[c * 128 + L.row]; ss[c] = ps[c * 128 + L.row]; }
+            const float mc = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+            float sc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { ss[c] *= ex2_ftz(kL2E * (sm[c] - mc)); sc += ss[c]; }       // slice masses against the CTA's maximum
+            // ONE warp per lane quadrant (slice 0) talks to the other CTAs: it publishes this CTA's {max, sum} (one 16-byte word with
+            // the step tag in both upper halves), gathers the others', forms the global maximum M, the normaliser Z, the threshold
+            // u Z, the owner CTA and -- if that is this CTA -- the owner slice, and leaves the verdict in shared memory; the other
+            // three slice warps sleep on the quadrant's barrier meanwhile (16 warps polling the same 16 KB of words from 16 CTAs
+            // delayed the words themselves: 2-3 us per step, measured).
+            float* vd = ps + 4 * 128;                                    // verdict [4][128 folds]: owner slice (or -1), its base mass, M, threshold
+            if (L.cs == 0) {
+                uint4* pw = reinterpret_cast<uint4*>(p.bP) + (((size_t)g * 2 + (t & 1)) * 128 + L.row_ld) * kRsMaxSamplers;
+                if (L.live) st_chunk(pw + cta, make_uint4(__float_as_uint(mc), tag, __float_as_uint(sc), tag));
+                ctrace<kTrace>(p, t, 4);
+                float mq[kRsMaxSamplers], zq[kRsMaxSamplers];
+                uint32_t pend = 0u;
+#pragma unroll
+                for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                    mq[q2] = -INFINITY; zq[q2] = 0.f;
+                    if (q2 == cta) { mq[q2] = mc; zq[q2] = sc; }
+                    else if (q2 < nq) pend |= 1u << q2;
+                }
+                {   // every pass requests ALL the missing partials at once (a pass is one L2 round trip; one after the other cost a
+                    // round trip EACH, because the first requests always leave before the other CTAs have published)
+                    long long t0 = 0;
+                    int spins = 0;
+                    while (pend) {
+                        uint4 w[kRsMaxSamplers];
+#pragma unroll
+                        for (int q2 = 0; q2 < kRsMaxSamplers; ++q2)
+                            if ((pend >> q2) & 1u) w[q2] = ld_chunk(pw + q2);
+#pragma unroll
+                        for (int q2 = 0; q2 < kRsMaxSamplers; ++q2)
+                            if (((pend >> q2) & 1u) && w[q2].y == tag && w[q2].w == tag) {
+                                mq[q2] = __uint_as_float(w[q2].x); zq[q2] = __uint_as_float(w[q2].z);
+                                pend &= ~(1u << q2);
+                            }
+                        if (pend && RS_SPIN_CHECK(255)) break;
+                    }
+                }
+                ctrace<kTrace>(p, t, 5);
+                float M = mq[0];
+#pragma unroll
+                for (int q2 = 1; q2 < kRsMaxSamplers; ++q2) M = fmaxf(M, mq[q2]);
+                // masses against the global maximum (same order and arithmetic in every CTA); owner CTA = the first whose cumulative
+                // mass reaches the threshold (the last one if rounding left the total short)
+                float before = 0.f, Z = 0.f;
+#pragma unroll
+                for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                    if (q2 < nq) {
+                        zq[q2] *= ex2_ftz(kL2E * (mq[q2] - M));
+                        if (q2 == cta) before = Z;
+                        Z += zq[q2];
+                    }
+                }
+                const float thr = u * Z;
+                float cum = 0.f;
+                int qs = nq - 1;
+                bool got = false;
+#pragma unroll
+                for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
+                    if (q2 < nq) {
+                        cum += zq[q2];
+                        if (!got && thr <= cum) { qs = q2; got = true; }
+                    }
+                }
+                int cs_own = -1;
+                float base_own = 0.f;
+                if (qs == cta) {        // owner slice inside the CTA: the first whose cumulative mass reaches the threshold (the last if none)
+                    const float fc = ex2_ftz(kL2E * (mc - M));
+                    float base = before;
+                    bool found = false;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float e = ss[c] * fc;
+                        if (!found && (thr <= base + e || c == 3)) { cs_own = c; base_own = base; found = true; }
+                        base += e;
+                    }
+                }
+                vd[0 * 128 + L.row] = __int_as_float(cs_own); vd[1 * 128 + L.row] = base_own; vd[2 * 128 + L.row] = M; vd[3 * 128 + L.row] = thr;
+            }
+            ctrace<kTrace>(p, t, 6);
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + L.q) : "memory");
+            if (__float_as_int(vd[0 * 128 + L.row]) == L.cs && L.live) {
+                const float base_own = vd[1 * 128 + L.row], M = vd[2 * 128 + L.row], thr = vd[3 * 128 + L.row];
+                const float fs = ex2_ftz(kL2E * (m - M));
+                float acc = base_own;
+                int k = kCls - 1;
+                bool hit = false;
+#pragma unroll
+                for (int i = 0; i < kCls; ++i) {
+                    acc = fmaf(l[i], fs, acc);
+                    if (!hit && acc >= thr) { k = i; hit = true; }
+                }
+                const float xs = 2.0f * (float)(kQC * cta + kCls * L.cs + k) / ((float)p.C - 1.0f) - 1.0f;      // fatchord_version.py:228
+                p.samples[srow + t] = xs;
+                ll_store(xw, p.forced ? p.forced[srow + t] : xs, tag);
+            }
+        } else {
+            tcgen05_fence_before();
+        }
+        trace<kTrace>(p, t, 5);
+        ctrace<kTrace>(p, t, 7);
+    }
+#undef MAT
+#undef GEN
+}
+
 }  // namespace
 
 template <bool kTrace>
@@ -583,11 +746,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
 
     // ---- one-time setup: weight tiles, constants, barriers, TMEM ------------------------------------------------------
     {
-        const unsigned char* img = role == 4 ? p.w5 + (size_t)cta * (kRsQCols * 128 * 8)
+        const unsigned char* img = role == 4 ? p.w5 + (size_t)cta * ((size_t)p.qcols * 128 * 8)
                                  : role == 0 ? p.w1 + (size_t)cta * (kW1 + 32 * 128 * 8)
                                  : role == 1 ? p.w2 + (size_t)cta * kWEnd
                                  : role == 2 ? p.w3 + (size_t)cta * (kFU * 128 * 8) : p.w4 + (size_t)cta * (kFU * 128 * 8);
-        const int bytes = role == 4 ? kRsQCols * 128 * 8 : role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : kFU * 128 * 8);
+        const int bytes = role == 4 ? p.qcols * 128 * 8 : role == 0 ? kW1 + 32 * 128 * 8 : (role == 1 ? kWEnd : kFU * 128 * 8);
         const uint4* src = reinterpret_cast<const uint4*>(img);
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
@@ -601,7 +764,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     } else if (role == 2) {     // v3 x 64 units
         if (tid < kFU) cst[tid] = p.v3[kFU * cta + tid];
     } else if (role == 4) {     // fc3 bias of my 128 classes
-        if (tid < kRsQCols) cst[tid] = p.bfc3[kRsQCols * cta + tid];
+        if (tid < p.qcols) cst[tid] = p.bfc3[p.qcols * cta + tid];
     }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], NW);
@@ -645,7 +808,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 job(96u, kColD1, kW1, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);               // W_hh2 h2(t)
             }
         } else if (role == 4) {
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kRsQCols, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);   // fc3 slice f2(t)
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)p.qcols, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);   // fc3 slice f2(t)
         } else {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
         }
@@ -882,126 +1045,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 cs_release(t);
             }
         } else if (role == 4) {
-            // ---- T5 (RAW): my 128 classes of fc3 on f2(t), the soft-max partials, and -- in the CTA whose classes contain the
-            // threshold -- the inverse-CDF draw (rule: oracle sample_raw; fatchord_version.py:224-230: first k with cdf[k] >= u, one
-            // Philox uniform per (step, fold)).  Thread (q, cs): fold 32 q + lane, classes 32 cs .. 32 cs + 31 of this CTA's 128.
-            // The four slices of a fold meet in shared memory ({max, sum} per slice), the CTAs of the group exchange {max, sum} of
-            // their 128 classes as tagged words (double-buffered by step parity), every CTA forms the same normaliser Z and
-            // threshold u Z, and exactly one thread finds the class.  The sample goes out as the tagged word T1, T2 and T3 wait for.
-            const int nq = p.n_samplers;
-            float* pm = reinterpret_cast<float*>(smem + kNoiseOfs);          // [4 slices][128 folds] max, then sums
-            float* ps = pm + 4 * 128;
-            const uint32_t bias_s = cst_s + 128u * L.cs;
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                trace<kTrace>(p, t, 0);
-                const uint32_t tag = (uint32_t)t + 1u;
-                ingest<kTrace>(p, ctl, ctl_s, L, MAT(MF2, t), kTagS, GEN(t), -1, t, 1, nullptr, 0u);
-                wait_mbar<true>(p, ctl, ctl_s + kBarD, (uint32_t)t & 1u);
-                tcgen05_fence_after();
-                trace<kTrace>(p, t, 4);
-                if (L.wlive) {
-                    float l[32];
-                    tmem_ld8(L.tlane + kColD0 + 32 * L.cs, l); tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 8, l + 8);
-                    tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 16, l + 16); tmem_ld8(L.tlane + kColD0 + 32 * L.cs + 24, l + 24);
-                    tmem_ld_wait();
-                    tcgen05_fence_before();
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = lds4(bias_s + 4u * i);
-                        l[i] += b4.x; l[i + 1] += b4.y; l[i + 2] += b4.z; l[i + 3] += b4.w;
-                        m = fmaxf(fmaxf(m, fmaxf(l[i], l[i + 1])), fmaxf(l[i + 2], l[i + 3]));
-                    }
-                    float ssum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) ssum += ex2_ftz(kL2E * (l[i] - m));
-                    if (p.logits_out && L.live) {
-                        float* lo = p.logits_out + (srow + t) * p.C + kRsQCols * cta + 32 * L.cs;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) lo[i] = l[i];
-                    }
-                    pm[L.cs * 128 + L.row] = m;
-                    ps[L.cs * 128 + L.row] = ssum;
-                    asm volatile("bar.sync %0, 128;" ::"r"(3 + L.q) : "memory");       // the four slice warps of my lane quadrant
-                    float sm[4], ss[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) { sm[c] = pm[c * 128 + L.row]; ss[c] = ps[c * 128 + L.row]; }
-                    const float mc = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
-                    float sc = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) sc += ss[c] * ex2_ftz(kL2E * (sm[c] - mc));
-                    unsigned long long* pw = p.bP + ((((size_t)g * 2 + (t & 1)) * 128 + L.row_ld) * kRsMaxSamplers) * 2;
-                    if (L.cs == 0 && L.live) { ll_store(pw + 2 * cta, mc, tag); ll_store(pw + 2 * cta + 1, sc, tag); }
-                    float mq[kRsMaxSamplers], zq[kRsMaxSamplers];
-#pragma unroll
-                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
-                        mq[q2] = -INFINITY; zq[q2] = 0.f;
-                        if (q2 == cta) { mq[q2] = mc; zq[q2] = sc; }
-                        else if (q2 < nq) {
-                            long long t0 = 0;
-                            int spins = 0;
-                            while (true) {
-                                unsigned long long wa, wb;
-                                ll_load2(pw + 2 * q2, wa, wb);
-                                if (ll_tag(wa) == tag && ll_tag(wb) == tag) { mq[q2] = ll_val(wa); zq[q2] = ll_val(wb); break; }
-                                if (RS_SPIN_CHECK(255)) break;
-                            }
-                        }
-                    }
-                    float M = mq[0];
-#pragma unroll
-                    for (int q2 = 1; q2 < kRsMaxSamplers; ++q2) M = fmaxf(M, mq[q2]);
-                    float before = 0.f, Z = 0.f;                 // mass of the CTAs before mine, total mass (same order in every CTA)
-#pragma unroll
-                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
-                        if (q2 < nq) {
-                            if (q2 == cta) before = Z;
-                            Z += zq[q2] * ex2_ftz(kL2E * (mq[q2] - M));
-                        }
-                    }
-                    const uint4 r = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)fd.fold, (uint32_t)fd.utt, 0u), key);
-                    const float thr = u01(r.x) * Z;
-                    // owner CTA: the first whose cumulative mass reaches the threshold (the last one if rounding left the total short)
-                    float cum = 0.f;
-                    int qs = nq - 1;
-#pragma unroll
-                    for (int q2 = 0; q2 < kRsMaxSamplers; ++q2) {
-                        if (q2 < nq) {
-                            cum += zq[q2] * ex2_ftz(kL2E * (mq[q2] - M));
-                            if (qs == nq - 1 && thr <= cum && q2 < nq - 1) qs = q2;
-                        }
-                    }
-                    if (qs == cta) {
-                        // owner slice inside the CTA: the first whose cumulative mass reaches the threshold (the last if none)
-                        float base = before;
-                        int cs_own = 3;
-                        float base_own = 0.f;
-                        bool found = false;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float e = ss[c] * ex2_ftz(kL2E * (sm[c] - M));
-                            if (!found && (thr <= base + e || c == 3)) { cs_own = c; base_own = base; found = true; }
-                            base += e;
-                        }
-                        if (cs_own == L.cs && L.live) {
-                            float acc = base_own;
-                            int k = 31;
-                            bool hit = false;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                acc += ex2_ftz(kL2E * (l[i] - M));
-                                if (!hit && acc >= thr) { k = i; hit = true; }
-                            }
-                            const float xs = 2.0f * (float)(kRsQCols * cta + 32 * L.cs + k) / ((float)p.C - 1.0f) - 1.0f;      // fatchord_version.py:228
-                            p.samples[srow + t] = xs;
-                            ll_store(xw, p.forced ? p.forced[srow + t] : xs, tag);
-                        }
-                    }
-                } else {
-                    tcgen05_fence_before();
-                }
-                trace<kTrace>(p, t, 5);
-            }
+            // ---- T5 (RAW): my slice of fc3 (p.qcols = 64 or 128 classes) on f2(t), the soft-max partials, and -- in the CTA whose
+            // classes contain the threshold -- the inverse-CDF draw (rule: oracle sample_raw; fatchord_version.py:224-230: first k
+            // with cdf[k] >= u, one Philox uniform per (step, fold)).
+            if (p.qcols == 64) sampler_role<kTrace, 16>(p, ctl, ctl_s, smem, cst_s, L, X, g, cta, S, fd, srow, xw, key);
+            else sampler_role<kTrace, 32>(p, ctl, ctl_s, smem, cst_s, L, X, g, cta, S, fd, srow, xw, key);
         } else {
             // ---- T3 / T4: fc1 on s2(t) (+ the sample's rank-1 term) / fc2 on f1(t); ReLU; publish ------------------------------
             const bool fc1 = role == 2;

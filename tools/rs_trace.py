@@ -14,20 +14,21 @@ if not os.path.exists(path) or os.environ.get("RS_TRACE_RUN"):
                    stdout=subprocess.DEVNULL, check=True)
 rows = np.loadtxt(path, dtype=np.int64)
 ncta = rows[:, 0].max() + 1
+NC = int(os.environ.get("RS_CTAS", "48"))
 ev = rows[:, 2:].reshape(ncta, 8, 48).astype(np.float64)
 ev[ev == 0] = np.nan
-names = {0: "T1 GRU1+fc3", 1: "T2 GRU2", 2: "T3 fc1", 3: "T4 fc2"}
+names = {0: "T1 GRU1+fc3", 1: "T2 GRU2", 2: "T3 fc1", 3: "T4 fc2", 4: "T5 sampler"}
 evn = ["step top", "in1 canaries", "in1 loaded", "in1 in TMEM", "MMA done", "published", "in2 canaries", "in2 loaded", "in2 in TMEM",
        "mma1 first kq", "mma1 last kq", "mma2 first kq", "mma2 last kq"]
 def passes(cs, k):
     a, b = ev[cs, k, 13], ev[cs, k, 14]
     return " | passes in1 %s in2 %s" % (np.nanmax(a) if not np.all(np.isnan(a)) else "-", np.nanmax(b) if not np.all(np.isnan(b)) else "-")
 def role_of(c):
-    r = c % 48
-    return 0 if r < 16 else (1 if r < 32 else (2 if r < 40 else 3))
-G = ncta // 48
+    r = c % NC
+    return 0 if r < 16 else (1 if r < 32 else (2 if r < 40 else (3 if r < 48 else 4)))
+G = ncta // NC
 for g in range(min(G, 1)):
-    ctas = np.arange(g * 48, (g + 1) * 48)
+    ctas = np.arange(g * NC, (g + 1) * NC)
     roles = np.array([role_of(c) for c in ctas])
     # chain origin of step k: last T4 publish of step k-1 (event 5)
     t4 = ctas[roles == 3]
@@ -35,7 +36,7 @@ for g in range(min(G, 1)):
     for k in range(1, 8):
         origin = np.nanmax(ev[t4, k - 1, 5])
         line = "  step +%d (chain origin = last f2 publish): " % k
-        for r in range(4):
+        for r in range(5 if NC > 48 else 4):
             cs = ctas[roles == r]
             line += "\n    %-12s" % names[r]
             for j in range(13):
