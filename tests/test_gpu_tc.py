@@ -12,6 +12,13 @@ def model():
     return make_model(seed=11, bits=9, mode="RAW")[0]
 
 
+@pytest.fixture(autouse=True)
+def _large_fold_loop(monkeypatch):
+    """This file tests loop_tc.cu (what calls with more than 256 folds run on) at every size: keep the role-specialised loop out
+    (tests/test_gpu_rs.py covers it, MOL and RAW)."""
+    monkeypatch.setenv("WRNN_RS", "0")
+
+
 @pytest.mark.parametrize("N", [16, 32, 64])
 def test_tc_gemm_self_test(model, N):
     rng = np.random.default_rng(N)
