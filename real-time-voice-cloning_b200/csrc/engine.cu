@@ -88,6 +88,7 @@ struct wrnn_engine {
     DevBuf bPostUtt, bFade, bScratch, bWav, bFloor, bCsDone;
     DevBuf wTc, wTcS, bTcExch, bCS;
     DevBuf wTc2;                // cluster-local tensor-core loop (MOL): 16 per-CTA weight tile streams
+    DevBuf wRsX[3], bFR, bM16, bRsPlace;  // inline conditioning of the role-specialised loop: W_q tiles per role, per-frame rows, upsampled mel (fp16)
     DevBuf wRs[5], bRsExch;     // role-specialised tensor-core loop: per-role weight images ([4]: RAW sampler CTAs), exchange matrices + sample words
     DevBuf wSp[2];              // block-sparse cluster loop: per-CTA compressed images for cluster sizes 16 and 8
     int spStride[2] = {0, 0};
@@ -235,7 +236,7 @@ int wrnn_destroy(wrnn_engine* e) {
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->wLoop, &e->wCond, &e->bMel, &e->bUtt, &e->bX0, &e->bMP, &e->bH[0], &e->bH[1], &e->bH[2], &e->bAux,
                       &e->bTA1, &e->bTA2, &e->bTQ1, &e->bTQ2, &e->bFolds, &e->bExch, &e->bSamples, &e->bLogits, &e->bForced,
-                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2, &e->wRs[0], &e->wRs[1], &e->wRs[2], &e->wRs[3], &e->wRs[4], &e->bRsExch};
+                      &e->bPostUtt, &e->bFade, &e->bScratch, &e->bWav, &e->bFloor, &e->bCsDone, &e->wTc, &e->wTcS, &e->bTcExch, &e->bCS, &e->wCondTc, &e->bCondH, &e->wSp[0], &e->wSp[1], &e->wTc2, &e->wRs[0], &e->wRs[1], &e->wRs[2], &e->wRs[3], &e->wRs[4], &e->bRsExch, &e->wRsX[0], &e->wRsX[1], &e->wRsX[2], &e->bFR, &e->bM16, &e->bRsPlace};
     for (DevBuf* b : bufs) b->release();
     if (e->dAbort) cudaFree(e->dAbort);
     if (e->hProgress) cudaFreeHost(e->hProgress);
@@ -478,6 +479,35 @@ int wrnn_finalize(wrnn_engine* e) {
             }
             CU(e->wRs[role].ensure(hw.size()));
             CU(cudaMemcpy(e->wRs[role].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+        }
+        // inline conditioning: the mel columns (1..80) of the folded input-side matrices P1 / P2 / P3 as fp16 tiles
+        // [k-block 2][rows][128 B] (k-block 0: mel 0..63, k-block 1: mel 64..79 in the first two 16-byte columns).
+        // T1's tile has 128 rows -- r, z, 32 zero rows, n -- so that the candidate's input side lands next to W_hn h, not on it.
+        {
+            auto put_x = [&](unsigned char* tile, int nrows, int r, const double* src) {
+                for (int k = 0; k < kFeat; ++k) {
+                    const int kb = k >> 6, c = (k & 63) >> 3;
+                    reinterpret_cast<__half*>(tile + (size_t)kb * nrows * 128 + r * 128 + ((c ^ (r & 7)) << 4))[k & 7] = __float2half_rn((float)src[k]);
+                }
+            };
+            for (int role = 0; role < 3; ++role) {
+                const size_t img = loop_rs_ximage_bytes(role);
+                std::vector<unsigned char> hw((size_t)nct[role] * img, 0);
+                for (int c = 0; c < nct[role]; ++c) {
+                    unsigned char* t0 = hw.data() + (size_t)c * img;
+                    if (role < 2) {
+                        const std::vector<double>& P = role == 0 ? P1 : P2;
+                        for (int u = 0; u < 32; ++u)
+                            for (int gt = 0; gt < 3; ++gt)
+                                put_x(t0, role == 0 ? 128 : 96, (role == 0 && gt == 2 ? 96 : 32 * gt) + u, &P[(size_t)(gt * H + 32 * c + u) * 113 + 1]);
+                    } else {
+                        const int FU = H / kRsT3;
+                        for (int u = 0; u < FU; ++u) put_x(t0, FU, u, &P3[(size_t)(FU * c + u) * 113 + 1]);
+                    }
+                }
+                CU(e->wRsX[role].ensure(hw.size()));
+                CU(cudaMemcpy(e->wRsX[role].p, hw.data(), hw.size(), cudaMemcpyHostToDevice));
+            }
         }
         if (rs_raw) {
             // sampler CTAs per group: classes / 128 (4 for 9 bits, 8 for 10) -- fewer, fatter samplers exchange fewer partials;
@@ -965,6 +995,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     const int rs_ctas = kRsCtas + rs_samplers;
     const int rs_groups_max = std::max(0, e->n_sms / rs_ctas);
     const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
+    bool rs_tables = false;
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);
         CU(cudaMemsetAsync(e->dAbort, 0, sizeof(int), st));
@@ -1048,7 +1079,10 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
         } else if (use_tc && (e->mode == WRNN_MODE_MOL || rs_samplers > 0) && e->wRs[0].p && B <= rs_max_folds) {
             // ---- role-specialised tensor-core loop (loop_rs.cu): the latency-bound regime, <= 128 folds per 48-CTA group ---------
             // groups: two leave 52 SMs to the expanders (three groups run the loop 4 % faster but starve them)
-            int G = std::min(std::min(rs_groups_max, 2), std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
+            // inline conditioning (default; WRNN_RS_INLINE=0: records from expander CTAs): no per-sample records at all -- the aux share is
+            // a per-frame row, the mel share one more K = 80 slab of the on-path MMAs -- so every SM can belong to a group
+            const bool inl = e->wRsX[0].p && !(getenv("WRNN_RS_INLINE") && atoi(getenv("WRNN_RS_INLINE")) == 0);
+            int G = std::min(std::min(rs_groups_max, inl ? 3 : 2), std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
             G = std::max(G, (B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup);
             if (const char* ev = getenv("WRNN_RS_GROUPS")) G = std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, std::min(rs_groups_max, atoi(ev)));
             const int Ng = (B + G - 1) / G;
@@ -1057,7 +1091,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             // counters per chunk of kRsChunk steps order the two sides.  WRNN_RS_EXPAND=0 (or no SM left): the whole table is
             // expanded before the launch.
             const int n_exp = e->n_sms - G * rs_ctas;
-            const bool ring = n_exp >= 1 && !(getenv("WRNN_RS_EXPAND") && atoi(getenv("WRNN_RS_EXPAND")) == 0);
+            const bool ring = !inl && n_exp >= 1 && !(getenv("WRNN_RS_EXPAND") && atoi(getenv("WRNN_RS_EXPAND")) == 0);
             const int nchunks = (S + kRsChunk - 1) / kRsChunk;
             int cs_steps = nchunks * kRsChunk;
             if (ring) {
@@ -1066,13 +1100,22 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 const int ring_chunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(3, budget / chunk_bytes));
                 cs_steps = ring_chunks * kRsChunk;
             }
-            const size_t cs_bytes = (size_t)G * cs_steps * Ng * 4096 * sizeof(float);
+            const size_t cs_bytes = inl ? 0 : (size_t)G * cs_steps * Ng * 4096 * sizeof(float);
             if (cs_bytes > ((size_t)96 << 30)) return fail(e, WRNN_ERR_INVALID, "per-sample conditioning table would exceed 96 GiB");
-            CU(e->bCS.ensure(cs_bytes));
+            if (!inl) CU(e->bCS.ensure(cs_bytes));
             CU(e->bCsDone.ensure((size_t)2 * nchunks * sizeof(unsigned int)));
             CU(cudaMemsetAsync(e->bCsDone.p, 0, (size_t)2 * nchunks * sizeof(unsigned int), st));
             CU(cudaEventRecord(e->evx[0], st));
-            if (!ring)
+            if (inl) {
+                if (!rs_tables) {      // once per call (the waves of a long batch share them)
+                    CU(e->bFR.ensure((size_t)ta_rows * 4096 * sizeof(float)));
+                    CU(e->bM16.ensure(((size_t)tq_rows * kHop + 16) * kFeat * sizeof(__half)));
+                    CU(launch_rs_inline_tables(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bMel.as<float>(), e->bUtt.as<UttDesc>(), n_utts, e->dcoef,
+                                               ta_rows, e->bFR.as<float>(), e->bM16.as<__half>(), st));
+                    rs_tables = true;
+                    e->launches += 1;
+                }
+            } else if (!ring)
                 CU(launch_expand_cond_rs(e->bTA1.as<float4>(), e->bTA2.as<float4>(), e->bTQ1.as<float4>(), e->bTQ2.as<float4>(), e->dcoef,
                                          e->bFolds.as<FoldDesc>() + w0, B, S, Ng, cs_steps, e->bCS.as<float>(), st));
             CU(cudaEventRecord(e->evx[1], st));
@@ -1089,6 +1132,12 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.w3 = e->wRs[2].as<unsigned char>(); rp.w4 = e->wRs[3].as<unsigned char>();
             rp.v1 = e->dv1; rp.v2 = e->dv2; rp.v3 = e->dv3; rp.bhn1 = e->dbhn1; rp.bhn2 = e->dbhn2; rp.bfc3 = e->dbfc3;
             rp.CS = e->bCS.as<float>(); rp.cs_steps = cs_steps; rp.Ng = Ng; rp.G = G;
+            if (inl) {
+                rp.inl = 1;
+                rp.wx1 = e->wRsX[0].as<unsigned char>(); rp.wx2 = e->wRsX[1].as<unsigned char>(); rp.wx3 = e->wRsX[2].as<unsigned char>();
+                rp.FR = e->bFR.as<float>(); rp.M16 = e->bM16.as<__half>(); rp.m16_zero = (long long)tq_rows * kHop;
+                rp.n_expanders = (getenv("WRNN_RS_PAD") && atoi(getenv("WRNN_RS_PAD")) == 0) ? 0 : std::max(0, n_exp);
+            }
             if (ring) {
                 rp.cs_done = e->bCsDone.as<unsigned int>(); rp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
                 rp.CSw = e->bCS.as<float>();
@@ -1144,6 +1193,14 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                     }
                     cudaGetLastError();
                 }
+            }
+            // physical placement (loop_rs.cu: p.place): WRNN_RS_PLACE=1 [WRNN_RS_ROT=k]; not with the timeline / checkpoints (indexed by blockIdx)
+            if (getenv("WRNN_RS_PLACE") && atoi(getenv("WRNN_RS_PLACE")) && !rp.trace && !rp.dbg) {
+                const int grid = G * rs_ctas + ((rp.cs_done || rp.inl) ? rp.n_expanders : 0);
+                CU(e->bRsPlace.ensure((size_t)grid * sizeof(unsigned int)));
+                CU(cudaMemsetAsync(e->bRsPlace.p, 0, (size_t)grid * sizeof(unsigned int), st));
+                rp.place = e->bRsPlace.as<unsigned int>();
+                rp.rot = getenv("WRNN_RS_ROT") ? std::max(0, atoi(getenv("WRNN_RS_ROT"))) % grid : 0;
             }
             CU(launch_loop_rs(rp, st));
             if (l2_window) {

@@ -136,6 +136,17 @@ struct RsParams {
     const float4 *TA1, *TA2, *TQ1, *TQ2;
     const float* coef;
     int n_expanders;
+    // inline conditioning (inl != 0; no records, no expanders): the aux share + biases of a record as one per-FRAME row
+    // FR[frame row][8][512] fp32, the mel share as one more K = 80 slab of the role's on-path product -- operand M16[row][80] fp16
+    // (the upsampled mel of every sample, row = (tq_row0 + frame) * 200 + phase; row m16_zero is all zeros), weights wx1..3
+    // (per-CTA tiles [k-block 2][rows][128 B] of W_ih1 / W_ih2a / fc1a . I[:, mel]: 128 / 96 / kFU rows)
+    int inl;
+    const unsigned char *wx1, *wx2, *wx3;
+    const float* FR;
+    const __half* M16;
+    long long m16_zero;
+    unsigned int* place;         // optional [grid] zeroed words: logical CTA index from the physical SM (rank of %smid), rotated by rot
+    int rot;
     int canary_all;              // phase 1 of an ingest waits for all producers' canaries (1) or the first one (0)
     int offpath_delay_ns;        // T1 waits this long before it reads h1(t) for the recurrent product (the T2 CTAs read it first)
     int Ng, G;                   // folds per group (<= 128), groups; fold f = row f % Ng of group f / Ng
@@ -156,6 +167,10 @@ size_t loop_rs_image_bytes(int role);
 size_t loop_rs_exchange_bytes(int groups);
 cudaError_t set_rs_deadline(long long cycles);
 cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream);
+struct UttDesc;
+size_t loop_rs_ximage_bytes(int role);
+cudaError_t launch_rs_inline_tables(const float4* TA1, const float4* TA2, const float* mel, const UttDesc* utts, int n_utts, const float* coef,
+                                    int rows, float* FR, __half* M16, cudaStream_t stream);
 cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const float4* TQ1, const float4* TQ2, const float* coef,
                                   const FoldDesc* folds, int B, int S, int Ng, int cs_steps, float* CS, cudaStream_t stream);
 

@@ -47,7 +47,9 @@ constexpr uint32_t kTagS = 0x80008000u;       // of non-negative matrices (ReLU 
 // TMEM columns
 constexpr uint32_t kColA = 0;                 // activation operand, 128 lanes x 256 columns (512 fp16 per lane)
 constexpr uint32_t kColD0 = 256;              // on-path accumulator (T1: W_hh1 h1 [96] lives here too, see below)
-constexpr uint32_t kColD1 = 352;              // second accumulator
+constexpr uint32_t kColD1 = 352;              // second accumulator (T2: W_hh2 h2)
+constexpr uint32_t kColD1T1 = 384;            // T1's second accumulator (fc3): its D0 is 128 columns wide with the inline conditioning
+constexpr uint32_t kColX = 448;               // inline conditioning: 80 fp16 of upsampled mel per fold = 40 columns, K steps 0..4
 // shared memory: weight tiles (K-major SWIZZLE_128B, [k-block 8][rows N][128 B]) then constants and the control block
 constexpr int kW0 = 0;                                   // first tile: T1 W_hh1 (96 rows), T2 W_ih2a (96), T3 fc1a (64), T4 fc2 (64)
 constexpr int kW1 = 96 * 128 * 8;                        // second tile: T1 fc3 (32 rows), T2 W_hh2 (96)
@@ -55,7 +57,14 @@ constexpr int kNoiseOfs = kW1 + 32 * 128 * 8;            // T1 only: the step's 
 constexpr int kWEnd = kW1 + 96 * 128 * 8;                // 196608
 constexpr int kFU = kRnn / kRsT3;                        // units per FC-role CTA: 64 (8 CTAs per role) or 32 (16)
 static_assert(kRsT3 == kRsT4 && (kFU == 128 || kFU == 64 || kFU == 32), "thread <-> unit map of the FC roles");
-constexpr int kConstOfs = kWEnd;                         // per-unit constants, <= 5 x 64 floats
+// inline conditioning (kInl): the MEL share of every record is one more K = 80 slab of the role's on-path product: tiles
+// [k-block 2][rows][128 B] of W_q = (W_ih1 | W_ih2a | fc1a) . I[:, mel] next to the role's other tiles
+constexpr int kXW1 = kNoiseOfs + 12 * 512 * 4;           // T1: 128 rows (r, z, 32 zero rows, n) behind the noise buffer
+constexpr int kXW2 = kWEnd;                              // T2: 96 rows behind its two tiles
+constexpr int kXW3 = kFU * 128 * 8;                      // T3: kFU rows behind fc1a
+constexpr int kXWEnd = kWEnd + 96 * 128 * 2;
+static_assert(kXW1 + 128 * 128 * 2 <= kWEnd && (kXW1 & 1023) == 0 && kXW3 + kFU * 128 * 2 <= kWEnd, "inline-conditioning tiles");
+constexpr int kConstOfs = kXWEnd;                        // per-unit constants, <= 5 x 64 floats
 constexpr int kCtlOfs = kConstOfs + 2048;
 constexpr int kSmemBytes = kCtlOfs + 256;
 static_assert(kNoiseOfs + 12 * 512 * 4 <= kWEnd, "T1 noise buffer");
@@ -64,12 +73,13 @@ struct Ctl {
     uint64_t abar[4];      // K quarter kq of the A operand is in TMEM (all 16 warps arrive)
     uint64_t dbar[2];      // accumulator complete (tcgen05.commit): [0] on-path job, [1] recurrent (off-path) job
     uint64_t ebar;         // all 16 epilogue warps have read the recurrent accumulator of the previous step
+    uint64_t xbar;         // inline conditioning: the step's upsampled-mel operand is in TMEM (all 16 warps arrive)
     uint32_t tmem;
     int abort_local;
 };
 // barriers are addressed by their 32-bit shared-memory address (ctl_s + offset): the generic -> shared conversion of a pointer
 // costs ~10 uniform instructions wherever the compiler rematerialises it, and every instruction of the chain counts
-constexpr uint32_t kBarA = 0, kBarD = 32, kBarE = 48;
+constexpr uint32_t kBarA = 0, kBarD = 32, kBarE = 48, kBarX = 56;
 
 __device__ __forceinline__ bool aborted_local(Ctl* c) { return *reinterpret_cast<volatile int*>(&c->abort_local) != 0; }
 // warp-uniform view of the abort flag (lane 0's): the step loops end together for all lanes of a warp
@@ -181,6 +191,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const 
         "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
         "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]^T, A = 128 lanes x 8 columns (16 fp16 per lane)
@@ -430,16 +445,36 @@ __device__ __forceinline__ float mol_draw(const float* lg, uint32_t nz_s, uint32
 // One MMA job: D[128 folds x N] = A (TMEM, 512 fp16 per lane) x W^T (shared memory tile [k-block][N][64]); issued K quarter by K
 // quarter as the ingest warps deliver them.  Whole warp in the loop, one elected lane issues (tc_common.cuh: elect_one); a K
 // step is one add on the descriptor and one UTCHMMA.
+// Inline conditioning: the five K = 16 steps of W_q . m (upsampled mel, TMEM columns kColX..) START the accumulator, so they
+// are issued as soon as the operand is there and the accumulator is free -- long before the awaited matrix arrives.
+__device__ __forceinline__ void mma_ext(uint32_t xw_smem, uint32_t NX, uint32_t d, uint32_t tmem_x) {
+    if (elect_one()) {
+        const uint32_t idx = umma_idesc_f16(128, (int)NX);
+        const uint64_t bx = umma_desc_sw128(xw_smem);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(d, tmem_x + 8u * k, bx + 2u * k, idx, k != 0 ? 1u : 0u);
+        umma_ts(d, tmem_x + 32u, bx + NX * 8u, idx, 1u);           // mel 64..79: first K step of the second k-block
+    }
+    __syncwarp();
+}
 template <bool kTrace>
 __device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t ctl_s, uint32_t w_smem, uint32_t N, uint32_t d, uint32_t a0, uint32_t a_par,
-                                     uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev) {
+                                     uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev, uint32_t xw_smem = 0u, uint32_t NX = 0u,
+                                     uint32_t x_par = 0u) {
     const uint32_t idesc = umma_idesc_f16(128, (int)N);
     const uint64_t bd0 = umma_desc_sw128(w_smem);
     const uint32_t kb_step = N * 8u;                      // one k-block of the tile, in descriptor units of 16 bytes
+    const bool ext = xw_smem != 0u;
+    if (ext) {
+        if (wait_e) wait_mbar(p, ctl, ctl_s + kBarE, e_par);
+        wait_mbar(p, ctl, ctl_s + kBarX, x_par);
+        tcgen05_fence_after();
+        mma_ext(xw_smem, NX, d, a0 + kColX);
+    }
 #pragma unroll 1
     for (int kq = 0; kq < 4; ++kq) {
         wait_mbar(p, ctl, ctl_s + kBarA + 8u * kq, a_par);
-        if (kq == 0 && wait_e) wait_mbar(p, ctl, ctl_s + kBarE, e_par);
+        if (kq == 0 && wait_e && !ext) wait_mbar(p, ctl, ctl_s + kBarE, e_par);
         tcgen05_fence_after();
         if (kq == 0) trace<kTrace>(p, tt, ev);
         if (elect_one()) {
@@ -449,7 +484,7 @@ __device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t ct
             for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    umma_ts(d, a, bd + 2u * k, idesc, (kq | kb | k) != 0 ? 1u : 0u);
+                    umma_ts(d, a, bd + 2u * k, idesc, (ext || (kq | kb | k) != 0) ? 1u : 0u);
                     a += 8u;
                 }
                 bd += kb_step;
@@ -682,7 +717,7 @@ __device__ __forceinline__ void sampler_role(const RsParams& p, Ctl* ctl, uint32
 
 }  // namespace
 
-template <bool kTrace>
+template <bool kTrace, bool kInl>
 __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_constant__ RsParams p) {
     // (no static shared memory in this kernel: the dynamic window starts 1024-byte aligned, which SWIZZLE_128B tiles need;
     //  checked below instead of rounded up -- the round-up was recomputed at every use of a shared address)
@@ -691,19 +726,41 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     float* cst = reinterpret_cast<float*>(smem + kConstOfs);
     const uint32_t smem_s = smem_u32(smem), ctl_s = smem_s + kCtlOfs, cst_s = smem_s + kConstOfs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = (int)blockIdx.x / p.ctas, rc = (int)blockIdx.x % p.ctas;
+    // Which SMs a group lives on is the block scheduler's choice (bid -> SM differs between GPUs and grid sizes) and the step time
+    // follows it (measured: up to 2 us of a 15 us RAW step between two B200s running the same binary).  With p.place the logical
+    // CTA index is taken from the PHYSICAL SM instead: rank of my %smid among the SMs of this grid (one CTA per SM: the grid is
+    // padded to the SM count), rotated by p.rot -- the engine can then choose the layout (engine.cu: rs_calibrate).
+    int bid = (int)blockIdx.x;
+    if (p.place) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.place + blockIdx.x), "r"(smid + 1u) : "memory");
+        int below = 0;
+        if (tid < (int)gridDim.x) {
+            uint32_t v = 0;
+            long long t0 = clock64();
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.place + tid) : "memory");
+                if (v != 0u || clock64() - t0 > 2000000000ll) break;
+            }
+            below = (v != 0u && v - 1u < smid) ? 1 : 0;
+        }
+        bid = (__syncthreads_count(below) + p.rot) % (int)gridDim.x;
+    }
+    const int g = bid / p.ctas, rc = bid % p.ctas;
     const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : (rc < kRsCtas ? 3 : 4)));      // 4: RAW sampler (T5)
     const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : (role == 3 ? rc - kRsT1 - kRsT2 - kRsT3 : rc - kRsCtas)));
     const bool raw = p.mode == 0;                                   // RAW: fc3 + the draw live on the sampler CTAs, T1 only waits for the sample
     const int fold0 = g * p.Ng, nrows = max(0, min(p.Ng, p.B - fold0));
     const int S = p.S;
-    const bool expander = (int)blockIdx.x >= p.G * p.ctas;         // CTAs past the groups produce the conditioning records
+    const bool expander = bid >= p.G * p.ctas;         // CTAs past the groups produce the conditioning records
     const unsigned int consumers = (unsigned int)(p.G * kRsCtas * NW);   // warps that read every record chunk (the samplers read none)
     if ((smem_s & 1023u) != 0u) {          // never on this toolchain; a misaligned tile would compute garbage silently
         if (tid == 0) atomicExch(p.abort_flag, 1);
         return;
     }
 
+    if (expander && kInl) return;          // (inline conditioning: CTAs past the groups only pad the grid -- see launch_loop_rs)
     if (expander) {
         // =================================== conditioning expander ==========================================================
         // work item = (chunk of kRsChunk steps, fold), chunk-major, so chunks complete in the order the loop consumes them;
@@ -714,7 +771,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         __syncthreads();
         if (warp < NW) {
             const float* coef_s = reinterpret_cast<const float*>(smem);
-            const int e_idx = (int)blockIdx.x - p.G * p.ctas;
+            const int e_idx = bid - p.G * p.ctas;
             const int nchunks = (S + kRsChunk - 1) / kRsChunk, ring_chunks = p.cs_steps / kRsChunk;
             const long long nitems = (long long)nchunks * p.B;
             int waited = -1;
@@ -754,6 +811,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         const uint4* src = reinterpret_cast<const uint4*>(img);
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
+        if (kInl && role <= 2) {      // the role's W_q tile (mel share of the conditioning)
+            const int xrows = role == 0 ? 128 : (role == 1 ? 96 : kFU);
+            const uint4* xs = reinterpret_cast<const uint4*>((role == 0 ? p.wx1 : role == 1 ? p.wx2 : p.wx3) + (size_t)cta * (xrows * 256));
+            uint4* xd = reinterpret_cast<uint4*>(smem + (role == 0 ? kXW1 : role == 1 ? kXW2 : kXW3));
+            for (int i = tid; i < xrows * 16; i += NT) xd[i] = xs[i];
+        }
         fence_proxy_async_smem();
     }
     if (role == 0) {            // [v1 r,z,n | b_hn1] x 32 units, fc3 bias (32)
@@ -770,6 +833,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         for (int i = 0; i < 4; ++i) mbar_init(&ctl->abar[i], NW);
         mbar_init(&ctl->dbar[0], 1); mbar_init(&ctl->dbar[1], 1);
         mbar_init(&ctl->ebar, NW);
+        mbar_init(&ctl->xbar, NW);
         ctl->abort_local = 0;
         mbar_fence_init();
     }
@@ -793,24 +857,36 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         if (warp == NW) {
         // =================================== MMA issuer ====================================================================
         uint32_t n_ingest = 0;
-        auto job = [&](uint32_t N, uint32_t dcol, uint32_t wofs, uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev) {
-            mma_job<kTrace>(p, ctl, ctl_s, smem_s + wofs, N, tmem + dcol, tmem + kColA, n_ingest & 1u, done_bar, wait_e, e_par, tt, ev);
+        // (xofs != 0: the job's accumulator starts with the inline-conditioning slab W_q m, operand generation x_par)
+        auto job = [&](uint32_t N, uint32_t dcol, uint32_t wofs, uint32_t done_bar, bool wait_e, uint32_t e_par, int tt, int ev, uint32_t xofs = 0u,
+                       uint32_t NX = 0u, uint32_t x_par = 0u) {
+            mma_job<kTrace>(p, ctl, ctl_s, smem_s + wofs, N, tmem + dcol, tmem + kColA, n_ingest & 1u, done_bar, wait_e, e_par, tt, ev,
+                            (kInl && xofs) ? smem_s + xofs : 0u, NX, x_par);
             ++n_ingest;
         };
         if (role == 0) {
+            if (kInl) {      // "job -1": D0 = W_q1 m(0) (no recurrent share before the first step); completes phase 0 of dbar[1]
+                wait_mbar(p, ctl, ctl_s + kBarX, 0u);
+                tcgen05_fence_after();
+                mma_ext(smem_s + kXW1, 128u, tmem + kColD0, tmem + kColX);
+                if (elect_one()) umma_commit_s(ctl_s + kBarD + 8u);
+                __syncwarp();
+            }
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
-                if (t > 0 && !raw) job(32u, kColD1, kW1, ctl_s + kBarD, false, 0, t, 9);               // fc3 f2(t-1)
-                if (t < S) job(96u, kColD0, kW0, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);    // W_hh1 h1(t)
+                if (t > 0 && !raw) job(32u, kColD1T1, kW1, ctl_s + kBarD, false, 0, t, 9);               // fc3 f2(t-1)
+                if (t < S) job(96u, kColD0, kW0, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11, kXW1, 128u, (uint32_t)(t + 1) & 1u);    // W_hh1 h1(t) [+ W_q1 m(t+1)]
             }
         } else if (role == 1) {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
-                job(96u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);                                  // W_ih2a h1(t)
+                job(96u, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9, kXW2, 96u, (uint32_t)t & 1u);      // W_ih2a h1(t) [+ W_q2 m(t)]
                 job(96u, kColD1, kW1, ctl_s + kBarD + 8u, true, (uint32_t)t & 1u, t, 11);               // W_hh2 h2(t)
             }
         } else if (role == 4) {
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)p.qcols, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);   // fc3 slice f2(t)
+        } else if (role == 2) {
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9, kXW3, (uint32_t)kFU, (uint32_t)t & 1u);   // fc1a s2(t) [+ W_q3 m(t)]
         } else {
-            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc1a s2(t) / fc2 f1(t)
+            for (int t = 0; t < S && !warp_aborted(ctl); ++t) job((uint32_t)kFU, kColD0, kW0, ctl_s + kBarD, false, 0, t, 9);          // fc2 f1(t)
         }
         }
     } else {
@@ -861,6 +937,28 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 a[8 * k + 4] = hi.x; a[8 * k + 5] = hi.y; a[8 * k + 6] = hi.z; a[8 * k + 7] = hi.w;
             }
         };
+        // ---- inline conditioning (kInl): no per-sample records, no expanders.  A record is the per-FRAME row FR[frame] (aux share +
+        // biases, fp32, one 16 KB row per frame: it changes every 200 steps) and the mel share is W_q . m(n) inside the role's MMA,
+        // m(n) = the upsampled mel of sample n (80 fp16, table M16).  (c_frame, c_phase) = position of sample n0 + t.
+        int c_frame = fd.n0 / kHop, c_phase = fd.n0 - c_frame * kHop;
+        auto rec_row = [&]() { return p.FR + (size_t)(fd.ta_row0 + min(c_frame, fd.T)) * 4096; };     // row T: bias only (fold tail padding, Q9)
+        auto m_row = [&](int frame, int phase) { return frame < fd.T ? (long long)(fd.tq_row0 + frame) * kHop + phase : p.m16_zero; };
+        auto advance = [&]() { if (++c_phase == kHop) { c_phase = 0; ++c_frame; } };
+        // my warp's K step(s) of row `mrow` -> TMEM columns kColX + 8 k (warp cs: k = cs; cs 0 also k = 4); every warp arrives
+        auto ext_store = [&](long long mrow) {
+            if (L.wlive) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.M16 + mrow * kFeat);
+                const uint4 v0 = __ldg(src + 2 * L.cs), v1 = __ldg(src + 2 * L.cs + 1);
+                uint4 v2 = make_uint4(0u, 0u, 0u, 0u), v3 = v2;
+                if (L.cs == 0) { v2 = __ldg(src + 8); v3 = __ldg(src + 9); }
+                tmem_st8(L.tlane + kColX + 8u * (uint32_t)L.cs, v0, v1);
+                if (L.cs == 0) tmem_st8(L.tlane + kColX + 32u, v2, v3);
+                tmem_st_wait();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(ctl_s + kBarX);
+        };
         if (role == 0) {
             // ---- T1: fc3 + draw of step t-1, GRU1 of step t, then the recurrent product for step t+1 -----------------------
             float h1[8];
@@ -869,30 +967,37 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             const uint32_t v1_s = cst_s + 32u * L.cs;            // [a][32 units]: + 128 a bytes
             const uint32_t sbias_s = cst_s + 512u;
             const uint32_t nz_s = smem_s + kNoiseOfs + 4u * tid;
+            if (kInl) ext_store(m_row(c_frame, c_phase));        // m(0) for "job -1"
             for (int t = 0; t <= S && !warp_aborted(ctl); ++t) {
                 trace<kTrace>(p, t, 0);
                 // everything that does not need f2(t-1) happens BEFORE the wait for it: the conditioning record, the mixture
                 // noise, and the recurrent accumulator W_hh1 h1(t-1) (complete since the off-path job of the previous step)
                 // folded into the record: a[] = (c_r + gh_r, c_z + gh_z, c_n), bn[] = gh_n + b_hn
                 float a[24], bn[8];
-                if (t < S) cs_wait(t);
-                if (t < S && L.wlive) load_rec24(csrow + (size_t)(t % p.cs_steps) * cs_step + 32 * cta + 8 * L.cs, a);
+                if (!kInl && t < S) cs_wait(t);
+                if (t < S && L.wlive) load_rec24((kInl ? rec_row() : csrow + (size_t)(t % p.cs_steps) * cs_step) + 32 * cta + 8 * L.cs, a);
                 if (raw && t == S) break;           // (RAW: the sampler CTAs draw the last sample; nothing is left to do here)
                 if (t > 0 && L.wlive && !raw) mol_noise(nz_s, sbias_s, (uint32_t)(t - 1), (uint32_t)fd.fold, (uint32_t)fd.utt, key);
-                if (t > 0) {
-                    wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(t - 1) & 1u);      // recurrent job of step t-1: D0 complete, A free
+                if (kInl || t > 0) {      // (kInl: phase t of dbar[1] is job t-1, phase 0 the conditioning-only "job -1")
+                    wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(kInl ? t : t - 1) & 1u);      // recurrent job of step t-1: D0 complete, A free
                     tcgen05_fence_after();
                 }
                 if (t < S) {
                     if (L.wlive) {
                         lds8(v1_s + 384u, bn);
-                        if (t > 0) {
+                        if (kInl || t > 0) {
                             float gh[24];
                             tmem_ld8(L.tlane + kColD0 + 0 + 8 * L.cs, gh); tmem_ld8(L.tlane + kColD0 + 32 + 8 * L.cs, gh + 8);
                             tmem_ld8(L.tlane + kColD0 + 64 + 8 * L.cs, gh + 16);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { a[i] += gh[i]; a[8 + i] += gh[8 + i]; bn[i] += gh[16 + i]; }
+                            if (kInl) {       // columns 96..127: the mel share of the candidate's input side (kept apart from W_hn h)
+                                tmem_ld8(L.tlane + kColD0 + 96 + 8 * L.cs, gh);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) a[16 + i] += gh[i];
+                            }
                         }
                     }
                     tcgen05_fence_before();
@@ -922,8 +1027,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                     ctrace<kTrace>(p, t, 1);
                     if (L.wlive) {
                         float lg[32];
-                        tmem_ld8(L.tlane + kColD1 + 0, lg); tmem_ld8(L.tlane + kColD1 + 8, lg + 8);
-                        tmem_ld8(L.tlane + kColD1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1 + 24, lg + 24);
+                        tmem_ld8(L.tlane + kColD1T1 + 0, lg); tmem_ld8(L.tlane + kColD1T1 + 8, lg + 8);
+                        tmem_ld8(L.tlane + kColD1T1 + 16, lg + 16); tmem_ld8(L.tlane + kColD1T1 + 24, lg + 24);
                         tmem_ld_wait();
                         ctrace<kTrace>(p, t, 2);
                         const float xs = mol_draw(lg, nz_s, sbias_s);
@@ -957,11 +1062,19 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 }
                 trace<kTrace>(p, t, 5);
                 ctrace<kTrace>(p, t, 6);
+                if (kInl) {       // m(t+1) for the job below (the previous reader of these columns, job t-1, completed before this step)
+                    advance();
+                    if (L.wlive && L.cs == 1) {      // and the row of step t + 9 on its way into L2 (T1 is the first reader of every row)
+                        const __half* pf = p.M16 + m_row(c_frame, c_phase) * kFeat + 8 * kFeat;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    }
+                    ext_store(m_row(c_frame, c_phase));
+                }
                 // recurrent product for step t+1: the full h1(t) -> A buffer (the fc3 job has completed: dbar[0] was waited).
                 // Off the critical path: wait until the T2 CTAs have read the same lines for the on-path product.
                 __nanosleep(p.offpath_delay_ns);
                 ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH1, t), kTagE, GEN(t), -1, t, 6, nullptr, 0u);
-                cs_release(t);
+                if (!kInl) cs_release(t);
                 if (cta == 0 && g == 0 && tid == 0 && (t % 100) == 0 && p.progress) {
                     *reinterpret_cast<volatile int*>(p.progress) = t;
                     __threadfence_system();
@@ -977,8 +1090,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 trace<kTrace>(p, t, 0);
                 // before the wait for h1(t): the record and the recurrent accumulator W_hh2 h2(t-1), folded together (see T1)
                 float a[24], bn[8];
-                cs_wait(t);
-                if (L.wlive) load_rec24(csrow + (size_t)(t % p.cs_steps) * cs_step + 3 * 512 + 32 * cta + 8 * L.cs, a);
+                if (kInl) ext_store(m_row(c_frame, c_phase));     // m(t): the on-path job starts with W_q2 m(t)
+                else cs_wait(t);
+                if (L.wlive) load_rec24((kInl ? rec_row() : csrow + (size_t)(t % p.cs_steps) * cs_step) + 3 * 512 + 32 * cta + 8 * L.cs, a);
                 if (t > 0) {
                     wait_mbar(p, ctl, ctl_s + kBarD + 8u, (uint32_t)(t - 1) & 1u);
                     tcgen05_fence_after();
@@ -1042,7 +1156,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 trace<kTrace>(p, t, 5);
                 ctrace<kTrace>(p, t, 6);
                 ingest<kTrace>(p, ctl, ctl_s, L, MAT(MH2, t), kTagE, GEN(t), -1, t, 6, nullptr, 0u);
-                cs_release(t);
+                if (kInl) advance(); else cs_release(t);
             }
         } else if (role == 4) {
             // ---- T5 (RAW): my slice of fc3 (p.qcols = 64 or 128 classes) on f2(t), the soft-max partials, and -- in the CTA whose
@@ -1058,9 +1172,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
             for (int t = 0; t < S && !warp_aborted(ctl); ++t) {
                 trace<kTrace>(p, t, 0);
                 float cc[kPU];
-                cs_wait(t);
+                if (kInl) { if (fc1) ext_store(m_row(c_frame, c_phase)); }     // m(t): fc1's job starts with W_q3 m(t)
+                else cs_wait(t);
                 if (L.wlive) {
-                    const float4* c = reinterpret_cast<const float4*>(csrow + (size_t)(t % p.cs_steps) * cs_step + (fc1 ? 6 : 7) * 512 + kFU * cta + kPU * L.cs);
+                    const float4* c = reinterpret_cast<const float4*>((kInl ? rec_row() : csrow + (size_t)(t % p.cs_steps) * cs_step) + (fc1 ? 6 : 7) * 512 + kFU * cta + kPU * L.cs);
 #pragma unroll
                     for (int i = 0; i < kPU / 4; ++i) { const float4 q4 = __ldcg(c + i); cc[4 * i] = q4.x; cc[4 * i + 1] = q4.y; cc[4 * i + 2] = q4.z; cc[4 * i + 3] = q4.w; }
                 }
@@ -1093,7 +1208,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
                 }
                 tcgen05_fence_before();
                 trace<kTrace>(p, t, 5);
-                cs_release(t);
+                if (kInl) advance(); else cs_release(t);
             }
         }
     }
@@ -1118,6 +1233,52 @@ __global__ void __launch_bounds__(512) expand_cond_rs_kernel(const float4* __res
     expand_item_rs(TA1, TA2, TQ1, TQ2, coef, folds[b], b / Ng, b % Ng, t0, min(S, t0 + steps_per_block), cs_steps, Ng, CS, threadIdx.x);
 }
 
+// Tables of the inline-conditioning form (kInl), one block per row of the utterances' common row space (T + 4 rows each):
+//   FR[row][8][512]     = the aux share + biases of a record (TA1 / TA2 in plane order c1 r,z,n | c2 r,z,n | c3 | c4): frames and the bias-only row T
+//   M16[row*200+ph][80] = fp16 of the upsampled mel of sample (frame = row - tq_row0, phase ph): sum_d coef[ph][d] melpad[frame + d]
+//                         (same taps and order as the per-frame tables of cond.cu; rows of frames >= T are never read)
+// and the all-zero row M16[rows * 200] (+ slack for the prefetch ahead).
+__global__ void __launch_bounds__(256) rs_inline_tables_kernel(const float4* __restrict__ TA1, const float4* __restrict__ TA2, const float* __restrict__ mel,
+                                                               const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ coef, int rows,
+                                                               float* __restrict__ FR, __half* __restrict__ M16) {
+    __shared__ float mp[kTaps][kFeat];
+    __shared__ float cf[kHop * kTaps];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    if (row >= rows) {          // the zero rows behind the table
+        for (int i = tid; i < 16 * kFeat; i += 256) M16[(size_t)rows * kHop * kFeat + i] = __float2half_rn(0.f);
+        return;
+    }
+    int lo = 0, hi = n_utts - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (utts[mid].tq_row0 <= row) lo = mid; else hi = mid - 1; }
+    const UttDesc u = utts[lo];
+    const int f = row - u.tq_row0;
+    for (int i = tid; i < kRnn; i += 256) {
+        const float4 a = TA1[(size_t)row * kRnn + i], b = TA2[(size_t)row * kRnn + i];
+        float* o = FR + (size_t)row * 4096 + i;
+        o[0] = a.x; o[512] = a.y; o[1024] = a.z; o[1536] = b.x; o[2048] = b.y; o[2560] = b.z; o[3072] = a.w; o[3584] = b.w;
+    }
+    for (int i = tid; i < kTaps * kFeat; i += 256) {
+        const int d = i / kFeat, c = i - d * kFeat, t = f + d - kPad;
+        mp[d][c] = (t >= 0 && t < u.T) ? mel[u.mel_off + (long long)c * u.T + t] : 0.f;
+    }
+    for (int i = tid; i < kHop * kTaps; i += 256) cf[i] = coef[i];
+    __syncthreads();
+    __half2* out = reinterpret_cast<__half2*>(M16 + (size_t)row * kHop * kFeat);
+    for (int i = tid; i < kHop * kFeat / 2; i += 256) {
+        const int ph = i / (kFeat / 2), c = 2 * (i - ph * (kFeat / 2));
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < kTaps; ++d) { const float w = cf[ph * kTaps + d]; v0 = fmaf(w, mp[d][c], v0); v1 = fmaf(w, mp[d][c + 1], v1); }
+        out[i] = __floats2half2_rn(v0, v1);
+    }
+}
+cudaError_t launch_rs_inline_tables(const float4* TA1, const float4* TA2, const float* mel, const UttDesc* utts, int n_utts, const float* coef,
+                                    int rows, float* FR, __half* M16, cudaStream_t stream) {
+    rs_inline_tables_kernel<<<rows + 1, 256, 0, stream>>>(TA1, TA2, mel, utts, n_utts, coef, rows, FR, M16);
+    return cudaGetLastError();
+}
+size_t loop_rs_ximage_bytes(int role) { return (size_t)(role == 0 ? 128 : (role == 1 ? 96 : kFU)) * 256; }
+
 cudaError_t set_rs_deadline(long long cycles) { return cudaMemcpyToSymbol(g_rs_deadline, &cycles, sizeof(cycles)); }
 size_t loop_rs_image_bytes(int role) { return role == 0 ? (size_t)kW1 + 32 * 128 * 8 : (role == 1 ? (size_t)kWEnd : (size_t)kFU * 128 * 8); }
 size_t loop_rs_exchange_bytes(int groups) { return (size_t)groups * kMats * kRsBufs * kMatChunks * 16; }
@@ -1132,12 +1293,16 @@ cudaError_t launch_expand_cond_rs(const float4* TA1, const float4* TA2, const fl
 
 cudaError_t launch_loop_rs(const RsParams& p, cudaStream_t stream) {
     // the instrumented instantiation only when a timeline or checkpoints were asked for
-    const void* fn = (p.trace || p.dbg) ? (const void*)wrnn_loop_rs_kernel<true> : (const void*)wrnn_loop_rs_kernel<false>;
+    const bool tr = p.trace || p.dbg;
+    const void* fn = p.inl ? (tr ? (const void*)wrnn_loop_rs_kernel<true, true> : (const void*)wrnn_loop_rs_kernel<false, true>)
+                           : (tr ? (const void*)wrnn_loop_rs_kernel<true, false> : (const void*)wrnn_loop_rs_kernel<false, false>);
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
     RsParams pp = p;
     void* args[] = {&pp};
-    const int grid = p.G * p.ctas + (p.cs_done ? p.n_expanders : 0);
+    // inline conditioning: n_expanders CTAs that exit at once pad the grid to the SM count, so that the groups sit on the SMs they
+    // sat on with the expanders behind them (the step time follows the placement: +-1 us between grid sizes on one GPU, measured)
+    const int grid = p.G * p.ctas + ((p.cs_done || p.inl) ? p.n_expanders : 0);
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, kSmemBytes, stream);
 }
 
