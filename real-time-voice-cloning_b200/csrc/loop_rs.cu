@@ -185,6 +185,32 @@ __device__ __forceinline__ uint32_t bad4(const uint4* v, uint32_t tb, bool gen1)
                        (v[3].x | v[3].y | v[3].z) | v[3].w;
     return o & tb;
 }
+// K parts of an ingest / MMA job, in k-blocks of 64 fp16 (8 chunks; 4 K = 16 steps): the matrix arrives and is multiplied part by
+// part; two parts are requested up front, part k + 2 when part k has arrived.  Four even quarters.  -DWRNN_RS_UNEVEN_PARTS makes the
+// last part the smallest ({2, 2, 3, 1} k-blocks: fewer MMAs exposed behind the last byte) -- measured SLOWER, 13.8 vs 12.9 us per
+// 213-fold step: a T2 job (N = 96, 55 clocks per K step = the tensor pipe's peak rate at M = 128) is already as long as the
+// ingest of <= 107 folds, so a larger third part only queues MMAs, and 14 chunks in flight instead of 12 spill another 100 bytes.
+#ifndef WRNN_RS_UNEVEN_PARTS
+#define RS_PART_KB(kq) 2
+#define RS_PART_KB0(kq) (2 * (kq))
+#else
+#define RS_PART_KB(kq) ((kq) == 2 ? 3 : ((kq) == 3 ? 1 : 2))
+#define RS_PART_KB0(kq) ((kq) == 3 ? 7 : 2 * (kq))
+#endif
+template <int N>
+__device__ __forceinline__ uint32_t badN(const uint4* v, uint32_t tb, bool gen1) {
+    if constexpr (N == 4) return bad4(v, tb, gen1);
+    if (gen1) {
+        uint32_t a = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < N; ++i) a &= (v[i].x & v[i].y) & (v[i].z & v[i].w);
+        return ~a & tb;
+    }
+    uint32_t o = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) o |= (v[i].x | v[i].y) | (v[i].z | v[i].w);
+    return o & tb;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -295,7 +321,6 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, uint32_
         }
         return o;
     }
-    const uint4* base = mat + (size_t)(L.cs * 4) * 128 + L.row_ld;         // + (16 kq + i) * 128
     {   // phase 1, ONE warp per CTA: lane l polls the canary chunk 2 l of the group's first fold (32 different producer warps:
         // every CTA of the producing role) until the first of them shows this step's generation (p.canary_all: until all
         // do); the other live warps sleep on a named barrier.  (All 16 warps polling cost 16 KB of L2 traffic per CTA and
@@ -319,45 +344,58 @@ __device__ __forceinline__ IngestOut ingest(const RsParams& p, Ctl* ctl, uint32_
     dbg<kTrace>(p, dbg_t, 0x11);
     trace<kTrace>(p, dbg_t, ev0);
     if (ev0 == 1) ctrace<kTrace>(p, dbg_t, 8);
+    // my chunks of part kq: 8 kb0 + (2 kb) cs + i, i < 2 kb (kb = k-blocks of the part, kb0 = its first); kept in v[2 kb0 ..]
+    const uint4* base = mat + (size_t)(L.cs * 4) * 128 + L.row_ld;
     uint4 v[16];
+    auto request = [&](auto KQ) {
+        constexpr int kq = decltype(KQ)::value, n = 2 * RS_PART_KB(kq), c0 = 8 * RS_PART_KB0(kq);
+        const uint4* b = n == 4 ? base : base + (n - 4) * L.cs * 128;            // (one base pointer; a 4-chunk part is constant offsets from it)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ld_chunk(base + ((i >> 2) * 16 + (i & 3)) * 128);
+        for (int i = 0; i < n; ++i) v[2 * RS_PART_KB0(kq) + i] = ld_chunk(b + (c0 + i) * 128);
+    };
+    request(std::integral_constant<int, 0>{});
+    request(std::integral_constant<int, 1>{});
     const uint4* xp = mat + (size_t)(extra_chunk >= 0 ? extra_chunk : 0) * 128 + L.row_ld;
     if (extra_chunk >= 0) o.extra = ld_chunk(xp);
     unsigned long long xword = 0ull;
     if (xw) xword = ll_load(xw);            // the sample word was published before this matrix: its load rides along
     int passes = 1;
-#pragma unroll
-    for (int kq = 0; kq < 4; ++kq) {
-        uint32_t bad = bad4(&v[4 * kq], tb, gen1);
-        asm volatile("" ::"r"(bad) : "memory");          // (pins the next requests behind the arrival of this quarter: volatile asm keeps its order)
-        if (kq < 2) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[4 * (kq + 2) + i] = ld_chunk(base + ((kq + 2) * 16 + i) * 128);
-        }
-        if (bad != 0u) {                                   // rare: a producer of this quarter is late
+    auto part = [&](auto KQ) {
+        constexpr int kq = decltype(KQ)::value, n = 2 * RS_PART_KB(kq), v0 = 2 * RS_PART_KB0(kq);
+        uint32_t bad = badN<n>(&v[v0], tb, gen1);
+        asm volatile("" ::"r"(bad) : "memory");          // (pins the next requests behind the arrival of this part: volatile asm keeps its order)
+        if constexpr (kq < 2) request(std::integral_constant<int, kq + 2>{});
+        if (bad != 0u) {                                   // rare: a producer of this part is late
             long long t0 = 0;
             int spins = 0;
             do {
                 ++passes;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[4 * kq + i] = ld_chunk(base + (kq * 16 + i) * 128);
-                bad = bad4(&v[4 * kq], tb, gen1);
+                request(KQ);
+                bad = badN<n>(&v[v0], tb, gen1);
             } while (bad != 0u && !RS_SPIN_CHECK(255));
         }
         if (gen1) {      // generation 1: the bit is set in every half; take it out (generation 0 needs nothing)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { v[4 * kq + i].x ^= tb; v[4 * kq + i].y ^= tb; v[4 * kq + i].z ^= tb; v[4 * kq + i].w ^= tb; }
+            for (int i = 0; i < n; ++i) { v[v0 + i].x ^= tb; v[v0 + i].y ^= tb; v[v0 + i].z ^= tb; v[v0 + i].w ^= tb; }
         }
         __syncwarp();
-        if (kq > 0) {              // the previous quarter's store has had the checks above to complete
+        if constexpr (kq > 0) {    // the previous part's store has had the checks above to complete
             tmem_st_wait();
             tcgen05_fence_before();
             if (L.lane == 0) mbar_arrive_s(ctl_s + kBarA + 8u * (kq - 1));
             trace_kq<kTrace>(p, dbg_t, ev0, kq - 1);
         }
-        tmem_st16(L.tlane + kColA + (uint32_t)(kq * 64 + L.cs * 16), v[4 * kq], v[4 * kq + 1], v[4 * kq + 2], v[4 * kq + 3]);
-    }
+        const uint32_t col = L.tlane + kColA + 4u * (uint32_t)(8 * RS_PART_KB0(kq) + n * L.cs);       // a chunk = 4 columns
+        if constexpr (n == 4) tmem_st16(col, v[v0], v[v0 + 1], v[v0 + 2], v[v0 + 3]);
+        else {                     // (8-column stores: a 6-chunk part starts at a multiple of 8 columns, not of 16)
+#pragma unroll
+            for (int i = 0; i < n; i += 2) tmem_st8(col + 4u * i, v[v0 + i], v[v0 + i + 1]);
+        }
+    };
+    part(std::integral_constant<int, 0>{});
+    part(std::integral_constant<int, 1>{});
+    part(std::integral_constant<int, 2>{});
+    part(std::integral_constant<int, 3>{});
     tmem_st_wait();
     tcgen05_fence_before();
     if (L.lane == 0) mbar_arrive_s(ctl_s + kBarA + 24u);
@@ -478,10 +516,12 @@ __device__ __forceinline__ void mma_job(const RsParams& p, Ctl* ctl, uint32_t ct
         tcgen05_fence_after();
         if (kq == 0) trace<kTrace>(p, tt, ev);
         if (elect_one()) {
-            uint64_t bd = bd0 + (uint64_t)(2u * (uint32_t)kq * kb_step);
-            uint32_t a = a0 + 64u * (uint32_t)kq;
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t kb0 = (uint32_t)RS_PART_KB0(kq);
+            const int nkb = RS_PART_KB(kq);
+            uint64_t bd = bd0 + (uint64_t)(kb0 * kb_step);
+            uint32_t a = a0 + 32u * kb0;                   // a k-block = 64 fp16 = 32 columns of the A operand
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     umma_ts(d, a, bd + 2u * k, idesc, (ext || (kq | kb | k) != 0) ? 1u : 0u);
@@ -730,6 +770,11 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
     // follows it (measured: up to 2 us of a 15 us RAW step between two B200s running the same binary).  With p.place the logical
     // CTA index is taken from the PHYSICAL SM instead: rank of my %smid among the SMs of this grid (one CTA per SM: the grid is
     // padded to the SM count), rotated by p.rot -- the engine can then choose the layout (engine.cu: rs_calibrate).
+    // (compiled in with -DWRNN_RS_PLACEMENT only -- tools/mkvariant.py: a logical index that is not blockIdx.x costs the product
+    //  kernel ~100 bytes of spills, because everything derived from it can no longer be rematerialised from the special register)
+#ifndef WRNN_RS_PLACEMENT
+    const int bid = (int)blockIdx.x;
+#else
     int bid = (int)blockIdx.x;
     if (p.place) {
         uint32_t smid;
@@ -747,6 +792,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_loop_rs_kernel(const __grid_consta
         }
         bid = (__syncthreads_count(below) + p.rot) % (int)gridDim.x;
     }
+#endif
     const int g = bid / p.ctas, rc = bid % p.ctas;
     const int role = rc < kRsT1 ? 0 : (rc < kRsT1 + kRsT2 ? 1 : (rc < kRsT1 + kRsT2 + kRsT3 ? 2 : (rc < kRsCtas ? 3 : 4)));      // 4: RAW sampler (T5)
     const int cta = role == 0 ? rc : (role == 1 ? rc - kRsT1 : (role == 2 ? rc - kRsT1 - kRsT2 : (role == 3 ? rc - kRsT1 - kRsT2 - kRsT3 : rc - kRsCtas)));
