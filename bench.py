@@ -411,7 +411,11 @@ def main():
         n_exch = 8 if kern == "wrnn_loop_rr_kernel" else (6 if ctx["plan"][0] == "RAW" else 4) if kern == "wrnn_loop_rs_kernel" else 4 if kern == "wrnn_loop_gn_kernel" else (5 if (lt.get("precision") == _native.PREC_SPARSE_F32 or ctx["plan"][0] == "MOL") else 6)
         us = mres["loop_s"] * 1e6 / (lt["n_steps"] * max(1, lt["n_launches"]))
         fl = {"f32": floor["ll_us"], "f16": floor["counter_us"], "sparse": floor["cluster_us"]}[precision]
-        return {"kernel": kern, "us_per_step": us, "folds": lt["n_folds"], "loop_steps": lt["n_steps"], "exchanges_per_step": n_exch,
+        extra = {}
+        if kern == "wrnn_loop_rs_kernel":       # which conditioning form ran (engine default: inline; WRNN_RS_INLINE=0: record ring)
+            extra["conditioning"] = ("records from expander CTAs through an L2-resident ring" if os.environ.get("WRNN_RS_INLINE") == "0" else
+                                     "inline: per-frame rows + the mel share as a K = 80 slab of the on-path MMA (no per-sample records)")
+        return {"kernel": kern, **extra, "us_per_step": us, "folds": lt["n_folds"], "loop_steps": lt["n_steps"], "exchanges_per_step": n_exch,
                 "exchange_floor_us": floor["ll_us"], "counter_barrier_floor_us": floor["counter_us"], "cluster16_exchange_floor_us": floor["cluster_us"],
                 "step_over_floor": us / (n_exch * fl), "step_over_flag_in_data_floor": us / (n_exch * floor["ll_us"]),
                 "floor_used": {"f32": "flag-in-data exchange through L2", "f16": "fence+atomic counter barrier through L2",
