@@ -989,12 +989,18 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
     *e->hProgress = 0;
     auto t_start = std::chrono::steady_clock::now();
     float ms_expand = 0.f;
-    const int wave = is_rr ? kRrMaxFolds : is_gn ? kGnMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
+    int wave = is_rr ? kRrMaxFolds : is_gn ? kGnMaxFolds : (use_tc ? kTcMaxFolds : (use_sparse ? 4096 : kMaxFoldsPerLaunch));
     // role-specialised loop: as many 48-CTA groups as the device holds; WRNN_RS=0 keeps loop_tc.cu for every fold count
     const int rs_samplers = (e->mode == WRNN_MODE_RAW && e->wRs[4].p) ? e->rs_samplers : 0;      // RAW: sampler CTAs per group
     const int rs_ctas = kRsCtas + rs_samplers;
     const int rs_groups_max = std::max(0, e->n_sms / rs_ctas);
     const int rs_max_folds = (getenv("WRNN_RS") && atoi(getenv("WRNN_RS")) == 0) ? 0 : rs_groups_max * kRsMaxFoldsPerGroup;
+    // MOL, one to two role-specialised launches' worth of folds: two balanced waves of loop_rs beat one launch of loop_tc
+    // (measured, us per step over all folds: 385 folds 2 x 12.8 vs 27.0, 512: 2 x 13.0 vs 28.6, 766: 2 x 14.1 vs 29.9; three waves
+    // lose at 1024: 3 x 13.9 vs 36.6 -- tools/wave_crossover.py), and loop_rs keeps no per-sample conditioning records
+    if (use_tc && !is_rr && !is_gn && !use_sparse && e->mode == WRNN_MODE_MOL && e->wRs[0].p && e->wRsX[0].p && rs_max_folds > 0 &&
+        Btot > rs_max_folds && Btot <= 2 * rs_max_folds && !(getenv("WRNN_RS_WAVES") && atoi(getenv("WRNN_RS_WAVES")) == 0))
+        wave = (Btot + 1) / 2;
     bool rs_tables = false;
     for (int w0 = 0; w0 < Btot; w0 += wave) {
         const int B = std::min(wave, Btot - w0);

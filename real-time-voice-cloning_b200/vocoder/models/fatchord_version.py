@@ -413,7 +413,7 @@ def resolve_precision(n_classes, sparsity, n_folds, sparse_available=True):
     sections 4.5, 6): a pruned checkpoint whose compressed images fit one cluster -> the block-sparse cluster loop (62.9x vs
     38.8x real-time on cfg4; a pruned checkpoint that does NOT fit falls through to the dense loops -- its tensors are dense
     with zeros, vocoder/pruner.py:55-58); a dense one with at least AUTO_F16_MIN_FOLDS folds in the call -> the fp16
-    tensor-core loops (up to 256 folds: the role-specialised loop_rs.cu, MOL and RAW; above: loop_tc.cu); fewer folds -> the
+    tensor-core loops (MOL up to 384 folds, RAW up to 256: the role-specialised loop_rs.cu; MOL 385..768: two waves of it; above: loop_tc.cu); fewer folds -> the
     fp32 loop, which is then as fast AND bit-faithful (one fold: the only loop built for it).  Measured crossover, us per
     step fp32 loop / loop_rs.cu (tools/auto_crossover_raw.py, RAW 9-bit): 2 folds 14.6 / 14.3, 5 folds 16.1 / 15.5, 9 folds
     18.6 / 15.7, 13 folds 20.5 / 15.9, 19 folds 26.2 / 16.1; MOL on loop_rs.cu runs 10.6 us per step at 18 folds.

@@ -52,6 +52,28 @@ def test_rs_loop_config3_full_size_vs_oracle(target, overlap, folds):
     assert dict(model.last_timings)["n_folds"] == folds
 
 
+def test_rs_loop_three_full_groups_vs_oracle():
+    """257 .. 384 folds: three groups of up to 128 folds each (only possible since no SM is needed for expanders) against the ORACLE."""
+    model, sd = make_model(seed=12, bits=9, mode="MOL")
+    mel = norm_mel(4800, 2)
+    out = _oracle_check(model, sd, "MOL", mel, 2200, 360, 48, 9, "loop_rs three groups 2200/360")
+    assert 257 <= out["samples"].shape[0] <= 384, out["samples"].shape
+    assert dict(model.last_timings)["loop_kernel"] == "wrnn_loop_rs_kernel"
+
+
+def test_rs_loop_two_waves_vs_oracle(monkeypatch):
+    """385 .. 768 MOL folds run as two balanced waves of the role-specialised loop (measured faster than one loop_tc launch):
+    against the ORACLE, and WRNN_RS_WAVES=0 puts the same call back on loop_tc."""
+    model, sd = make_model(seed=12, bits=9, mode="MOL")
+    mel = norm_mel(4800, 2)
+    out = _oracle_check(model, sd, "MOL", mel, 1705, 170, 32, 9, "loop_rs two waves 1705/170")
+    t = dict(model.last_timings)
+    assert out["samples"].shape[0] == 512 and t["loop_kernel"] == "wrnn_loop_rs_kernel" and t["n_launches"] == 2, t
+    monkeypatch.setenv("WRNN_RS_WAVES", "0")
+    model.generate_debug(mel, True, 1705, 170, seed=9, max_steps=8, precision=F16)
+    assert dict(model.last_timings)["loop_kernel"] == "wrnn_loop_tc_kernel"
+
+
 @pytest.mark.parametrize("bits,T,target,overlap,folds,steps", [(9, 800, 8000, 800, 19, 96), (10, 4800, 3000, 1500, 213, 64), (9, 4800, 6000, 1000, 137, 64)])
 def test_rs_loop_raw_vs_oracle(bits, T, target, overlap, folds, steps):
     """RAW on the role-specialised loop (sampler CTAs: fc3 slices, soft-max partials exchanged between the CTAs, inverse-CDF draw):
