@@ -52,6 +52,26 @@ def test_rs_loop_config3_full_size_vs_oracle(target, overlap, folds):
     assert dict(model.last_timings)["n_folds"] == folds
 
 
+@pytest.mark.parametrize("mode,seed,bits,T,target,overlap,folds", [("MOL", 12, 9, 4800, 3000, 1500, 213), ("RAW", 11, 9, 800, 8000, 800, 19)])
+def test_rs_loop_full_length_vs_fp32_loop(mode, seed, bits, T, target, overlap, folds):
+    """EVERY step of the two headline calls (config 3 on infer_waveform's own plan: 213 folds x 6000 steps; config 1: 19 folds x 9600
+    steps) -- all phases of all frames, the fold tails past the utterance, 30 / 48 generations of the exchange buffers' bit: the fp16
+    loop free-running, the oracle-anchored fp32 loop teacher-forced on its samples; logits within 1e-3 of the largest logit, draws >= 99.9 %."""
+    model, _ = make_model(seed=seed, bits=bits, mode=mode)
+    mel = norm_mel(T, 1)
+    S = target + 2 * overlap
+    b = model.generate_debug(mel, True, target, overlap, want_logits=True, seed=9, precision=F16)
+    assert b["samples"].shape == (folds, S) and dict(model.last_timings)["loop_kernel"] == "wrnn_loop_rs_kernel"
+    a = model.generate_debug(mel, True, target, overlap, forced=b["samples"], want_logits=True, seed=9, precision=0)
+    assert dict(model.last_timings)["loop_kernel"] == "wrnn_loop_f32_kernel"
+    err = _rel(b["logits"], a["logits"])
+    agree = float((a["samples"] == b["samples"]).mean()) if mode == "RAW" else float((np.abs(a["samples"] - b["samples"]) < 1e-3).mean())
+    worst = float(np.abs(b["logits"] - a["logits"]).max(axis=(0, 2)).argmax())
+    print("loop_rs %s full length, %d folds x %d steps vs fp32 loop: logits rel err %.3e (worst step %d), draw agreement %.5f" % (mode, folds, S, err, worst, agree))
+    assert np.isfinite(b["logits"]).all()
+    assert err < REL_TOL and agree >= AGREE, (err, agree)
+
+
 def test_rs_loop_three_full_groups_vs_oracle():
     """257 .. 384 folds: three groups of up to 128 folds each (only possible since no SM is needed for expanders) against the ORACLE."""
     model, sd = make_model(seed=12, bits=9, mode="MOL")
