@@ -38,7 +38,14 @@ using namespace tc;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NW = 16;                        // ingest / epilogue warps: warp w = (lane quadrant q = w & 3, column slice cs = w >> 2)
 constexpr int NT = (NW + 4) * 32;             // + a service warpgroup: the MMA warp and three idle warps (setmaxnreg works on whole warpgroups)
-constexpr int kRegsEpi = 104, kRegsSvc = 64;  // after the hand-over: 16 x 104 + 4 x 64 = 20 x 96, the launch allocation (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
+// 16 x 112 + 4 x 32 = 20 x 96, the launch allocation.  The chain warps take everything the MMA warp can spare: against 104 / 64 the
+// kernel's spills fall from 264 to 220 bytes (MOL instantiation) and the step by 0.5 % (MOL, 213 folds) to 1.5 % (RAW); 19 MOL folds
+// lose 0.5 % (profiles/r2_probes/ab_regs.txt).  -DWRNN_RS_REGS_EPI=104 -DWRNN_RS_REGS_SVC=64 restores the earlier split.
+#ifndef WRNN_RS_REGS_EPI
+#define WRNN_RS_REGS_EPI 112
+#define WRNN_RS_REGS_SVC 32
+#endif
+constexpr int kRegsEpi = WRNN_RS_REGS_EPI, kRegsSvc = WRNN_RS_REGS_SVC;  // (the SM's spare registers are NOT available to setmaxnreg.inc: measured, it blocks for ever)
 constexpr int kChunks = kRnn / 8;             // 64 chunks of 8 fp16 per activation row
 constexpr size_t kMatChunks = (size_t)kChunks * 128;     // one buffer of one exchange matrix: [chunk][fold] x 16 bytes = 128 KB
 enum { MH1 = 0, MH2, MS2, MF1, MF2, kMats };
