@@ -100,6 +100,8 @@ struct wrnn_engine {
     int fade_overlap = -1;
     cudaEvent_t ev[8] = {};
     cudaEvent_t evx[2] = {};     // brackets the per-sample conditioning expansion of a wave
+    cudaEvent_t evc[2] = {};     // brackets one trial of the role-specialised loop's layout calibration
+    std::map<int, std::pair<int, int>> rs_layout;     // (mode, samplers, fold bucket) -> (groups, grid padded): measured once per engine
 };
 
 namespace {
@@ -213,6 +215,7 @@ int wrnn_create(int device, int bits, int mode, wrnn_engine** out) {
     if (err == cudaSuccess) err = cudaHostGetDevicePointer(&e->dProgress, e->hProgress, 0);
     for (int i = 0; i < 8 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->ev[i]);
     for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->evx[i]);
+    for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaEventCreate(&e->evc[i]);
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))   // profilers slow the loop down: let them widen the guard
         if (err == cudaSuccess) err = set_spin_deadline((long long)(atof(dl) * 1.9e6));
     if (const char* dl = getenv("WRNN_SPIN_DEADLINE_MS"))
@@ -242,6 +245,7 @@ int wrnn_destroy(wrnn_engine* e) {
     if (e->hProgress) cudaFreeHost(e->hProgress);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->evx) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->evc) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return WRNN_OK;
@@ -1088,9 +1092,44 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             // inline conditioning (default; WRNN_RS_INLINE=0: records from expander CTAs): no per-sample records at all -- the aux share is
             // a per-frame row, the mel share one more K = 80 slab of the on-path MMAs -- so every SM can belong to a group
             const bool inl = e->wRsX[0].p && !(getenv("WRNN_RS_INLINE") && atoi(getenv("WRNN_RS_INLINE")) == 0);
-            int G = std::min(std::min(rs_groups_max, inl ? 3 : 2), std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, (B + 63) / 64));
-            G = std::max(G, (B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup);
-            if (const char* ev = getenv("WRNN_RS_GROUPS")) G = std::max((B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, std::min(rs_groups_max, atoi(ev)));
+            const int G_min = (B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, G_max = std::max(G_min, std::min(rs_groups_max, inl ? 3 : 2));
+            int G_def = std::max(G_min, std::min(G_max, (B + 63) / 64));
+            if (const char* ev = getenv("WRNN_RS_GROUPS")) G_def = std::max(G_min, std::min(rs_groups_max, atoi(ev)));
+            const int pad_def = (getenv("WRNN_RS_PAD") && atoi(getenv("WRNN_RS_PAD")) == 0) ? 0 : 1;
+            // Layout calibration.  Which SMs a group gets is the block scheduler's choice, it depends on the GPU and on the grid size, and
+            // the step time follows it: the same binary runs the 137-fold RAW step in 15.3 us or in 17.6 us.  So the first
+            // call of a shape on an engine times kRsCalSteps steps of up to four layouts -- the default group count and its neighbour,
+            // each with the grid padded to the SM count and not -- and the engine keeps the fastest.  The result does not depend on the
+            // layout (tests: bit-identical samples across groups and padding).  WRNN_RS_CALIBRATE=0: the default layout always.
+            constexpr int kRsCalSteps = 256;
+            struct RsLayout { int G, pad; };
+            std::vector<RsLayout> cands;
+            const bool can_cal = inl && S >= 8 * kRsCalSteps && !getenv("WRNN_RS_GROUPS") && !getenv("WRNN_RS_PAD") && !getenv("WRNN_RS_TRACE") &&
+                                 !getenv("WRNN_RS_DEBUG") && !getenv("WRNN_RS_PLACE") && !(getenv("WRNN_RS_CALIBRATE") && atoi(getenv("WRNN_RS_CALIBRATE")) == 0);
+            const int cal_key = (e->mode << 24) | (rs_samplers << 16) | ((B + 15) / 16);
+            RsLayout chosen{G_def, pad_def};
+            bool have_choice = !can_cal;
+            if (can_cal) {
+                auto it = e->rs_layout.find(cal_key);
+                if (it != e->rs_layout.end()) { chosen = RsLayout{it->second.first, it->second.second}; have_choice = true; }
+                else {
+                    const int G_alt = G_def + 1 <= G_max ? G_def + 1 : (G_def - 1 >= G_min ? G_def - 1 : G_def);
+                    for (int k = 0; k < (G_alt == G_def ? 1 : 2); ++k)
+                        for (int pad : {1, 0}) {
+                            const int g = k == 0 ? G_def : G_alt;
+                            if (pad == 0 && e->n_sms - g * rs_ctas < 8) continue;        // (padding a handful of CTAs changes nothing)
+                            cands.push_back(RsLayout{g, pad});
+                        }
+                    if (cands.size() < 2) have_choice = true;
+                }
+            }
+            const int n_cal = have_choice ? 0 : (int)cands.size();
+            float best_ms = 0.f;
+            for (int trial = 0; trial <= n_cal; ++trial) {
+            const bool cal = trial < n_cal;
+            const RsLayout lay = cal ? cands[trial] : chosen;
+            const int G = lay.G;
+            const int S_run = cal ? kRsCalSteps : S;
             const int Ng = (B + G - 1) / G;
             // Conditioning records (16 KB per fold and step) are produced INSIDE the loop kernel by expander CTAs on the SMs the
             // groups leave free, into a ring sized to stay resident in L2 (WRNN_RS_RING_MB, default 48 MB: three 4-step chunks at 213 folds): produced / consumed
@@ -1142,7 +1181,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 rp.inl = 1;
                 rp.wx1 = e->wRsX[0].as<unsigned char>(); rp.wx2 = e->wRsX[1].as<unsigned char>(); rp.wx3 = e->wRsX[2].as<unsigned char>();
                 rp.FR = e->bFR.as<float>(); rp.M16 = e->bM16.as<__half>(); rp.m16_zero = (long long)tq_rows * kHop;
-                rp.n_expanders = (getenv("WRNN_RS_PAD") && atoi(getenv("WRNN_RS_PAD")) == 0) ? 0 : std::max(0, n_exp);
+                rp.n_expanders = lay.pad ? std::max(0, n_exp) : 0;
             }
             if (ring) {
                 rp.cs_done = e->bCsDone.as<unsigned int>(); rp.cs_consumed = e->bCsDone.as<unsigned int>() + nchunks;
@@ -1155,16 +1194,16 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             rp.offpath_delay_ns = getenv("WRNN_RS_DELAY_NS") ? atoi(getenv("WRNN_RS_DELAY_NS")) : 2500;
             rp.canary_all = getenv("WRNN_RS_CANARY_ALL") ? atoi(getenv("WRNN_RS_CANARY_ALL")) : 0;
             rp.folds = e->bFolds.as<FoldDesc>() + w0;
-            rp.B = B; rp.S = S; rp.seed = rq->seed;
+            rp.B = B; rp.S = S_run; rp.seed = rq->seed;
             rp.X = e->bRsExch.as<uint4>();
             rp.bX = reinterpret_cast<unsigned long long*>(e->bRsExch.as<unsigned char>() + xbytes);
             rp.bP = rp.bX + (size_t)G * 128;
             rp.w5 = e->wRs[4].as<unsigned char>();
             rp.mode = e->mode; rp.C = e->C; rp.n_samplers = rs_samplers; rp.ctas = rs_ctas; rp.qcols = rs_samplers ? e->C / rs_samplers : 0;
             rp.samples = e->bSamples.as<float>() + (size_t)w0 * S;
-            rp.logits_out = rq->logits ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
+            rp.logits_out = (rq->logits && !cal) ? e->bLogits.as<float>() + (size_t)w0 * S * e->C : nullptr;
             rp.forced = rq->forced ? e->bForced.as<float>() + (size_t)w0 * S : nullptr;
-            rp.progress = e->dProgress;
+            rp.progress = cal ? nullptr : e->dProgress;
             rp.abort_flag = e->dAbort;
             int* hdbg = nullptr;
             if (getenv("WRNN_RS_DEBUG") && atoi(getenv("WRNN_RS_DEBUG"))) {     // checkpoints in mapped host memory: readable while the kernel hangs
@@ -1208,6 +1247,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 rp.place = e->bRsPlace.as<unsigned int>();
                 rp.rot = getenv("WRNN_RS_ROT") ? std::max(0, atoi(getenv("WRNN_RS_ROT"))) % grid : 0;
             }
+            if (cal) CU(cudaEventRecord(e->evc[0], st));
             CU(launch_loop_rs(rp, st));
             if (l2_window) {
                 cudaStreamAttrValue av;
@@ -1215,6 +1255,19 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 av.accessPolicyWindow.num_bytes = 0;
                 cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
                 cudaGetLastError();
+            }
+            if (cal) {        // one trial: its time, and -- after the last -- the layout this engine keeps for the shape
+                CU(cudaEventRecord(e->evc[1], st));
+                int ab = 0;
+                CU(cudaMemcpyAsync(&ab, e->dAbort, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (ab) return fail(e, WRNN_ERR_TIMEOUT, "sample loop deadlock guard fired (layout calibration)");
+                const float ms = elapsed(e->evc[0], e->evc[1]);
+                if (getenv("WRNN_VERBOSE")) fprintf(stderr, "[wrnn] rs layout trial: %d folds, %d groups, padded %d: %.2f us per step\n", B, lay.G, lay.pad, ms * 1e3 / kRsCalSteps);
+                if (trial == 0 || ms < 0.985f * best_ms) { best_ms = ms; chosen = lay; }      // (the default layout -- trial 0 -- unless another is clearly faster)
+                e->launches += 1;
+                if (trial == n_cal - 1) e->rs_layout[cal_key] = std::make_pair(chosen.G, chosen.pad);
+                continue;
             }
             rq->loop_kernel = WRNN_LOOP_RS;
             if (rs_trace) {
@@ -1251,6 +1304,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
                 cudaFreeHost(hdbg);
             }
             e->launches += 2;
+            }     // (layout trials, then the run)
         } else if (use_tc && e->mode == WRNN_MODE_MOL && e->wTc2.p && getenv("WRNN_TC_V2") && atoi(getenv("WRNN_TC_V2"))) {
             // (opt-in: measured equal to loop_tc.cu in round 1 -- 27.4 vs 26.6 us/step -- see DESIGN.md section 4.3)
             // ---- cluster-local tensor-core loop (MOL): folds partitioned over independent 16-CTA clusters -----------------

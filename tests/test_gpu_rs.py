@@ -144,6 +144,23 @@ def test_rs_loop_deterministic_and_groups_invisible(monkeypatch):
     monkeypatch.delenv("WRNN_RS_PAD")
 
 
+def test_rs_loop_layout_calibration_is_invisible(monkeypatch):
+    """The first long call of a shape on an engine times a few layouts (groups x grid padding) and keeps the fastest: the samples
+    are the same with the calibration (first call: trials + run; second call: the kept layout) and without it, RAW and MOL."""
+    for mode, seed in (("RAW", 11), ("MOL", 12)):
+        mel = norm_mel(300, 3)                                   # 60000 samples, 1500 + 2 x 300 -> 34 folds x 2100 steps
+        monkeypatch.setenv("WRNN_RS_CALIBRATE", "0")
+        ref_model, _ = make_model(seed=seed, bits=9, mode=mode)
+        a = ref_model.generate_debug(mel, True, 1500, 300, seed=4, precision=F16)
+        monkeypatch.delenv("WRNN_RS_CALIBRATE")
+        model, _ = make_model(seed=seed, bits=9, mode=mode)
+        b = model.generate_debug(mel, True, 1500, 300, seed=4, precision=F16)
+        c = model.generate_debug(mel, True, 1500, 300, seed=4, precision=F16)
+        assert a["samples"].shape[1] == 2100 and dict(model.last_timings)["loop_kernel"] == "wrnn_loop_rs_kernel"
+        np.testing.assert_array_equal(a["samples"], b["samples"])
+        np.testing.assert_array_equal(a["samples"], c["samples"])
+
+
 def test_rs_loop_record_ring_path(monkeypatch):
     """WRNN_RS_INLINE=0 keeps the round's first form of the loop -- conditioning records from expander CTAs through an L2-resident
     ring -- selectable: against the ORACLE on the 213-fold plan, and the same samples (a) run to run, (b) with the records expanded
