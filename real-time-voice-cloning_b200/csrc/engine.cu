@@ -1094,6 +1094,7 @@ int wrnn_generate(wrnn_engine* e, wrnn_request* rq) {
             const bool inl = e->wRsX[0].p && !(getenv("WRNN_RS_INLINE") && atoi(getenv("WRNN_RS_INLINE")) == 0);
             const int G_min = (B + kRsMaxFoldsPerGroup - 1) / kRsMaxFoldsPerGroup, G_max = std::max(G_min, std::min(rs_groups_max, inl ? 3 : 2));
             int G_def = std::max(G_min, std::min(G_max, (B + 63) / 64));
+            if (G_max >= 3 && B > 96) G_def = std::max(G_def, 3);      // measured (profiles/r2_probes/cal_trials_2gpu.txt): 106 folds 11.96 us in three groups, 12.44 in two; 68 folds 12.18 vs 11.99
             if (const char* ev = getenv("WRNN_RS_GROUPS")) G_def = std::max(G_min, std::min(rs_groups_max, atoi(ev)));
             const int pad_def = (getenv("WRNN_RS_PAD") && atoi(getenv("WRNN_RS_PAD")) == 0) ? 0 : 1;
             // Layout calibration.  Which SMs a group gets is the block scheduler's choice, it depends on the GPU and on the grid size, and
